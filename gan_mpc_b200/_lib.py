@@ -1,0 +1,287 @@
+"""ctypes binding of libgmpc.so (include/gmpc.h) -- the only way Python reaches the kernels.
+
+PyTorch is used for device memory and streams only: every call passes `tensor.data_ptr()` and
+`torch.cuda.current_stream().cuda_stream`.  There is no CPU fallback: a missing library or a
+non-zero status raises.
+"""
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgmpc.so")
+
+METHOD_GRAD, METHOD_ADAM = 0, 1
+PATH_AUTO, PATH_FFMA, PATH_TC = 0, 1, 2
+METHODS = {"grad": METHOD_GRAD, "adam": METHOD_ADAM}
+PATHS = {"auto": PATH_AUTO, "ffma": PATH_FFMA, "tc": PATH_TC}
+
+
+class GmpcError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in (
+        "n", "m", "T", "dyn_layers", "dyn_hidden", "cost_layers", "cost_hidden", "cost_fout",
+        "critic_features", "critic_layers", "critic_hidden", "device")]
+
+
+_f = C.c_void_p  # device/host float*
+_SIGS = {
+    "gmpc_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "gmpc_destroy": (C.c_int, [C.c_void_p]),
+    "gmpc_last_error": (C.c_char_p, []),
+    "gmpc_critic_param_count": (C.c_int64, [C.c_void_p]),
+    "gmpc_set_path": (C.c_int, [C.c_void_p, C.c_int]),
+    "gmpc_last_path": (C.c_int, [C.c_void_p]),
+    "gmpc_launch_count": (C.c_int64, [C.c_void_p]),
+    "gmpc_set_weights": (C.c_int, [C.c_void_p, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f),
+                                   C.POINTER(_f), _f, C.c_void_p]),
+    "gmpc_rollout": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.c_void_p]),
+    "gmpc_objective_grad": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, _f, _f, _f, _f,
+                                      C.c_void_p]),
+    "gmpc_l2_loss_grad": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, _f, _f, _f, C.c_void_p]),
+    "gmpc_plan": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_int32, C.c_int32,
+                            C.c_float, C.c_float, C.c_float, C.c_float, _f, _f, _f, _f, _f,
+                            C.c_void_p]),
+    "gmpc_plan_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_int32,
+                                 C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, _f, _f,
+                                 _f, _f, _f, C.c_void_p]),
+    "gmpc_critic_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_void_p]),
+    "gmpc_critic_loss_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_float,
+                                        _f, _f, C.c_void_p]),
+    "gmpc_critic_loss_grad_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, _f,
+                                               C.c_float, _f, _f, C.c_void_p]),
+    "gmpc_clip_adam_step": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, _f, C.c_int32, C.c_float,
+                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_void_p]),
+    "gmpc_l2_loss": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.c_void_p]),
+}
+EXPORTS = tuple(_SIGS)
+
+_lib = None
+
+
+def load():
+    """Load libgmpc.so (built in-tree by __graft_entry__.build()).  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GmpcError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise GmpcError(f"libgmpc status {rc}: {load().gmpc_last_error().decode()}")
+
+
+def _ptr(t, dtype=torch.float32, device=None, name="tensor"):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    if device is not None and t.device != device:
+        raise ValueError(f"{name}: expected device {device}, got {t.device}")
+    return t.data_ptr()
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Handle:
+    """One planner/critic instance bound to one GPU (include/gmpc.h gmpc_handle)."""
+
+    def __init__(self, n, m, T, dyn_layers, dyn_hidden, cost_layers, cost_hidden, cost_fout,
+                 critic_features=0, critic_layers=1, critic_hidden=1, device=0):
+        self.lib = load()
+        self.device = torch.device("cuda", int(device))
+        self.cfg = Config(n, m, T, dyn_layers, dyn_hidden, cost_layers, cost_hidden, cost_fout,
+                          critic_features, critic_layers, critic_hidden, int(device))
+        self._h = C.c_void_p()
+        _check(self.lib.gmpc_create(C.byref(self.cfg), C.byref(self._h)))
+        self.n, self.m, self.T = n, m, T
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.gmpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- configuration
+    def set_path(self, path):
+        _check(self.lib.gmpc_set_path(self._h, PATHS[path] if isinstance(path, str) else path))
+
+    @property
+    def last_path(self):
+        return {PATH_FFMA: "ffma", PATH_TC: "tc"}[self.lib.gmpc_last_path(self._h)]
+
+    @property
+    def launch_count(self):
+        return int(self.lib.gmpc_launch_count(self._h))
+
+    @property
+    def critic_param_count(self):
+        return int(self.lib.gmpc_critic_param_count(self._h))
+
+    def set_weights(self, dyn_W, dyn_b, cost_W, cost_b, mpc_weights):
+        dev = self.device
+        if len(dyn_W) != self.cfg.dyn_layers or len(cost_W) != self.cfg.cost_layers:
+            raise ValueError("set_weights: layer count does not match the handle's config")
+
+        def arr(ts, nm):
+            a = (_f * len(ts))()
+            for i, t in enumerate(ts):
+                a[i] = _ptr(t, device=dev, name=f"{nm}[{i}]")
+            return a
+
+        self._keep = (dyn_W, dyn_b, cost_W, cost_b, mpc_weights)
+        _check(self.lib.gmpc_set_weights(
+            self._h, arr(dyn_W, "dyn_W"), arr(dyn_b, "dyn_b"), arr(cost_W, "cost_W"),
+            arr(cost_b, "cost_b"), _ptr(mpc_weights, device=dev, name="mpc_weights"),
+            _stream(dev)))
+
+    # ---------------------------------------------------------------- planner
+    def rollout(self, x0, U):
+        B = x0.shape[0]
+        X = torch.empty(B, self.T + 1, self.n, device=self.device, dtype=torch.float32)
+        _check(self.lib.gmpc_rollout(self._h, B, _ptr(x0, device=self.device, name="x0"),
+                                     _ptr(U, device=self.device, name="U"), _ptr(X),
+                                     _stream(self.device)))
+        return X
+
+    def objective_grad(self, x0, U, goal, want_grad=True, want_X=True, want_lam=False):
+        B, dev = x0.shape[0], self.device
+        J = torch.empty(B, device=dev, dtype=torch.float32)
+        dU = torch.empty(B, self.T, self.m, device=dev, dtype=torch.float32) if want_grad else None
+        X = torch.empty(B, self.T + 1, self.n, device=dev, dtype=torch.float32) if want_X else None
+        lam = torch.empty(B, self.T + 1, self.n, device=dev, dtype=torch.float32) if want_lam else None
+        _check(self.lib.gmpc_objective_grad(
+            self._h, B, _ptr(x0, device=dev, name="x0"), _ptr(U, device=dev, name="U"),
+            _ptr(goal, device=dev, name="goal"), _ptr(J), _ptr(dU), _ptr(X), _ptr(lam),
+            _stream(dev)))
+        return J, dU, X, lam
+
+    def l2_loss_grad(self, x0, U, desired, want_grad=True, want_X=True):
+        B, dev = x0.shape[0], self.device
+        loss = torch.empty(B, device=dev, dtype=torch.float32)
+        dU = torch.empty(B, self.T, self.m, device=dev, dtype=torch.float32) if want_grad else None
+        X = torch.empty(B, self.T + 1, self.n, device=dev, dtype=torch.float32) if want_X else None
+        _check(self.lib.gmpc_l2_loss_grad(
+            self._h, B, _ptr(x0, device=dev, name="x0"), _ptr(U, device=dev, name="U"),
+            _ptr(desired, device=dev, name="desired"), _ptr(loss), _ptr(dU), _ptr(X),
+            _stream(dev)))
+        return loss, dU, X
+
+    def plan(self, x0, U0, goal, method="adam", iters=20, lr=1e-2, b1=0.9, b2=0.999, eps=1e-8,
+             want_J_all=True, out=None):
+        """x0 [B,n], U0 [B,K,T,m], goal [B,T+1,n] -> (U_best, X_best, J_best, idx, J_all)."""
+        dev = self.device
+        B, K = U0.shape[0], U0.shape[1]
+        if out is None:
+            out = self.alloc_plan_outputs(B, K, want_J_all)
+        U_best, X_best, J_best, idx, J_all = out
+        _check(self.lib.gmpc_plan(
+            self._h, B, K, _ptr(x0, device=dev, name="x0"), _ptr(U0, device=dev, name="U0"),
+            _ptr(goal, device=dev, name="goal"), METHODS[method], iters, lr, b1, b2, eps,
+            _ptr(U_best), _ptr(X_best), _ptr(J_best), _ptr(idx, dtype=torch.int32), _ptr(J_all),
+            _stream(dev)))
+        return out
+
+    def alloc_plan_outputs(self, B, K, want_J_all=True, device=None, pin=False):
+        dev = self.device if device is None else device
+        kw = dict(device=dev, pin_memory=pin) if pin else dict(device=dev)
+        return (torch.empty(B, self.T, self.m, dtype=torch.float32, **kw),
+                torch.empty(B, self.T + 1, self.n, dtype=torch.float32, **kw),
+                torch.empty(B, dtype=torch.float32, **kw),
+                torch.empty(B, dtype=torch.int32, **kw),
+                torch.empty(B, K, dtype=torch.float32, **kw) if want_J_all else None)
+
+    def plan_host(self, x0, U0, goal, method="adam", iters=20, lr=1e-2, b1=0.9, b2=0.999,
+                  eps=1e-8, out=None):
+        """Same as plan() with HOST (cpu, ideally pinned) tensors in and out; synchronous."""
+        B, K = U0.shape[0], U0.shape[1]
+        cpu = torch.device("cpu")
+        if out is None:
+            out = self.alloc_plan_outputs(B, K, True, device=cpu, pin=True)
+        U_best, X_best, J_best, idx, J_all = out
+        _check(self.lib.gmpc_plan_host(
+            self._h, B, K, _ptr(x0, device=cpu, name="x0"), _ptr(U0, device=cpu, name="U0"),
+            _ptr(goal, device=cpu, name="goal"), METHODS[method], iters, lr, b1, b2, eps,
+            _ptr(U_best, device=cpu), _ptr(X_best, device=cpu), _ptr(J_best, device=cpu),
+            _ptr(idx, dtype=torch.int32, device=cpu), _ptr(J_all, device=cpu),
+            _stream(self.device)))
+        return out
+
+    # ---------------------------------------------------------------- critic / losses
+    def critic_forward(self, xseq, params_flat):
+        Bc, T1 = xseq.shape[0], xseq.shape[1]
+        logit = torch.empty(Bc, device=self.device, dtype=torch.float32)
+        _check(self.lib.gmpc_critic_forward(
+            self._h, Bc, T1, _ptr(xseq, device=self.device, name="xseq"),
+            _ptr(params_flat, device=self.device, name="params_flat"), _ptr(logit),
+            _stream(self.device)))
+        return logit
+
+    def critic_loss_grad(self, xseq, label, params_flat, inv_count=None, want_grad=True,
+                         perm=None, batch=None):
+        """BCE loss (and flat gradient).  With `perm` (int32 [Bc]) xseq/label are the whole
+        dataset and the minibatch is gathered inside the kernel."""
+        dev = self.device
+        T1 = xseq.shape[1]
+        Bc = xseq.shape[0] if perm is None else perm.shape[0]
+        if inv_count is None:
+            inv_count = 1.0 / Bc
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        grad = torch.empty(self.critic_param_count, device=dev, dtype=torch.float32) if want_grad else None
+        if perm is None:
+            _check(self.lib.gmpc_critic_loss_grad(
+                self._h, Bc, T1, _ptr(xseq, device=dev, name="xseq"),
+                _ptr(label, device=dev, name="label"),
+                _ptr(params_flat, device=dev, name="params_flat"), inv_count, _ptr(loss),
+                _ptr(grad), _stream(dev)))
+        else:
+            _check(self.lib.gmpc_critic_loss_grad_gather(
+                self._h, Bc, T1, _ptr(xseq, device=dev, name="xseq"),
+                _ptr(label, device=dev, name="label"),
+                _ptr(perm, dtype=torch.int32, device=dev, name="perm"),
+                _ptr(params_flat, device=dev, name="params_flat"), inv_count, _ptr(loss),
+                _ptr(grad), _stream(dev)))
+        return loss, grad
+
+    def clip_adam_step(self, params_flat, grad_flat, mom, vel, step, lr, max_norm=100.0,
+                       grad_scale=1.0, b1=0.9, b2=0.999, eps=1e-8):
+        dev = self.device
+        _check(self.lib.gmpc_clip_adam_step(
+            self._h, params_flat.numel(), _ptr(params_flat, device=dev, name="params_flat"),
+            _ptr(grad_flat, device=dev, name="grad_flat"), _ptr(mom, device=dev, name="mom"),
+            _ptr(vel, device=dev, name="vel"), int(step), lr, max_norm, grad_scale, b1, b2, eps,
+            _stream(dev)))
+
+    def l2_loss(self, X, desired):
+        B = X.shape[0]
+        loss = torch.empty(B, device=self.device, dtype=torch.float32)
+        _check(self.lib.gmpc_l2_loss(self._h, B, _ptr(X, device=self.device, name="X"),
+                                     _ptr(desired, device=self.device, name="desired"),
+                                     _ptr(loss), _stream(self.device)))
+        return loss

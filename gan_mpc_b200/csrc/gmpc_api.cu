@@ -1,0 +1,582 @@
+// gmpc_api.cu -- C ABI of libgmpc.so (see include/gmpc.h).  Host-side handle, weight packing,
+// workspace management and kernel launches.  No torch types cross this boundary.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/gmpc.h"
+#include "common.cuh"
+#include "critic.cuh"
+#include "plan_ffma.cuh"
+#include "plan_tc.cuh"
+
+using namespace gmpc;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_CHECK(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(GMPC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+static inline int rup4(int v) { return (v + 3) & ~3; }
+
+struct MlpPack {
+  int L = 0;
+  int dims[MAXL + 1] = {0};
+  // device pointers into the handle's packed weight buffer
+  float* Wf[MAXL] = {nullptr};
+  float* Wb[MAXL] = {nullptr};
+  float* bias[MAXL] = {nullptr};
+  int ldf[MAXL] = {0}, ldb[MAXL] = {0};
+};
+
+struct gmpc_handle {
+  gmpc_config cfg;
+  int num_sms = 0;
+  int path = GMPC_PATH_AUTO;
+  int last_path = GMPC_PATH_FFMA;
+  int64_t launches = 0;
+  bool have_weights = false;
+  int maxt = 1;
+  int hpad = 4;
+  size_t smem_bytes = 0;
+  MlpPack dyn, cost;
+  float* d_wpack = nullptr;
+  float* d_mpcw = nullptr;
+  // FFMA per-CTA scratch
+  float *ws_X = nullptr, *ws_G = nullptr, *ws_U = nullptr, *ws_M = nullptr, *ws_V = nullptr;
+  uint32_t* ws_mask = nullptr;
+  // growable scratch for K>1 candidate outputs and host staging
+  void* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  // critic
+  CriticDims cd;
+  float* d_partial = nullptr;
+  float* d_losses = nullptr;
+  size_t losses_cap = 0;
+  int critic_grid = 0;
+  // tensor-core path state
+  TcState tc;
+};
+
+extern "C" const char* gmpc_last_error(void) { return g_err.c_str(); }
+
+static int grow(void** p, size_t* cap, size_t need) {
+  if (need <= *cap) return GMPC_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  CU_CHECK(cudaMalloc(p, need));
+  *cap = need;
+  return GMPC_OK;
+}
+
+static void fill_dims(MlpPack& mp, int in, int hidden, int out, int L) {
+  mp.L = L;
+  mp.dims[0] = in;
+  for (int l = 1; l < L; ++l) mp.dims[l] = hidden;
+  mp.dims[L] = out;
+}
+
+static size_t pack_floats(const MlpPack& mp) {
+  size_t tot = 0;
+  for (int l = 0; l < mp.L; ++l) {
+    tot += (size_t)rup4(mp.dims[l]) * rup4(mp.dims[l + 1]) * 2;  // forward + transposed
+    tot += rup4(mp.dims[l + 1]);                                  // bias
+  }
+  return tot;
+}
+
+static float* carve(MlpPack& mp, float* base) {
+  for (int l = 0; l < mp.L; ++l) {
+    const int Kp = rup4(mp.dims[l]), Np = rup4(mp.dims[l + 1]);
+    mp.ldf[l] = Np;
+    mp.ldb[l] = Kp;
+    mp.Wf[l] = base; base += (size_t)Kp * Np;
+    mp.Wb[l] = base; base += (size_t)Np * Kp;
+    mp.bias[l] = base; base += Np;
+  }
+  return base;
+}
+
+static void make_layer(LayerDesc& d, const float* W, const float* bias, int Ki_true, int No,
+                       int ld) {
+  d.W = W;
+  d.bias = bias;
+  d.Ki = rup4(Ki_true);
+  d.No = No;
+  d.ld = ld;
+  d.kc = std::max(4, (STAGE_FLOATS / ld) & ~3);
+  d.nchunks = (d.Ki + d.kc - 1) / d.kc;
+  d.pad_ = 0;
+}
+
+static void make_dirs(const MlpPack& mp, DirDesc& fwd, DirDesc& bwd) {
+  fwd.L = bwd.L = mp.L;
+  fwd.pad_ = bwd.pad_ = 0;
+  for (int l = 0; l < mp.L; ++l) {
+    make_layer(fwd.layer[l], mp.Wf[l], mp.bias[l], mp.dims[l], mp.dims[l + 1], mp.ldf[l]);
+    const int lt = mp.L - 1 - l;  // backward pass visits transposed layers L-1 .. 0
+    make_layer(bwd.layer[l], mp.Wb[lt], nullptr, mp.dims[lt + 1], mp.dims[lt], mp.ldb[lt]);
+  }
+}
+
+static size_t ffma_smem_bytes(const gmpc_config& c, int hpad) {
+  const int n4 = rup4(c.n), nm4 = rup4(c.n + c.m), f4 = rup4(c.cost_fout);
+  return sizeof(float) *
+         ((size_t)2 * hpad * RT + (size_t)NSTAGE * STAGE_FLOATS + (size_t)(2 * nm4 + n4 + f4 + c.n) * RT);
+}
+
+static void critic_dims(const gmpc_config& c, CriticDims& d) {
+  memset(&d, 0, sizeof(d));
+  d.n = c.n; d.F = c.critic_features; d.L = c.critic_layers; d.H = c.critic_hidden;
+  long long o = 0;
+  d.oWi = o; o += (long long)d.n * 4 * d.F;
+  d.oWh = o; o += (long long)d.F * 4 * d.F;
+  d.obh = o; o += 4 * d.F;
+  int din = d.F;
+  for (int l = 0; l < d.L - 1; ++l) {
+    d.din[l] = din;
+    d.oDk[l] = o; o += (long long)din * d.H;
+    d.oDb[l] = o; o += d.H;
+    din = d.H;
+  }
+  d.dlast = din;
+  d.oWo = o; o += din;
+  d.obo = o; o += 1;
+  d.P = o;
+}
+
+extern "C" int gmpc_create(const gmpc_config* cfg, gmpc_handle** out) {
+  if (!cfg || !out) return fail(GMPC_E_ARG, "gmpc_create: null argument");
+  const gmpc_config& c = *cfg;
+  if (c.n < 1 || c.m < 1 || c.T < 1) return fail(GMPC_E_ARG, "gmpc_create: n, m, T must be >= 1");
+  if (c.dyn_layers < 1 || c.dyn_layers > MAXL || c.cost_layers < 1 || c.cost_layers > MAXL)
+    return fail(GMPC_E_UNSUPPORTED, "gmpc_create: num_layers must be in [1, 8]");
+  if (c.dyn_hidden < 1 || c.cost_hidden < 1 || c.cost_fout < 1)
+    return fail(GMPC_E_ARG, "gmpc_create: hidden/fout must be >= 1");
+  const int hmax = std::max(c.dyn_layers > 1 ? c.dyn_hidden : 1, c.cost_layers > 1 ? c.cost_hidden : 1);
+  if (hmax > 512 || c.n + c.m > 256 || c.cost_fout > 256)
+    return fail(GMPC_E_UNSUPPORTED,
+                "gmpc_create: supported widths are hidden <= 512, n+m <= 256, fout <= 256");
+  if (c.critic_features < 0 || 4 * c.critic_features > 1024 || c.critic_hidden > 1024 ||
+      (c.critic_features > 0 && (c.critic_layers < 1 || c.critic_layers > MAXL)))
+    return fail(GMPC_E_UNSUPPORTED, "gmpc_create: critic needs features <= 256, hidden <= 1024, layers in [1, 8]");
+  CU_CHECK(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CU_CHECK(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major != 10)
+    return fail(GMPC_E_UNSUPPORTED, "gmpc_create: libgmpc is built for sm_100a (B200) only");
+
+  gmpc_handle* h = new gmpc_handle();
+  h->cfg = c;
+  h->num_sms = prop.multiProcessorCount;
+  h->maxt = hmax <= 256 ? 1 : 2;
+  h->hpad = std::max(4, rup4(hmax));
+  h->smem_bytes = ffma_smem_bytes(c, h->hpad);
+  if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+    delete h;
+    return fail(GMPC_E_UNSUPPORTED, "gmpc_create: shape needs more shared memory than one SM has");
+  }
+  fill_dims(h->dyn, c.n + c.m, c.dyn_hidden, c.n, c.dyn_layers);
+  fill_dims(h->cost, c.n, c.cost_hidden, c.cost_fout, c.cost_layers);
+  const size_t wfl = pack_floats(h->dyn) + pack_floats(h->cost);
+  cudaError_t e = cudaMalloc(&h->d_wpack, wfl * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(h->d_wpack, 0, wfl * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_mpcw, 4 * sizeof(float));
+  carve(h->cost, carve(h->dyn, h->d_wpack));
+  // per-CTA scratch for a persistent grid of one CTA per SM
+  const size_t G = h->num_sms;
+  const size_t sx = (size_t)(c.T + 1) * c.n * RT, su = (size_t)c.T * c.m * RT;
+  const size_t smk = ((size_t)c.T * (c.dyn_layers - 1) + (c.cost_layers - 1)) * 2 * NTHREADS + 1;
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws_X, G * sx * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws_G, G * sx * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws_U, G * su * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws_M, G * su * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws_V, G * su * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws_mask, G * smk * sizeof(uint32_t));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(plan_ffma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)prop.sharedMemPerBlockOptin);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(plan_ffma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)prop.sharedMemPerBlockOptin);
+  if (e == cudaSuccess && c.critic_features > 0) {
+    critic_dims(c, h->cd);
+    h->critic_grid = 2 * h->num_sms;
+    e = cudaMalloc(&h->d_partial, (size_t)h->critic_grid * h->cd.P * sizeof(float));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)prop.sharedMemPerBlockOptin);
+  }
+  if (e != cudaSuccess) {
+    gmpc_destroy(h);
+    return fail(GMPC_E_CUDA, std::string("gmpc_create: ") + cudaGetErrorString(e));
+  }
+  int rc = tc_create(h->tc, c, h->dyn.dims, h->cost.dims, prop);
+  if (rc != GMPC_OK) {
+    std::string msg = g_err;
+    gmpc_destroy(h);
+    return fail(rc, msg);
+  }
+  *out = h;
+  return GMPC_OK;
+}
+
+extern "C" int gmpc_destroy(gmpc_handle* h) {
+  if (!h) return GMPC_OK;
+  cudaSetDevice(h->cfg.device);
+  tc_destroy(h->tc);
+  cudaFree(h->d_wpack); cudaFree(h->d_mpcw);
+  cudaFree(h->ws_X); cudaFree(h->ws_G); cudaFree(h->ws_U); cudaFree(h->ws_M); cudaFree(h->ws_V);
+  cudaFree(h->ws_mask); cudaFree(h->d_scratch); cudaFree(h->d_stage);
+  cudaFree(h->d_partial); cudaFree(h->d_losses);
+  delete h;
+  return GMPC_OK;
+}
+
+extern "C" int64_t gmpc_critic_param_count(const gmpc_handle* h) {
+  return (h && h->cfg.critic_features > 0) ? h->cd.P : 0;
+}
+
+extern "C" int gmpc_set_path(gmpc_handle* h, int path) {
+  if (!h || path < GMPC_PATH_AUTO || path > GMPC_PATH_TC) return fail(GMPC_E_ARG, "gmpc_set_path: bad argument");
+  if (path == GMPC_PATH_TC && !h->tc.supported)
+    return fail(GMPC_E_UNSUPPORTED, std::string("gmpc_set_path: tensor-core path unsupported for this shape: ") + h->tc.why);
+  h->path = path;
+  return GMPC_OK;
+}
+extern "C" int gmpc_last_path(const gmpc_handle* h) { return h ? h->last_path : GMPC_E_ARG; }
+extern "C" int64_t gmpc_launch_count(const gmpc_handle* h) { return h ? h->launches : 0; }
+
+static int pack_mlp(gmpc_handle* h, MlpPack& mp, const float* const* W, const float* const* b,
+                    cudaStream_t st) {
+  for (int l = 0; l < mp.L; ++l) {
+    if (!W[l] || !b[l]) return fail(GMPC_E_ARG, "gmpc_set_weights: null layer pointer");
+    const int K = mp.dims[l], N = mp.dims[l + 1];
+    pack_layer_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(W[l], K, N, mp.Wf[l], mp.ldf[l],
+                                                            mp.Wb[l], mp.ldb[l]);
+    ++h->launches;
+    CU_CHECK(cudaMemcpyAsync(mp.bias[l], b[l], sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+  }
+  return GMPC_OK;
+}
+
+extern "C" int gmpc_set_weights(gmpc_handle* h, const float* const* dyn_W,
+                                const float* const* dyn_b, const float* const* cost_W,
+                                const float* const* cost_b, const float* mpc_weights,
+                                void* stream) {
+  if (!h || !dyn_W || !dyn_b || !cost_W || !cost_b || !mpc_weights)
+    return fail(GMPC_E_ARG, "gmpc_set_weights: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU_CHECK(cudaSetDevice(h->cfg.device));
+  int rc = pack_mlp(h, h->dyn, dyn_W, dyn_b, st);
+  if (rc) return rc;
+  rc = pack_mlp(h, h->cost, cost_W, cost_b, st);
+  if (rc) return rc;
+  CU_CHECK(cudaMemcpyAsync(h->d_mpcw, mpc_weights, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  rc = tc_set_weights(h->tc, dyn_W, dyn_b, cost_W, cost_b, st, &h->launches);
+  if (rc) return rc;
+  CU_CHECK(cudaGetLastError());
+  h->have_weights = true;
+  return GMPC_OK;
+}
+
+// Fill the parts of PlanParams shared by every mode and launch the FFMA kernel.
+static int launch_ffma(gmpc_handle* h, PlanParams& P, cudaStream_t st) {
+  const gmpc_config& c = h->cfg;
+  make_dirs(h->dyn, P.dir[DIR_DYN_F], P.dir[DIR_DYN_B]);
+  make_dirs(h->cost, P.dir[DIR_COST_F], P.dir[DIR_COST_B]);
+  P.n = c.n; P.m = c.m; P.T = c.T;
+  P.hpad = h->hpad;
+  P.fout = c.cost_fout;
+  P.mpcw = h->d_mpcw;
+  P.ws_X = h->ws_X; P.ws_G = h->ws_G; P.ws_U = h->ws_U; P.ws_M = h->ws_M; P.ws_V = h->ws_V;
+  P.ws_mask = h->ws_mask;
+  P.ntiles = (int)((P.NQ + RT - 1) / RT);
+  const int grid = std::min(P.ntiles, h->num_sms);
+  if (grid <= 0) return GMPC_OK;
+  if (h->maxt == 1)
+    plan_ffma_kernel<1><<<grid, NTHREADS, h->smem_bytes, st>>>(P);
+  else
+    plan_ffma_kernel<2><<<grid, NTHREADS, h->smem_bytes, st>>>(P);
+  ++h->launches;
+  CU_CHECK(cudaGetLastError());
+  h->last_path = GMPC_PATH_FFMA;
+  return GMPC_OK;
+}
+
+static int check_ready(gmpc_handle* h, const char* who, int64_t B) {
+  if (!h) return fail(GMPC_E_ARG, std::string(who) + ": null handle");
+  if (!h->have_weights) return fail(GMPC_E_STATE, std::string(who) + ": call gmpc_set_weights first");
+  if (B < 0 || B > (int64_t)1 << 40) return fail(GMPC_E_ARG, std::string(who) + ": bad batch size");
+  cudaError_t e = cudaSetDevice(h->cfg.device);
+  if (e != cudaSuccess) return fail(GMPC_E_CUDA, cudaGetErrorString(e));
+  return GMPC_OK;
+}
+
+static bool use_tc(gmpc_handle* h, int64_t NQ) {
+  if (h->path == GMPC_PATH_FFMA) return false;
+  if (h->path == GMPC_PATH_TC) return true;
+  return h->tc.supported && tc_worthwhile(h->tc, NQ);
+}
+
+extern "C" int gmpc_rollout(gmpc_handle* h, int64_t B, const float* x0, const float* U, float* X,
+                            void* stream) {
+  int rc = check_ready(h, "gmpc_rollout", B);
+  if (rc) return rc;
+  if (B == 0) return GMPC_OK;
+  if (!x0 || !U || !X) return fail(GMPC_E_ARG, "gmpc_rollout: null argument");
+  PlanParams P;
+  memset(&P, 0, sizeof(P));
+  P.mode = MODE_ROLLOUT; P.iters = 0; P.use_cost = 0; P.final_fwd = 1;
+  P.K = 1; P.NQ = B;
+  P.x0 = x0; P.U_in = U; P.goal = nullptr; P.X_out = X;
+  return launch_ffma(h, P, (cudaStream_t)stream);
+}
+
+extern "C" int gmpc_objective_grad(gmpc_handle* h, int64_t B, const float* x0, const float* U,
+                                   const float* goal, float* J, float* dU, float* X, float* lam,
+                                   void* stream) {
+  int rc = check_ready(h, "gmpc_objective_grad", B);
+  if (rc) return rc;
+  if (B == 0) return GMPC_OK;
+  if (!x0 || !U || !goal) return fail(GMPC_E_ARG, "gmpc_objective_grad: null argument");
+  PlanParams P;
+  memset(&P, 0, sizeof(P));
+  P.mode = MODE_OBJGRAD; P.use_cost = 1;
+  const bool need_bwd = (dU != nullptr) || (lam != nullptr);
+  P.iters = need_bwd ? 1 : 0;
+  P.final_fwd = need_bwd ? 0 : 1;
+  P.K = 1; P.NQ = B;
+  P.x0 = x0; P.U_in = U; P.goal = goal;
+  P.J_out = J; P.dU_out = dU; P.X_out = X; P.lam_out = lam;
+  return launch_ffma(h, P, (cudaStream_t)stream);
+}
+
+extern "C" int gmpc_l2_loss_grad(gmpc_handle* h, int64_t B, const float* x0, const float* U,
+                                 const float* desired, float* loss, float* dU, float* X,
+                                 void* stream) {
+  int rc = check_ready(h, "gmpc_l2_loss_grad", B);
+  if (rc) return rc;
+  if (B == 0) return GMPC_OK;
+  if (!x0 || !U || !desired) return fail(GMPC_E_ARG, "gmpc_l2_loss_grad: null argument");
+  PlanParams P;
+  memset(&P, 0, sizeof(P));
+  P.mode = MODE_L2GRAD; P.use_cost = 0; P.iters = 1; P.final_fwd = 0;
+  P.K = 1; P.NQ = B;
+  P.x0 = x0; P.U_in = U; P.goal = desired;
+  P.J_out = loss; P.dU_out = dU; P.X_out = X;
+  return launch_ffma(h, P, (cudaStream_t)stream);
+}
+
+extern "C" int gmpc_plan(gmpc_handle* h, int64_t B, int32_t K, const float* x0, const float* U0,
+                         const float* goal, int32_t method, int32_t N, float lr, float b1,
+                         float b2, float eps, float* U_best, float* X_best, float* J_best,
+                         int32_t* idx_best, float* J_all, void* stream) {
+  int rc = check_ready(h, "gmpc_plan", B);
+  if (rc) return rc;
+  if (K < 1 || N < 0 || (method != GMPC_METHOD_GRAD && method != GMPC_METHOD_ADAM))
+    return fail(GMPC_E_ARG, "gmpc_plan: need K >= 1, N >= 0, method in {GRAD, ADAM}");
+  if (B == 0) return GMPC_OK;
+  if (!x0 || !U0 || !goal || !U_best || !X_best || !J_best || !idx_best)
+    return fail(GMPC_E_ARG, "gmpc_plan: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const gmpc_config& c = h->cfg;
+  const int64_t NQ = B * K;
+  const size_t ub = (size_t)c.T * c.m, xb = (size_t)(c.T + 1) * c.n;
+  float *U_out = U_best, *X_out = X_best, *J_out = J_best;
+  if (K > 1) {
+    const size_t need = sizeof(float) * ((size_t)NQ * (ub + xb + 1));
+    rc = grow(&h->d_scratch, &h->scratch_bytes, need);
+    if (rc) return rc;
+    U_out = (float*)h->d_scratch;
+    X_out = U_out + (size_t)NQ * ub;
+    J_out = J_all ? J_all : X_out + (size_t)NQ * xb;
+  }
+  if (use_tc(h, NQ)) {
+    rc = tc_plan(h->tc, NQ, K, x0, U0, goal, h->d_mpcw, method, N, lr, b1, b2, eps, U_out, X_out,
+                 J_out, st, &h->launches);
+    if (rc) return rc;
+    h->last_path = GMPC_PATH_TC;
+  } else {
+    PlanParams P;
+    memset(&P, 0, sizeof(P));
+    P.mode = MODE_PLAN; P.method = method; P.iters = N; P.use_cost = 1; P.final_fwd = 1;
+    P.K = K; P.NQ = NQ;
+    P.lr = lr; P.b1 = b1; P.b2 = b2; P.eps = eps;
+    P.x0 = x0; P.U_in = U0; P.goal = goal;
+    P.U_out = U_out; P.X_out = X_out; P.J_out = J_out;
+    rc = launch_ffma(h, P, st);
+    if (rc) return rc;
+  }
+  if (K > 1) {
+    const int grid = (int)std::min<int64_t>(B, 8 * h->num_sms);
+    select_best_kernel<<<grid, 128, 0, st>>>(B, K, c.T, c.n, c.m, J_out, U_out, X_out, U_best,
+                                             X_best, J_best, idx_best);
+    ++h->launches;
+  } else {
+    CU_CHECK(cudaMemsetAsync(idx_best, 0, sizeof(int32_t) * B, st));
+    if (J_all) CU_CHECK(cudaMemcpyAsync(J_all, J_best, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+  }
+  CU_CHECK(cudaGetLastError());
+  return GMPC_OK;
+}
+
+extern "C" int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float* x0_host,
+                              const float* U0_host, const float* goal_host, int32_t method,
+                              int32_t N, float lr, float b1, float b2, float eps,
+                              float* U_best_host, float* X_best_host, float* J_best_host,
+                              int32_t* idx_best_host, float* J_all_host, void* stream) {
+  int rc = check_ready(h, "gmpc_plan_host", B);
+  if (rc) return rc;
+  if (B == 0) return GMPC_OK;
+  if (K < 1) return fail(GMPC_E_ARG, "gmpc_plan_host: K must be >= 1");
+  if (!x0_host || !U0_host || !goal_host || !U_best_host || !X_best_host || !J_best_host ||
+      !idx_best_host)
+    return fail(GMPC_E_ARG, "gmpc_plan_host: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const gmpc_config& c = h->cfg;
+  const size_t ub = (size_t)c.T * c.m, xb = (size_t)(c.T + 1) * c.n;
+  const size_t f_x0 = (size_t)B * c.n, f_U0 = (size_t)B * K * ub, f_goal = (size_t)B * xb;
+  const size_t f_Ub = (size_t)B * ub, f_Xb = (size_t)B * xb, f_Jb = B, f_idx = B, f_Ja = (size_t)B * K;
+  const size_t tot = f_x0 + f_U0 + f_goal + f_Ub + f_Xb + f_Jb + f_idx + f_Ja;
+  rc = grow(&h->d_stage, &h->stage_bytes, tot * sizeof(float));
+  if (rc) return rc;
+  float* d_x0 = (float*)h->d_stage;
+  float* d_U0 = d_x0 + f_x0;
+  float* d_goal = d_U0 + f_U0;
+  float* d_Ub = d_goal + f_goal;
+  float* d_Xb = d_Ub + f_Ub;
+  float* d_Jb = d_Xb + f_Xb;
+  int32_t* d_idx = (int32_t*)(d_Jb + f_Jb);
+  float* d_Ja = (float*)(d_idx + f_idx);
+  CU_CHECK(cudaMemcpyAsync(d_x0, x0_host, f_x0 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_CHECK(cudaMemcpyAsync(d_U0, U0_host, f_U0 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_CHECK(cudaMemcpyAsync(d_goal, goal_host, f_goal * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = gmpc_plan(h, B, K, d_x0, d_U0, d_goal, method, N, lr, b1, b2, eps, d_Ub, d_Xb, d_Jb, d_idx,
+                 J_all_host ? d_Ja : nullptr, st);
+  if (rc) return rc;
+  CU_CHECK(cudaMemcpyAsync(U_best_host, d_Ub, f_Ub * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaMemcpyAsync(X_best_host, d_Xb, f_Xb * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaMemcpyAsync(J_best_host, d_Jb, f_Jb * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaMemcpyAsync(idx_best_host, d_idx, f_idx * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (J_all_host)
+    CU_CHECK(cudaMemcpyAsync(J_all_host, d_Ja, f_Ja * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaStreamSynchronize(st));
+  return GMPC_OK;
+}
+
+// ----------------------------------------------------------------------------------- critic
+static size_t critic_smem(const CriticDims& d, int T1) {
+  const int G = 4 * d.F, W = std::max(d.F, d.H);
+  return sizeof(float) * ((size_t)T1 * d.n + (size_t)T1 * G + (size_t)2 * (T1 + 1) * d.F + 2 * d.F +
+                          (size_t)d.L * W + 2 * W + 4);
+}
+
+static int critic_launch(gmpc_handle* h, const char* who, int64_t Bc, int32_t T1,
+                         const float* xseq, const float* label, const int32_t* perm,
+                         const float* params, float inv_count, float* loss, float* grad,
+                         float* logits, cudaStream_t st) {
+  if (!h) return fail(GMPC_E_ARG, std::string(who) + ": null handle");
+  if (h->cfg.critic_features <= 0) return fail(GMPC_E_STATE, std::string(who) + ": handle was created without a critic");
+  if (Bc < 0 || T1 < 1) return fail(GMPC_E_ARG, std::string(who) + ": need Bc >= 0, T1 >= 1");
+  if (Bc == 0) return GMPC_OK;
+  if (!xseq || !params || (!label && (loss || grad)))
+    return fail(GMPC_E_ARG, std::string(who) + ": null argument");
+  CU_CHECK(cudaSetDevice(h->cfg.device));
+  CriticDims d = h->cd;
+  d.T1 = T1;
+  const size_t smem = critic_smem(d, T1);
+  if (smem > 227 * 1024) return fail(GMPC_E_UNSUPPORTED, std::string(who) + ": sequence too long for one SM's shared memory");
+  if ((size_t)Bc > h->losses_cap) {
+    if (h->d_losses) cudaFree(h->d_losses);
+    h->d_losses = nullptr; h->losses_cap = 0;
+    CU_CHECK(cudaMalloc(&h->d_losses, sizeof(float) * (size_t)Bc * 2));
+    h->losses_cap = (size_t)Bc;
+  }
+  const int threads = std::max(64, ((std::max(4 * d.F, d.H) + 31) / 32) * 32);
+  const int grid = (int)std::min<int64_t>(Bc, h->critic_grid);
+  // labels are unused when only logits are requested: feed the losses buffer as a dummy
+  const float* lab = label ? label : h->d_losses + h->losses_cap;
+  if (!label) CU_CHECK(cudaMemsetAsync(h->d_losses + h->losses_cap, 0, sizeof(float) * (size_t)Bc, st));
+  critic_kernel<<<grid, threads, smem, st>>>(d, xseq, lab, perm, params, inv_count, Bc,
+                                             h->d_losses, logits, h->d_partial, grad ? 1 : 0);
+  ++h->launches;
+  if (loss || grad) {
+    const int rb = grad ? (int)((d.P + 255) / 256) : 1;
+    critic_reduce_kernel<<<rb, 256, 0, st>>>(h->d_partial, grid, d.P, grad, h->d_losses, Bc,
+                                             inv_count, loss);
+    ++h->launches;
+  }
+  CU_CHECK(cudaGetLastError());
+  return GMPC_OK;
+}
+
+extern "C" int gmpc_critic_forward(gmpc_handle* h, int64_t Bc, int32_t T1, const float* xseq,
+                                   const float* params_flat, float* logit, void* stream) {
+  if (!logit) return fail(GMPC_E_ARG, "gmpc_critic_forward: null argument");
+  return critic_launch(h, "gmpc_critic_forward", Bc, T1, xseq, nullptr, nullptr, params_flat, 0.f,
+                       nullptr, nullptr, logit, (cudaStream_t)stream);
+}
+
+extern "C" int gmpc_critic_loss_grad(gmpc_handle* h, int64_t Bc, int32_t T1, const float* xseq,
+                                     const float* label, const float* params_flat,
+                                     float inv_count, float* loss, float* grad_flat, void* stream) {
+  if (!loss) return fail(GMPC_E_ARG, "gmpc_critic_loss_grad: null loss pointer");
+  return critic_launch(h, "gmpc_critic_loss_grad", Bc, T1, xseq, label, nullptr, params_flat,
+                       inv_count, loss, grad_flat, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int gmpc_critic_loss_grad_gather(gmpc_handle* h, int64_t Bc, int32_t T1,
+                                            const float* data_xseq, const float* data_label,
+                                            const int32_t* perm, const float* params_flat,
+                                            float inv_count, float* loss, float* grad_flat,
+                                            void* stream) {
+  if (!loss || !perm) return fail(GMPC_E_ARG, "gmpc_critic_loss_grad_gather: null argument");
+  return critic_launch(h, "gmpc_critic_loss_grad_gather", Bc, T1, data_xseq, data_label, perm,
+                       params_flat, inv_count, loss, grad_flat, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int gmpc_clip_adam_step(gmpc_handle* h, int64_t P, float* params_flat,
+                                   const float* grad_flat, float* mom, float* vel, int32_t step,
+                                   float lr, float max_norm, float grad_scale, float b1, float b2,
+                                   float eps, void* stream) {
+  if (!h || !params_flat || !grad_flat || !mom || !vel || P < 0 || step < 1)
+    return fail(GMPC_E_ARG, "gmpc_clip_adam_step: bad argument");
+  if (P == 0) return GMPC_OK;
+  CU_CHECK(cudaSetDevice(h->cfg.device));
+  clip_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(P, params_flat, grad_flat, mom, vel, step,
+                                                         lr, max_norm, grad_scale, b1, b2, eps);
+  ++h->launches;
+  CU_CHECK(cudaGetLastError());
+  return GMPC_OK;
+}
+
+extern "C" int gmpc_l2_loss(gmpc_handle* h, int64_t B, const float* X, const float* desired,
+                            float* loss, void* stream) {
+  if (!h || !X || !desired || !loss || B < 0) return fail(GMPC_E_ARG, "gmpc_l2_loss: bad argument");
+  if (B == 0) return GMPC_OK;
+  CU_CHECK(cudaSetDevice(h->cfg.device));
+  const int wpb = 4;
+  l2_loss_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      B, h->cfg.T + 1, h->cfg.n, X, desired, loss);
+  ++h->launches;
+  CU_CHECK(cudaGetLastError());
+  return GMPC_OK;
+}

@@ -1,0 +1,165 @@
+/* gmpc.h -- C ABI of libgmpc.so: the B200-native gan_mpc planning hot path.
+ *
+ * This is the drop-in boundary.  The reference (returaj/gan_mpc) has no FFI; its boundary for
+ * this path is the Python API of gan_mpc.policy.optimizers + the policy classes.  Each entry
+ * point below cites the reference interface it replaces (paths relative to the reference root).
+ * The Python mirror of that API (gan_mpc_b200/policy/..., gan/..., norm/...) binds these with
+ * ctypes; see INTEGRATION.md for the stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - every call returns int: 0 ok, <0 error (GMPC_E_*); message via gmpc_last_error().
+ *  - all array arguments are DEVICE pointers to fp32 row-major data unless the name ends in
+ *    _host or the comment says otherwise.  The caller owns every buffer.  The library keeps no
+ *    pointer past the call (weights are copied/packed into the handle by gmpc_set_weights).
+ *  - work is enqueued on the caller's stream (a cudaStream_t passed as void*) and is
+ *    asynchronous; no hidden host sync except in the *_host convenience entry points.
+ *  - a handle is bound to one device and is not thread-safe (one handle per stream/GPU).
+ *  - weights use the flax layout kernel[in, out] (y = x @ kernel + bias), as stored in the
+ *    reference's params pytree ({"params": {"Dense_i": {"kernel", "bias"}}}).
+ */
+#ifndef GMPC_H_
+#define GMPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMPC_OK 0
+#define GMPC_E_ARG (-1)         /* bad argument / null pointer */
+#define GMPC_E_UNSUPPORTED (-2) /* shape outside what the kernels support */
+#define GMPC_E_CUDA (-3)        /* CUDA runtime error */
+#define GMPC_E_STATE (-4)       /* call order (e.g. plan before set_weights) */
+
+#define GMPC_METHOD_GRAD 0 /* U <- U - lr g */
+#define GMPC_METHOD_ADAM 1 /* optax adam(lr, b1, b2, eps), per-trajectory state */
+
+#define GMPC_MAX_LAYERS 8
+
+/* kernel family used for the MLP contractions */
+#define GMPC_PATH_AUTO 0 /* tcgen05 when the tile is a real dense contraction, else FFMA */
+#define GMPC_PATH_FFMA 1 /* fp32 CUDA-core path (exact fp32 FMA arithmetic) */
+#define GMPC_PATH_TC 2   /* tcgen05 3xTF32 tensor-core path (error if shape unsupported) */
+
+typedef struct gmpc_config {
+  int32_t n;             /* state size x_size                       (dynamics/nn.py:13 x_out) */
+  int32_t m;             /* action size u_size */
+  int32_t T;             /* MPC horizon            (config mpc.horizon, cost/cost_model.py:35) */
+  int32_t dyn_layers;    /* dynamics MLP num_layers L: L-1 hidden Dense+ReLU, then Dense(n) */
+  int32_t dyn_hidden;    /* dynamics MLP num_hidden_units */
+  int32_t cost_layers;   /* cost MLP num_layers                          (cost/nn.py:11-13) */
+  int32_t cost_hidden;   /* cost MLP num_hidden_units */
+  int32_t cost_fout;     /* cost MLP fout */
+  int32_t critic_features; /* critic LSTM features F (0 = no critic)    (critic/nn.py:11-14) */
+  int32_t critic_layers;   /* critic num_layers (num_layers-1 hidden Dense, then Dense(1)) */
+  int32_t critic_hidden;   /* critic num_hidden_units */
+  int32_t device;        /* CUDA device ordinal */
+} gmpc_config;
+
+typedef struct gmpc_handle gmpc_handle;
+
+/* Create/destroy.  Replaces constructing EvalMPC/BaseMPC (policy/eval.py:26-39) for the
+ * structured DynamicsModel(MLP) + MujocoBasedModel(cost MLP) (+ CriticModel(LSTM)) case. */
+int gmpc_create(const gmpc_config* cfg, gmpc_handle** out);
+int gmpc_destroy(gmpc_handle* h);
+
+/* Thread-local message for the last non-zero return. */
+const char* gmpc_last_error(void);
+
+/* Number of floats of the flat critic parameter vector for this handle's config
+ * (layout: Wi[n,4F] | Wh[F,4F] | bh[4F] | {Dk[in,H], Db[H]}* | Wo[in,1] | bo[1]; gates i,f,g,o). */
+int64_t gmpc_critic_param_count(const gmpc_handle* h);
+
+/* Select the contraction path (GMPC_PATH_*).  Default AUTO. */
+int gmpc_set_path(gmpc_handle* h, int path);
+/* Which path the last plan/objective call actually used (GMPC_PATH_FFMA or GMPC_PATH_TC). */
+int gmpc_last_path(const gmpc_handle* h);
+
+/* Stage model weights (copied and re-packed inside the handle; safe to free after return of
+ * the stream work).  dyn_W[l] is kernel[in_l, out_l], dyn_b[l] is bias[out_l]; l < dyn_layers.
+ * mpc_weights is the raw (pre-sigmoid) [action, state, terminal] vector, DEVICE pointer.
+ * Replaces reading params["dynamics_params"|"cost_params"|"mpc_weights"]
+ * (policy/eval.py:64-73). */
+int gmpc_set_weights(gmpc_handle* h, const float* const* dyn_W, const float* const* dyn_b,
+                     const float* const* cost_W, const float* const* cost_b,
+                     const float* mpc_weights, void* stream);
+
+/* trajax rollout as used at policy/optimizers.py:28,80:  X[b,0]=x0[b]; X[b,t+1]=dyn(X[b,t],U[b,t]).
+ * x0[B,n], U[B,T,m] -> X[B,T+1,n]. */
+int gmpc_rollout(gmpc_handle* h, int64_t B, const float* x0, const float* U, float* X,
+                 void* stream);
+
+/* objective (policy/optimizers.py:24-31) and its action gradient (jax.grad at :83,:103; trajax
+ * ilqr's `gradient`/`adjoints` outputs consumed at :55).
+ * x0[B,n], U[B,T,m], goal[B,T+1,n] -> J[B], dU[B,T,m] (nullable), X[B,T+1,n] (nullable),
+ * lam[B,T+1,n] (nullable adjoints). */
+int gmpc_objective_grad(gmpc_handle* h, int64_t B, const float* x0, const float* U,
+                        const float* goal, float* J, float* dU, float* X, float* lam,
+                        void* stream);
+
+/* loss_grad_wrt_control (policy/optimizers.py:78-83) for loss = L2MPC.loss
+ * (norm/l2_policy.py:12-18): x0[B,n], U[B,T,m], desired[B,T+1,n] -> loss[B], dU[B,T,m] (nullable),
+ * X[B,T+1,n] (nullable). */
+int gmpc_l2_loss_grad(gmpc_handle* h, int64_t B, const float* x0, const float* U,
+                      const float* desired, float* loss, float* dU, float* X, void* stream);
+
+/* The fused planner: replaces ilqr_solve (policy/optimizers.py:10-21) /
+ * EvalMPC.get_optimal_values (policy/eval.py:109-124) with the north-star first-order planner
+ * on the reference's exact objective.  For every start state b and candidate k: N iterations of
+ * {rollout, cost, adjoint, update}, final evaluation, then idx = argmin_k J (first minimum).
+ * x0[B,n], U0[B,K,T,m], goal[B,T+1,n] ->
+ * U_best[B,T,m], X_best[B,T+1,n], J_best[B], idx_best[B] (int32), J_all[B,K] (nullable). */
+int gmpc_plan(gmpc_handle* h, int64_t B, int32_t K, const float* x0, const float* U0,
+              const float* goal, int32_t method, int32_t N, float lr, float b1, float b2,
+              float eps, float* U_best, float* X_best, float* J_best, int32_t* idx_best,
+              float* J_all, void* stream);
+
+/* Same as gmpc_plan but every array argument is a HOST pointer (pinned or pageable): copies
+ * inputs host->device, plans, copies results back and synchronises `stream` before returning.
+ * This is the end-to-end call a non-GPU-aware reference caller would bind. */
+int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float* x0_host,
+                   const float* U0_host, const float* goal_host, int32_t method, int32_t N,
+                   float lr, float b1, float b2, float eps, float* U_best_host,
+                   float* X_best_host, float* J_best_host, int32_t* idx_best_host,
+                   float* J_all_host, void* stream);
+
+/* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
+int64_t gmpc_launch_count(const gmpc_handle* h);
+
+/* CriticModel.predict (critic/critic_model.py:15-16, critic/nn.py:27-42):
+ * xseq[Bc,T1,n], params_flat -> logit[Bc].  T1 = number of rows (T+1 in the reference). */
+int gmpc_critic_forward(gmpc_handle* h, int64_t Bc, int32_t T1, const float* xseq,
+                        const float* params_flat, float* logit, void* stream);
+
+/* JS_MPC.critic_loss_and_grad (gan/js_policy.py:41-58): BCE with +-1 labels (label > 0 test),
+ * batch mean, gradient w.r.t. the flat critic params.  `inv_count` scales loss and gradient
+ * (1/Bc on one GPU; 1/global_batch when the gradient is all-reduced across ranks afterwards).
+ * xseq[Bc,T1,n], label[Bc] -> loss[1], grad_flat[P]. */
+int gmpc_critic_loss_grad(gmpc_handle* h, int64_t Bc, int32_t T1, const float* xseq,
+                          const float* label, const float* params_flat, float inv_count,
+                          float* loss, float* grad_flat, void* stream);
+
+/* Same with a gather fused in front (gan/critic_trainer.py:55-56, X[p], Y[p]):
+ * sample i of the minibatch is data_xseq[perm[i]], data_label[perm[i]] (perm int32, device). */
+int gmpc_critic_loss_grad_gather(gmpc_handle* h, int64_t Bc, int32_t T1, const float* data_xseq,
+                                 const float* data_label, const int32_t* perm,
+                                 const float* params_flat, float inv_count, float* loss,
+                                 float* grad_flat, void* stream);
+
+/* optax.chain(clip_by_global_norm(max_norm), adam(lr)) + apply_updates on a flat vector
+ * (norm/runner.py:46-58, gan/critic_trainer.py:58-59).  `step` is the 1-based update count.
+ * grad_flat is scaled by grad_scale first (1.0, or 1/world after a sum all-reduce).
+ * In place on params_flat[P], mom[P], vel[P]. */
+int gmpc_clip_adam_step(gmpc_handle* h, int64_t P, float* params_flat, const float* grad_flat,
+                        float* mom, float* vel, int32_t step, float lr, float max_norm,
+                        float grad_scale, float b1, float b2, float eps, void* stream);
+
+/* L2MPC.loss (norm/l2_policy.py:12-18): X[B,T+1,n], desired[B,T+1,n] -> loss[B]. */
+int gmpc_l2_loss(gmpc_handle* h, int64_t B, const float* X, const float* desired, float* loss,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMPC_H_ */

@@ -1,0 +1,193 @@
+"""GPU parity: CUDA planner path (through the C ABI) vs the fp64 CPU oracle on identical seeded
+inputs.  Tolerance (BASELINE.json north_star): 1e-4 relative, trajectory-norm-wise, for rollout
+states, action gradients and final plan cost; selection indices bit-exact."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import planner as oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+PATHS = ["ffma"]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("cfg,B", [(util.SMALL, 1), (util.SMALL, 33), (util.MID, 70),
+                                   (util.ODD, 45), (util.WIDE, 40)])
+def test_rollout_and_objective_grad(cfg, B, path, built_lib):
+    p, x0, U0, goal = util.case(cfg, 21, B=B)
+    h = util.make_handle(cfg, p)
+    h.set_path(path)
+    op = util.to_oracle(p)
+    oX, oJ, odU, olam = oracle.objective_grad(util.tt(x0), util.tt(U0[:, 0]), util.tt(goal), op)
+    U = dev(U0[:, 0])
+    X = h.rollout(dev(x0), U)
+    assert util.rel_rows(X, oX) < TOL
+    J, dU, X2, lam = h.objective_grad(dev(x0), U, dev(goal), want_lam=True)
+    assert util.rel_rows(X2, oX) < TOL
+    assert util.rel_rows(J[:, None], oJ[:, None]) < TOL
+    assert util.rel_rows(dU, odU) < TOL
+    assert util.rel_rows(lam, olam) < TOL
+    J_only, none_dU, _, _ = h.objective_grad(dev(x0), U, dev(goal), want_grad=False, want_X=False)
+    assert none_dU is None and util.rel_rows(J_only[:, None], oJ[:, None]) < TOL
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("method", ["grad", "adam"])
+@pytest.mark.parametrize("cfg,B,K,iters", [(util.SMALL, 37, 1, 8), (util.SMALL, 19, 4, 6),
+                                           (util.MID, 50, 2, 5), (util.ODD, 9, 3, 7)])
+def test_plan_matches_oracle(cfg, B, K, iters, method, path, built_lib):
+    p, x0, U0, goal = util.case(cfg, 31, B=B, K=K)
+    h = util.make_handle(cfg, p)
+    h.set_path(path)
+    oU, oX, oJ, oidx, oJall = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal),
+                                          util.to_oracle(p), method, iters, 1e-2)
+    Ub, Xb, Jb, idx, Jall = h.plan(dev(x0), dev(U0), dev(goal), method=method, iters=iters, lr=1e-2)
+    assert util.rel_rows(Jall, oJall) < TOL
+    # selection is exact wherever the oracle's top-2 gap exceeds rounding noise
+    if K > 1:
+        top2 = torch.sort(oJall, dim=1).values[:, :2]
+        clear = ((top2[:, 1] - top2[:, 0]) / top2[:, 0].abs().clamp_min(1e-30)) > 1e-3
+        print("near-tie states:", int((~clear).sum()), "of", B)
+    else:
+        clear = torch.ones(B, dtype=torch.bool)
+    assert torch.equal(idx.cpu()[clear], oidx[clear])
+    same = idx.cpu() == oidx
+    assert util.rel_rows(Ub[same.cuda()], oU[same]) < TOL
+    assert util.rel_rows(Xb[same.cuda()], oX[same]) < TOL
+    assert util.rel_rows(Jb[:, None], oJ[:, None]) < TOL
+    assert h.last_path == path
+
+
+def test_plan_c2_dims_full_horizon(built_lib):
+    """C2 dims (n=17, m=6, T=32, N=20) at a batch the oracle finishes in seconds; the fp32 noise
+    floor (oracle32 vs oracle64) is printed beside the kernel error."""
+    cfg = dict(util.MID, T=32)
+    p, x0, U0, goal = util.case(cfg, 0, B=96, bias_scale=0.0)
+    h = util.make_handle(cfg, p)
+    o64 = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), util.to_oracle(p), "adam", 20, 1e-2)
+    f = torch.float32
+    o32 = oracle.plan(util.tt(x0, f), util.tt(U0, f), util.tt(goal, f), util.to_oracle(p, f), "adam", 20, 1e-2)
+    Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=20, lr=1e-2)
+    for name, k, o, f32 in (("U", Ub, o64[0], o32[0]), ("X", Xb, o64[1], o32[1]),
+                            ("J", Jb[:, None], o64[2][:, None], o32[2][:, None])):
+        print(f"{name}: kernel-vs-oracle64 {util.rel_rows(k, o):.3e}   fp32 floor {util.rel_rows(f32, o):.3e}")
+        assert util.rel_rows(k, o) < TOL
+    assert torch.equal(idx.cpu(), o64[3])
+
+
+def test_plan_zero_iterations_is_evaluation(built_lib):
+    cfg = util.SMALL
+    p, x0, U0, goal = util.case(cfg, 8, B=10, K=2)
+    h = util.make_handle(cfg, p)
+    Ub, Xb, Jb, idx, Jall = h.plan(dev(x0), dev(U0), dev(goal), iters=0)
+    ar = torch.arange(10)
+    assert torch.equal(Ub.cpu(), torch.from_numpy(U0)[ar, idx.cpu().long()])   # bit-exact gather
+    assert torch.equal(Jb.cpu(), Jall.cpu().min(1).values)
+    assert torch.equal(idx.cpu().long(), Jall.cpu().argmin(1))
+
+
+def test_argmin_first_minimum_on_ties(built_lib):
+    """identical candidates -> identical fp32 costs -> idx must be 0 (jnp.argmin semantics)."""
+    cfg = util.SMALL
+    p, x0, U0, goal = util.case(cfg, 9, B=12, K=1)
+    U0 = np.repeat(U0, 5, axis=1)
+    h = util.make_handle(cfg, p)
+    _, _, _, idx, Jall = h.plan(dev(x0), dev(U0), dev(goal), iters=3)
+    assert (Jall.cpu() == Jall.cpu()[:, :1]).all()
+    assert (idx.cpu() == 0).all()
+
+
+def test_empty_and_ragged_batches(built_lib):
+    cfg = util.SMALL
+    p, x0, U0, goal = util.case(cfg, 10, B=65)
+    h = util.make_handle(cfg, p)
+    full = h.plan(dev(x0), dev(U0), dev(goal), iters=2)
+    for B in (0, 1, 31, 32, 33, 64):
+        out = h.plan(dev(x0[:B]), dev(U0[:B]), dev(goal[:B]), iters=2)
+        for a, b in zip(out, full):
+            assert torch.equal(a.cpu(), b.cpu()[:B])       # rows are independent: bit-exact
+
+
+def test_batch_rows_independent_of_neighbours(built_lib):
+    """Shard-invariance: a state's plan does not depend on which tile/position it lands in."""
+    cfg = util.MID
+    p, x0, U0, goal = util.case(cfg, 12, B=100)
+    h = util.make_handle(cfg, p)
+    full = h.plan(dev(x0), dev(U0), dev(goal), iters=3)
+    perm = np.random.default_rng(0).permutation(100)
+    shuf = h.plan(dev(x0[perm]), dev(U0[perm]), dev(goal[perm]), iters=3)
+    for a, b in zip(shuf, full):
+        assert torch.equal(a.cpu(), b.cpu()[perm])
+
+
+def test_plan_host_equals_device_path(built_lib):
+    cfg = util.SMALL
+    p, x0, U0, goal = util.case(cfg, 13, B=40, K=2)
+    h = util.make_handle(cfg, p)
+    d = h.plan(dev(x0), dev(U0), dev(goal), iters=4)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hst = h.plan_host(pin(x0), pin(U0), pin(goal), iters=4)
+    for a, b in zip(hst, d):
+        assert torch.equal(a, b.cpu())
+
+
+def test_l2_loss_and_grad(built_lib):
+    cfg = util.ODD
+    p, x0, U0, goal = util.case(cfg, 14, B=50)
+    h = util.make_handle(cfg, p)
+    op = util.to_oracle(p)
+    tx0, tU, tdes = util.tt(x0), util.tt(U0[:, 0]), util.tt(goal)
+    oX = oracle.rollout(tx0, tU, op)
+    loss, dU, X = h.l2_loss_grad(dev(x0), dev(U0[:, 0]), dev(goal))
+    assert util.rel_rows(X, oX) < TOL
+    assert util.rel_rows(loss[:, None], oracle.l2_loss(oX, tdes)[:, None]) < TOL
+    assert util.rel_rows(dU, oracle.loss_grad_wrt_control_l2(tx0, tU, tdes, op)) < TOL
+    assert util.rel_rows(h.l2_loss(X, dev(goal))[:, None], oracle.l2_loss(oX, tdes)[:, None]) < TOL
+
+
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_golden_vectors(name, built_lib):
+    z = np.load(os.path.join(GOLDEN, f"planner_{name}.npz"))
+    cfg = {k: int(z[k]) for k in ("n", "m", "T", "dyn_layers", "dyn_hidden", "cost_layers",
+                                  "cost_hidden", "cost_fout")}
+    L, Lc = cfg["dyn_layers"], cfg["cost_layers"]
+    p = dict(dyn_W=[z[f"dyn_W{i}"] for i in range(L)], dyn_b=[z[f"dyn_b{i}"] for i in range(L)],
+             cost_W=[z[f"cost_W{i}"] for i in range(Lc)], cost_b=[z[f"cost_b{i}"] for i in range(Lc)],
+             mpc_weights=z["mpc_weights"])
+    h = util.make_handle(cfg, p)
+    J, dU, X, lam = h.objective_grad(dev(z["x0"]), dev(z["U0"][:, 0]), dev(z["goal"]), want_lam=True)
+    assert util.rel_rows(X, util.tt(z["X"])) < TOL
+    assert util.rel_rows(dU, util.tt(z["dU"])) < TOL
+    assert util.rel_rows(lam, util.tt(z["lam"])) < TOL
+    assert util.rel_rows(J[:, None], util.tt(z["J"])[:, None]) < TOL
+    for method in ("grad", "adam"):
+        Ub, Xb, Jb, idx, Jall = h.plan(dev(z["x0"]), dev(z["U0"]), dev(z["goal"]), method=method,
+                                       iters=int(z["iters"]), lr=float(z["lr"]))
+        assert np.array_equal(idx.cpu().numpy(), z[f"{method}_idx"])
+        assert util.rel_rows(Ub, util.tt(z[f"{method}_U_best"])) < TOL
+        assert util.rel_rows(Jall, util.tt(z[f"{method}_J_all"])) < TOL
+
+
+def test_errors_are_loud(built_lib):
+    from gan_mpc_b200 import _lib
+    cfg = util.SMALL
+    p, x0, U0, goal = util.case(cfg, 1, B=4)
+    h = _lib.Handle(cfg["n"], cfg["m"], cfg["T"], cfg["dyn_layers"], cfg["dyn_hidden"],
+                    cfg["cost_layers"], cfg["cost_hidden"], cfg["cost_fout"])
+    with pytest.raises(_lib.GmpcError, match="set_weights first"):
+        h.plan(dev(x0), dev(U0), dev(goal))
+    with pytest.raises(ValueError):
+        util.make_handle(cfg, p).plan(torch.from_numpy(x0), dev(U0), dev(goal))   # CPU tensor
+    with pytest.raises(TypeError):
+        util.make_handle(cfg, p).plan(dev(x0).double(), dev(U0), dev(goal))
