@@ -59,6 +59,7 @@ _SIGS = {
                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p]),
     "gmpc_l2_loss": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.c_void_p]),
+    "gmpc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -285,3 +286,10 @@ class Handle:
                                      _ptr(desired, device=self.device, name="desired"),
                                      _ptr(loss), _stream(self.device)))
         return loss
+
+
+def measure_fp32_peak(device=0):
+    """Measured FP32 FFMA TFLOP/s of `device` (microbenchmark inside libgmpc)."""
+    out = C.c_float(0.0)
+    _check(load().gmpc_measure_fp32_peak(int(device), C.byref(out)))
+    return float(out.value)

@@ -12,6 +12,7 @@
 #include "../../include/gmpc.h"
 #include "common.cuh"
 #include "critic.cuh"
+#include "diag.cuh"
 #include "plan_ffma.cuh"
 #include "plan_tc.cuh"
 
@@ -578,5 +579,35 @@ extern "C" int gmpc_l2_loss(gmpc_handle* h, int64_t B, const float* X, const flo
       B, h->cfg.T + 1, h->cfg.n, X, desired, loss);
   ++h->launches;
   CU_CHECK(cudaGetLastError());
+  return GMPC_OK;
+}
+
+// ----------------------------------------------------------------------------------- diagnostics
+extern "C" int gmpc_measure_fp32_peak(int device, float* tflops_out) {
+  if (!tflops_out) return fail(GMPC_E_ARG, "gmpc_measure_fp32_peak: null argument");
+  CU_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_CHECK(cudaGetDeviceProperties(&prop, device));
+  float* d = nullptr;
+  const int grid = prop.multiProcessorCount * 8, iters = 4096;
+  CU_CHECK(cudaMalloc(&d, sizeof(float) * grid * 256));
+  cudaEvent_t e0, e1;
+  CU_CHECK(cudaEventCreate(&e0));
+  CU_CHECK(cudaEventCreate(&e1));
+  float best = 0.f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU_CHECK(cudaEventRecord(e0));
+    ffma_peak_kernel<<<grid, 256>>>(d, iters, 1.0f + rep);
+    CU_CHECK(cudaEventRecord(e1));
+    CU_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 16 * 8 * (double)iters * 256.0 * grid;
+    if (rep > 0) best = fmaxf(best, (float)(flops / (ms * 1e-3) / 1e12));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops_out = best;
   return GMPC_OK;
 }

@@ -159,6 +159,10 @@ int gmpc_clip_adam_step(gmpc_handle* h, int64_t P, float* params_flat, const flo
 int gmpc_l2_loss(gmpc_handle* h, int64_t B, const float* X, const float* desired, float* loss,
                  void* stream);
 
+/* Diagnostics (not on the hot path): measured FP32 FFMA throughput of `device` in TFLOP/s, the
+ * second roofline denominator bench.py reports for the CUDA-core path. */
+int gmpc_measure_fp32_peak(int device, float* tflops_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,20 +69,46 @@ def test_plan_matches_oracle(cfg, B, K, iters, method, path, built_lib):
     assert h.last_path == path
 
 
-def test_plan_c2_dims_full_horizon(built_lib):
-    """C2 dims (n=17, m=6, T=32, N=20) at a batch the oracle finishes in seconds; the fp32 noise
-    floor (oracle32 vs oracle64) is printed beside the kernel error."""
+def rel_each(a, b):
+    a = a.double().cpu().reshape(a.shape[0], -1)
+    b = b.double().cpu().reshape(b.shape[0], -1)
+    return (a - b).norm(dim=1) / (b.norm(dim=1) + 1e-30)
+
+
+@pytest.mark.parametrize("method", ["grad", "adam"])
+def test_plan_c2_dims_full_horizon(method, built_lib):
+    """C2 dims (n=17, m=6, T=32, N=20) at a batch the oracle finishes in seconds.
+
+    The fp32 noise floor (oracle32 vs oracle64) is measured beside the kernel error.  Adam's
+    first steps are -lr*g/(|g|+eps): an action whose gradient is ~eps flips by +-lr under ANY
+    fp32 rounding, so for Adam a few trajectories have an fp32 floor above 1e-4 themselves.  The
+    bar: final plan cost J within 1e-4 on every row; U and X within 1e-4 on every row whose own
+    fp32 floor is below 2e-5 (all rows for `grad`); the ill-conditioned rows are counted and
+    printed, never silently tolerated."""
     cfg = dict(util.MID, T=32)
     p, x0, U0, goal = util.case(cfg, 0, B=96, bias_scale=0.0)
     h = util.make_handle(cfg, p)
-    o64 = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), util.to_oracle(p), "adam", 20, 1e-2)
+    # random-init residual dynamics amplify |x| to ~1e4 over 32 steps (|dJ/dU| ~ 1e6), so plain
+    # gradient descent needs a correspondingly small step; Adam's steps are scale-free.
+    lr = 1e-2 if method == "adam" else 1e-9
+    o64 = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), util.to_oracle(p), method, 20, lr)
     f = torch.float32
-    o32 = oracle.plan(util.tt(x0, f), util.tt(U0, f), util.tt(goal, f), util.to_oracle(p, f), "adam", 20, 1e-2)
-    Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=20, lr=1e-2)
-    for name, k, o, f32 in (("U", Ub, o64[0], o32[0]), ("X", Xb, o64[1], o32[1]),
-                            ("J", Jb[:, None], o64[2][:, None], o32[2][:, None])):
-        print(f"{name}: kernel-vs-oracle64 {util.rel_rows(k, o):.3e}   fp32 floor {util.rel_rows(f32, o):.3e}")
-        assert util.rel_rows(k, o) < TOL
+    o32 = oracle.plan(util.tt(x0, f), util.tt(U0, f), util.tt(goal, f), util.to_oracle(p, f), method, 20, lr)
+    Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method=method, iters=20, lr=lr)
+    floor = torch.maximum(rel_each(o32[0], o64[0]), rel_each(o32[1], o64[1]))
+    well = floor < 2e-5
+    print(f"{method}: rows with fp32 floor >= 2e-5: {int((~well).sum())} of {len(well)}; "
+          f"max floor {float(floor.max()):.3e}")
+    for name, k, o in (("U", Ub, o64[0]), ("X", Xb, o64[1])):
+        e = rel_each(k, o)
+        print(f"{name}: kernel-vs-oracle64 max {float(e.max()):.3e}, on well-conditioned rows {float(e[well].max()):.3e}")
+        assert float(e[well].max()) < TOL
+    eJ = rel_each(Jb[:, None], o64[2][:, None])
+    print(f"J: kernel-vs-oracle64 max {float(eJ.max()):.3e}")
+    assert float(eJ.max()) < TOL
+    assert int((~well).sum()) <= len(well) // 10
+    if method == "grad":
+        assert bool(well.all())
     assert torch.equal(idx.cpu(), o64[3])
 
 
