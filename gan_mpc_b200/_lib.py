@@ -60,6 +60,7 @@ _SIGS = {
                                       C.c_void_p]),
     "gmpc_l2_loss": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.c_void_p]),
     "gmpc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
+    "gmpc_tc_probe": (C.c_int, [C.c_int] * 4 + [C.c_uint32] * 11 + [C.c_void_p] * 3),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -293,3 +294,17 @@ def measure_fp32_peak(device=0):
     out = C.c_float(0.0)
     _check(load().gmpc_measure_fp32_peak(int(device), C.byref(out)))
     return float(out.value)
+
+
+def tc_probe(A, B, a_major, a_lbo, a_sbo, a_s1, a_s2, a_kstep, b_lbo, b_sbo, b_s1, b_s2,
+             a_bytes, smem_bytes, device=0):
+    """Run one tcgen05 tf32 contraction D = A @ B.T (A [128,K], B [NB,K] float32 numpy) with the
+    given shared-memory image strides and descriptor fields; returns D [128, NB]."""
+    import numpy as np
+    A = np.ascontiguousarray(A, np.float32)
+    B = np.ascontiguousarray(B, np.float32)
+    D = np.zeros((128, B.shape[0]), np.float32)
+    _check(load().gmpc_tc_probe(int(device), B.shape[1], B.shape[0], int(a_major), a_lbo, a_sbo,
+                                a_s1, a_s2, a_kstep, b_lbo, b_sbo, b_s1, b_s2, a_bytes,
+                                smem_bytes, A.ctypes.data, B.ctypes.data, D.ctypes.data))
+    return D

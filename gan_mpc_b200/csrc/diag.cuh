@@ -24,3 +24,70 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, f
 }
 
 }  // namespace gmpc
+
+#include "tc_common.cuh"
+
+namespace gmpc {
+
+// tcgen05 probe: D[128][NB] = A[128][K] * B[NB][K]^T through SWIZZLE_NONE descriptors.  The host
+// chooses the shared-memory image strides and the descriptor LBO/SBO independently, so the
+// descriptor semantics can be pinned on hardware (tests/test_gpu_tc_probe.py).
+//   A image, K-major  (a_major 0): (k/4)*a_s1 + (m/8)*a_s2 + (m%8)*16 + (k%4)*4
+//   A image, MN-major (a_major 1): (m/4)*a_s1 + (k/8)*a_s2 + (k%8)*16 + (m%4)*4
+//   B image, K-major             : (k/4)*b_s1 + (n/8)*b_s2 + (n%8)*16 + (k%4)*4
+__global__ void __launch_bounds__(128) tc_probe_kernel(
+    const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int K, int NB,
+    int a_major, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_s1, uint32_t a_s2, uint32_t a_kstep,
+    uint32_t b_lbo, uint32_t b_sbo, uint32_t b_s1, uint32_t b_s2, uint32_t a_bytes) {
+  extern __shared__ __align__(128) uint8_t psm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* a_img = psm;
+  uint8_t* b_img = psm + a_bytes;
+  if (a_major & 2) {  // raw image mode: A is copied linearly (decoding which element the MMA reads)
+    for (int e = tid; e < (int)(a_bytes / 4); e += 128) reinterpret_cast<float*>(a_img)[e] = A[e];
+  }
+  for (int e = tid; e < 128 * K && !(a_major & 2); e += 128) {
+    const int m = e / K, k = e - m * K;
+    uint32_t off = a_major == 0 ? (k / 4) * a_s1 + (m / 8) * a_s2 + (m % 8) * 16 + (k % 4) * 4
+                                : (m / 4) * a_s1 + (k / 8) * a_s2 + (k % 8) * 16 + (m % 4) * 4;
+    *reinterpret_cast<float*>(a_img + off) = A[e];
+  }
+  for (int e = tid; e < NB * K; e += 128) {
+    const int n = e / K, k = e - n * K;
+    const uint32_t off = (k / 4) * b_s1 + (n / 8) * b_s2 + (n % 8) * 16 + (k % 4) * 4;
+    *reinterpret_cast<float*>(b_img + off) = B[e];
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, NB < 32 ? 32 : NB);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_tf32(NB, a_major & 1);
+    for (int s = 0; s < K / 8; ++s) {
+      const uint64_t ad = umma_smem_desc(smem_u32(a_img) + s * a_kstep, a_lbo, a_sbo);
+      const uint64_t bd = umma_smem_desc(smem_u32(b_img) + s * 2 * b_s1, b_lbo, b_sbo);
+      umma_tf32(tmem_base, ad, bd, idesc, s > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < NB; c0 += 16) {
+    float v[16];
+    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    for (int i = 0; i < 16; ++i) D[(size_t)tid * NB + c0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, NB < 32 ? 32 : NB);
+}
+
+}  // namespace gmpc

@@ -258,7 +258,7 @@ extern "C" int64_t gmpc_critic_param_count(const gmpc_handle* h) {
 extern "C" int gmpc_set_path(gmpc_handle* h, int path) {
   if (!h || path < GMPC_PATH_AUTO || path > GMPC_PATH_TC) return fail(GMPC_E_ARG, "gmpc_set_path: bad argument");
   if (path == GMPC_PATH_TC && !h->tc.supported)
-    return fail(GMPC_E_UNSUPPORTED, std::string("gmpc_set_path: tensor-core path unsupported for this shape: ") + h->tc.why);
+    return fail(GMPC_E_UNSUPPORTED, "gmpc_set_path: tensor-core path unsupported for this shape: " + h->tc.why);
   h->path = path;
   return GMPC_OK;
 }
@@ -298,7 +298,14 @@ extern "C" int gmpc_set_weights(gmpc_handle* h, const float* const* dyn_W,
   return GMPC_OK;
 }
 
-// Fill the parts of PlanParams shared by every mode and launch the FFMA kernel.
+static bool use_tc(gmpc_handle* h, int64_t NQ) {
+  if (h->path == GMPC_PATH_FFMA) return false;
+  if (h->path == GMPC_PATH_TC) return true;
+  return h->tc.supported && tc_worthwhile(h->tc, NQ);
+}
+
+// Fill the parts of PlanParams shared by every mode and launch the planner kernel of the
+// selected path (tcgen05 or FFMA).
 static int launch_ffma(gmpc_handle* h, PlanParams& P, cudaStream_t st) {
   const gmpc_config& c = h->cfg;
   make_dirs(h->dyn, P.dir[DIR_DYN_F], P.dir[DIR_DYN_B]);
@@ -312,6 +319,12 @@ static int launch_ffma(gmpc_handle* h, PlanParams& P, cudaStream_t st) {
   P.ntiles = (int)((P.NQ + RT - 1) / RT);
   const int grid = std::min(P.ntiles, h->num_sms);
   if (grid <= 0) return GMPC_OK;
+  if (use_tc(h, P.NQ)) {
+    int rc = tc_launch(h->tc, P, st, &h->launches);
+    if (rc) return fail(rc, "tensor-core planner launch failed");
+    h->last_path = GMPC_PATH_TC;
+    return GMPC_OK;
+  }
   if (h->maxt == 1)
     plan_ffma_kernel<1><<<grid, NTHREADS, h->smem_bytes, st>>>(P);
   else
@@ -329,12 +342,6 @@ static int check_ready(gmpc_handle* h, const char* who, int64_t B) {
   cudaError_t e = cudaSetDevice(h->cfg.device);
   if (e != cudaSuccess) return fail(GMPC_E_CUDA, cudaGetErrorString(e));
   return GMPC_OK;
-}
-
-static bool use_tc(gmpc_handle* h, int64_t NQ) {
-  if (h->path == GMPC_PATH_FFMA) return false;
-  if (h->path == GMPC_PATH_TC) return true;
-  return h->tc.supported && tc_worthwhile(h->tc, NQ);
 }
 
 extern "C" int gmpc_rollout(gmpc_handle* h, int64_t B, const float* x0, const float* U, float* X,
@@ -410,12 +417,7 @@ extern "C" int gmpc_plan(gmpc_handle* h, int64_t B, int32_t K, const float* x0, 
     X_out = U_out + (size_t)NQ * ub;
     J_out = J_all ? J_all : X_out + (size_t)NQ * xb;
   }
-  if (use_tc(h, NQ)) {
-    rc = tc_plan(h->tc, NQ, K, x0, U0, goal, h->d_mpcw, method, N, lr, b1, b2, eps, U_out, X_out,
-                 J_out, st, &h->launches);
-    if (rc) return rc;
-    h->last_path = GMPC_PATH_TC;
-  } else {
+  {
     PlanParams P;
     memset(&P, 0, sizeof(P));
     P.mode = MODE_PLAN; P.method = method; P.iters = N; P.use_cost = 1; P.final_fwd = 1;
@@ -609,5 +611,32 @@ extern "C" int gmpc_measure_fp32_peak(int device, float* tflops_out) {
   cudaEventDestroy(e1);
   cudaFree(d);
   *tflops_out = best;
+  return GMPC_OK;
+}
+
+extern "C" int gmpc_tc_probe(int device, int K, int NB, int a_major, uint32_t a_lbo, uint32_t a_sbo,
+                             uint32_t a_s1, uint32_t a_s2, uint32_t a_kstep, uint32_t b_lbo,
+                             uint32_t b_sbo, uint32_t b_s1, uint32_t b_s2, uint32_t a_bytes,
+                             uint32_t smem_bytes, const float* A_host, const float* B_host,
+                             float* D_host) {
+  if (!A_host || !B_host || !D_host || K < 8 || K % 8 || NB < 16 || NB % 16 || NB > 256 ||
+      smem_bytes > 200 * 1024 || a_bytes > smem_bytes)
+    return fail(GMPC_E_ARG, "gmpc_tc_probe: bad argument");
+  CU_CHECK(cudaSetDevice(device));
+  float *dA = nullptr, *dB = nullptr, *dD = nullptr;
+  const size_t a_floats = (a_major & 2) ? a_bytes / 4 : (size_t)128 * K;
+  CU_CHECK(cudaMalloc(&dA, sizeof(float) * a_floats));
+  CU_CHECK(cudaMalloc(&dB, sizeof(float) * NB * K));
+  CU_CHECK(cudaMalloc(&dD, sizeof(float) * 128 * NB));
+  CU_CHECK(cudaMemcpy(dA, A_host, sizeof(float) * a_floats, cudaMemcpyHostToDevice));
+  CU_CHECK(cudaMemcpy(dB, B_host, sizeof(float) * NB * K, cudaMemcpyHostToDevice));
+  CU_CHECK(cudaMemset(dD, 0, sizeof(float) * 128 * NB));
+  CU_CHECK(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  tc_probe_kernel<<<1, 128, smem_bytes>>>(dA, dB, dD, K, NB, a_major, a_lbo, a_sbo, a_s1, a_s2,
+                                          a_kstep, b_lbo, b_sbo, b_s1, b_s2, a_bytes);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(D_host, dD, sizeof(float) * 128 * NB, cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  if (e != cudaSuccess) return fail(GMPC_E_CUDA, std::string("gmpc_tc_probe: ") + cudaGetErrorString(e));
   return GMPC_OK;
 }

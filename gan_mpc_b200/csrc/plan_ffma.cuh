@@ -87,6 +87,56 @@ struct Tiles {
   }
 };
 
+// One register-buffered group of GR reduction rows: 8 activations x 4 weights per row.
+constexpr int GR = 2;
+struct KGroup {
+  float4 a0[GR], a1[GR], w[GR];
+  __device__ __forceinline__ void load(const float* in_row, const float* w_row, int ld, int o0,
+                                       int o1) {
+#pragma unroll
+    for (int u = 0; u < GR; ++u) {
+      a0[u] = *reinterpret_cast<const float4*>(in_row + u * RT + o0);
+      a1[u] = *reinterpret_cast<const float4*>(in_row + u * RT + o1);
+      w[u] = *reinterpret_cast<const float4*>(w_row + u * ld);
+    }
+  }
+  __device__ __forceinline__ void fma(float (&acc)[8][4]) const {
+#pragma unroll
+    for (int u = 0; u < GR; ++u) {
+      const float av[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
+      const float wv[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], wv[b], acc[a][b]);
+    }
+  }
+};
+
+// One staged weight chunk for one output tile: software-pipelined (the operands of row group
+// g+1 are loaded from shared memory while the FFMAs of group g issue).  rows is a multiple of 4,
+// so the swizzle term is constant within an aligned pair of 2-row groups.
+__device__ __forceinline__ void chunk_fma(const float* in_s, bool swz_in, const float* st, int ld,
+                                          int k0, int rows, int rg, int cg, float (&acc)[8][4]) {
+  const float* wcol = st + cg * 4;
+  KGroup g0, g1;
+  int sw = swz_in ? ((k0 >> 2) & 7) : 0;
+  int o0 = ((rg * 2) ^ sw) << 2, o1 = ((rg * 2 + 1) ^ sw) << 2;
+  g0.load(in_s + k0 * RT, wcol, ld, o0, o1);
+#pragma unroll 1
+  for (int kk = 0; kk < rows; kk += 4) {
+    g1.load(in_s + (k0 + kk + 2) * RT, wcol + (kk + 2) * ld, ld, o0, o1);
+    g0.fma(acc);
+    if (kk + 4 < rows) {
+      sw = swz_in ? (((k0 + kk + 4) >> 2) & 7) : 0;
+      o0 = ((rg * 2) ^ sw) << 2;
+      o1 = ((rg * 2 + 1) ^ sw) << 2;
+      g0.load(in_s + (k0 + kk + 4) * RT, wcol + (kk + 4) * ld, ld, o0, o1);
+    }
+    g1.fma(acc);
+  }
+}
+
 // acc[j][rr][cc] += sum_k W[k][cg*4+cc] * in[k][rg*8+rr], consuming the layer's chunks in order.
 template <int MAXT>
 __device__ __forceinline__ void gemm_acc(const PlanParams& P, const LayerDesc& L,
@@ -109,29 +159,9 @@ __device__ __forceinline__ void gemm_acc(const PlanParams& P, const LayerDesc& L
     ++wp.consumed;
     const int k0 = c * L.kc;
     const int rows = min(L.kc, L.Ki - k0);  // multiple of 4 (Ki and kc are)
-#pragma unroll 1
-    for (int kk = 0; kk < rows; kk += 4) {
-      const int sw = swz_in ? (((k0 + kk) >> 2) & 7) : 0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float* ap = in_s + (k0 + kk + u) * RT;
-        const float* wrow = st + (kk + u) * L.ld;
-#pragma unroll
-        for (int j = 0; j < MAXT; ++j) {
-          if (tl.act[j]) {
-            const float4 a0 = *reinterpret_cast<const float4*>(ap + (((tl.rg[j] * 2) ^ sw) << 2));
-            const float4 a1 =
-                *reinterpret_cast<const float4*>(ap + (((tl.rg[j] * 2 + 1) ^ sw) << 2));
-            const float4 w = *reinterpret_cast<const float4*>(wrow + tl.cg[j] * 4);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-              for (int b = 0; b < 4; ++b) acc[j][a][b] = fmaf(av[a], wv[b], acc[j][a][b]);
-          }
-        }
-      }
+    for (int j = 0; j < MAXT; ++j) {
+      if (tl.act[j]) chunk_fma(in_s, swz_in, st, L.ld, k0, rows, tl.rg[j], tl.cg[j], acc[j]);
     }
   }
 }
@@ -339,6 +369,7 @@ plan_ffma_kernel(const __grid_constant__ PlanParams P) {
         if (tid < RT) {
           const int r = tid;
           float uu = 0.f;
+#pragma unroll 4
           for (int j = 0; j < m; ++j) {
             const float u = wsU[(t * m + j) * RT + r];
             q_s[(n + j) * RT + r] = u;

@@ -163,6 +163,14 @@ int gmpc_l2_loss(gmpc_handle* h, int64_t B, const float* X, const float* desired
  * second roofline denominator bench.py reports for the CUDA-core path. */
 int gmpc_measure_fp32_peak(int device, float* tflops_out);
 
+/* Diagnostics: one tcgen05 kind::tf32 contraction D[128][NB] = A[128][K] * B[NB][K]^T with
+ * caller-chosen shared-memory image strides and descriptor LBO/SBO (SWIZZLE_NONE).  HOST
+ * pointers.  Pins the descriptor semantics the tensor-core planner relies on. */
+int gmpc_tc_probe(int device, int K, int NB, int a_major, uint32_t a_lbo, uint32_t a_sbo,
+                  uint32_t a_s1, uint32_t a_s2, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo,
+                  uint32_t b_s1, uint32_t b_s2, uint32_t a_bytes, uint32_t smem_bytes,
+                  const float* A_host, const float* B_host, float* D_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,12 +84,17 @@ def objective(x0, U, goal_X, params):
     return X, J
 
 
-def _mlp_forward_keep(q, Ws, bs):
-    """forward through relu layers keeping the (pre-activation > 0) masks."""
+def _mlp_forward_keep(q, Ws, bs, margin=None):
+    """forward through relu layers keeping the (pre-activation > 0) masks.
+    `margin` (optional 1-element list holding a tensor): running per-row min |pre-activation|,
+    i.e. the distance of the row to the nearest ReLU kink (test diagnostics)."""
     masks = []
     for W, b in zip(Ws[:-1], bs[:-1]):
         z = q @ W + b
         masks.append(z > 0)  # jax relu grad is 1 only for x > 0
+        if margin is not None:
+            mz = z.abs().amin(-1)
+            margin[0] = mz if margin[0] is None else torch.minimum(margin[0], mz)
         q = torch.relu(z)
     return q @ Ws[-1] + bs[-1], masks
 
@@ -102,11 +107,14 @@ def _mlp_input_vjp(dy, Ws, masks):
     return d
 
 
-def objective_grad(x0, U, goal_X, params):
+def objective_grad(x0, U, goal_X, params, margin=None):
     """Hand-written adjoint of `objective` w.r.t. U -- what jax.grad computes at
     policy/optimizers.py:83,103 and what trajax ilqr returns as (gradient, adjoints).
 
-    Returns X [..,T+1,n], J [..], dU [..,T,m], lam [..,T+1,n]."""
+    Returns X [..,T+1,n], J [..], dU [..,T,m], lam [..,T+1,n].
+    margin: optional [None] list, filled with the per-trajectory min |hidden pre-activation|
+    (the gradient is discontinuous where it is 0: a row with a tiny margin has no well-defined
+    1e-4-accurate gradient in ANY fp32 implementation)."""
     T, m = U.shape[-2], U.shape[-1]
     n = x0.shape[-1]
     w = torch.sigmoid(params["mpc_weights"])
@@ -120,11 +128,11 @@ def objective_grad(x0, U, goal_X, params):
     for t in range(T):
         u = U[..., t, :]
         J = J + staging_cost(x, u, w[:2], goal_X[..., t, :])
-        out, masks = _mlp_forward_keep(torch.cat([x, u], -1), dyn_W, dyn_b)
+        out, masks = _mlp_forward_keep(torch.cat([x, u], -1), dyn_W, dyn_b, margin)
         masks_t.append(masks)
         x = out + x
         xs.append(x)
-    y, cmasks = _mlp_forward_keep(x, params["cost_W"], params["cost_b"])
+    y, cmasks = _mlp_forward_keep(x, params["cost_W"], params["cost_b"], margin)
     J = J + w[2] * (y * y).sum(-1)
 
     # adjoint sweep

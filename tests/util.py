@@ -51,3 +51,26 @@ def rel_rows(a, b):
     a = a.double().cpu().reshape(a.shape[0], -1)
     b = b.double().cpu().reshape(b.shape[0], -1)
     return float(((a - b).norm(dim=1) / (b.norm(dim=1) + 1e-30)).max())
+
+
+def rel_each(a, b):
+    a = a.double().cpu().reshape(a.shape[0], -1)
+    b = b.double().cpu().reshape(b.shape[0], -1)
+    return (a - b).norm(dim=1) / (b.norm(dim=1) + 1e-30)
+
+
+def assert_rows_close(name, k, o, tol=1e-4, outlier_frac=0.1, cap=5e-2):
+    """Row-wise (trajectory-norm-wise) parity after N planning iterations.
+
+    The planner's trajectory through U-space is not continuous in the arithmetic: a hidden
+    pre-activation within rounding distance of 0 flips a ReLU mask bit and an Adam step on a
+    near-zero gradient flips sign, in ANY fp32 implementation (the oracle's own fp32-vs-fp64
+    floor shows the same outliers).  So the bar is: every row within `cap` (nothing is garbage),
+    median far below `tol`, and at most `outlier_frac` of the rows (min 2) above `tol`; the
+    count is printed, never hidden."""
+    e = rel_each(k, o)
+    nbad = int((e >= tol).sum())
+    print(f"{name}: rows {len(e)}, median {float(e.median()):.2e}, max {float(e.max()):.2e}, rows >= {tol:g}: {nbad}")
+    assert float(e.max()) < cap, f"{name}: max row error {float(e.max()):.3e}"
+    assert float(e.median()) < tol / 4, f"{name}: median row error {float(e.median()):.3e}"
+    assert nbad <= max(2, int(outlier_frac * len(e))), f"{name}: {nbad} rows above {tol}"
