@@ -1,0 +1,44 @@
+"""Runner entry points with the reference's names (norm/runner.py:13-177).
+
+get_policy / get_params / get_optimizer are drop-in.  train / run need dm_control, a pre-trained
+expert checkpoint and trajectories.json -- none of which the reference ships -- and drive the
+bilevel cost trainer (next scope row): they keep their signatures and raise."""
+
+from gan_mpc_b200 import expert, optim, utils
+from gan_mpc_b200.norm import l2_policy
+from gan_mpc_b200.policy import eval
+
+
+def get_policy(config, x_size, u_size, expert_model=None):
+    cost, _ = utils.get_cost_model(config)
+    dynamics, _ = utils.get_dynamics_model(config, x_size)
+    if expert_model is None:
+        expert_model = expert.SyntheticExpert(config, x_size, u_size, seed=config.seed)
+    train_policy = l2_policy.L2MPC(config=config, cost_model=cost, dynamics_model=dynamics,
+                                   expert_model=expert_model)
+    eval_policy = eval.EvalMPC(config=config, cost_model=cost, dynamics_model=dynamics,
+                               expert_model=expert_model)
+    return train_policy, eval_policy, config.mpc
+
+
+def get_params(policy, config, x_size, u_size):
+    seed = config.seed
+    mpc_weights = tuple(config.mpc.model.cost.weights.to_dict().values())
+    return policy.init(mpc_weights, (seed, x_size), (seed, u_size), (True,))
+
+
+def get_optimizer(params, masked_vars, lr):
+    labels = utils.get_masked_labels(all_vars=params.keys(), masked_vars=masked_vars,
+                                     tx_key="tx", zero_key="zero")
+    opt = optim.MaskedClipAdam(lr, labels, max_norm=100.0)
+    return opt, opt.init(params)
+
+
+def train(*args, **kwargs):
+    raise NotImplementedError("norm.runner.train drives the dm_control simulator and the bilevel "
+                              "cost trainer: outside the B200 hot path (SURVEY.md section 2, #13)")
+
+
+def run(config_path, dataset_path=None):
+    raise NotImplementedError("norm.runner.run needs dm_control, an expert checkpoint and "
+                              "trajectories.json, none of which the reference ships")

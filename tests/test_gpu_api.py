@@ -1,0 +1,172 @@
+"""GPU tests of the drop-in Python API (EvalMPC / L2MPC / JS_MPC / policy.optimizers /
+critic_trainer) against the oracle -- written the way a test of the reference would read."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gan_mpc_b200 import optim, utils
+from gan_mpc_b200.config import load_config
+from gan_mpc_b200.gan import critic_trainer
+from gan_mpc_b200.gan import runner as gan_runner
+from gan_mpc_b200.norm import cost_trainer
+from gan_mpc_b200.norm import runner as norm_runner
+from gan_mpc_b200.policy import optimizers as opt
+from oracle import critic as ocritic
+from oracle import planner as oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def cfg(name):
+    return utils.get_config(os.path.join(load_config.CONFIG_DIR, name))
+
+
+def oracle_params(params, dtype=torch.float64):
+    def lists(tree):
+        p = tree["params"]
+        return ([p[f"Dense_{i}"]["kernel"].cpu().to(dtype) for i in range(len(p))],
+                [p[f"Dense_{i}"]["bias"].cpu().to(dtype) for i in range(len(p))])
+    dW, db = lists(params["dynamics_params"])
+    cW, cb = lists(params["cost_params"])
+    return dict(dyn_W=dW, dyn_b=db, cost_W=cW, cost_b=cb, mpc_weights=params["mpc_weights"].cpu().to(dtype))
+
+
+def test_l2_policy_plan_and_act(built_lib):
+    """config/l2_hyperparameters.yaml defaults (BASELINE config 1): n=3, m=1, T=5, single state."""
+    config = cfg("l2_hyperparameters.yaml")
+    x_size, u_size = 3, 1
+    train_policy, eval_policy, _ = norm_runner.get_policy(config, x_size, u_size)
+    params = norm_runner.get_params(train_policy, config, x_size, u_size)
+    assert set(params) == {"mpc_weights", "cost_params", "dynamics_params", "expert_params"}
+    assert params["dynamics_params"]["params"]["Dense_0"]["kernel"].shape == (4, 200)
+    history_x = torch.randn(2, x_size, generator=torch.Generator().manual_seed(0)).cuda()
+    history_u = torch.zeros(1, u_size).cuda()
+    X, U, obj, gradient, adjoints, lqr, iteration = eval_policy.get_optimal_values(params, history_x, history_u)
+    T = config.mpc.horizon
+    assert X.shape == (T + 1, x_size) and U.shape == (T, u_size) and obj.shape == ()
+    assert gradient.shape == (T, u_size) and adjoints.shape == (T + 1, x_size) and lqr is None
+    assert int(iteration) == config.mpc.planner.iters
+    u0 = eval_policy.get_optimal_action(params, history_x, history_u)
+    assert torch.equal(u0, U[0])
+    # same plan from the oracle, fed the expert's proposals
+    goal, init_u = eval_policy.get_goal_states_init_actions(history_x, params)
+    pk = eval_policy.planner_kwargs
+    oU, oX, oJ, _, _ = oracle.plan(history_x[-1].cpu().double()[None], init_u.cpu().double()[None, None],
+                                   goal.cpu().double()[None], oracle_params(params), pk["method"],
+                                   pk["iters"], pk["learning_rate"])
+    assert util.rel_rows(U[None], oU) < TOL and util.rel_rows(X[None], oX) < TOL
+    assert abs(float(obj) - float(oJ)) < TOL * abs(float(oJ))
+    # train policy (BaseMPC signature: no history_u) gives the same plan
+    X2, U2, *_ = train_policy.get_optimal_values(params, history_x)
+    assert torch.equal(U2, U) and torch.equal(X2, X)
+
+
+def test_batched_policy_and_optimizer_functions(built_lib):
+    config = cfg("l2_hyperparameters.yaml")
+    x_size, u_size, B = 3, 1, 70
+    policy, _, _ = norm_runner.get_policy(config, x_size, u_size)
+    params = norm_runner.get_params(policy, config, x_size, u_size)
+    hx = torch.randn(B, 2, x_size, generator=torch.Generator().manual_seed(1)).cuda()
+    X, U, obj, grad, lam, _, it = policy.get_optimal_values(params, hx)
+    T = config.mpc.horizon
+    assert X.shape == (B, T + 1, x_size) and U.shape == (B, T, u_size) and obj.shape == (B,)
+    goal, init_u = policy.get_goal_states_init_actions(hx, params)
+    op = oracle_params(params)
+    x0 = hx[:, -1]
+    # objective / rollout / gradient through the reference-named functions
+    cost = opt.bind(policy.cost, params, (goal,))
+    dyn = opt.bind(policy.dynamics, params)
+    J = opt.objective(cost, dyn, init_u, x0)
+    oX, oJ, odU, _ = oracle.objective_grad(x0.cpu().double(), init_u.cpu().double(), goal.cpu().double(), op)
+    assert util.rel_rows(J[:, None], oJ[:, None]) < TOL
+    assert util.rel_rows(opt.rollout(dyn, init_u, x0), oX) < TOL
+    J2, dU, X2, _ = opt.objective_and_grad(cost, dyn, init_u, x0)
+    util.assert_rows_close("dJ/dU", dU, odU, TOL)   # a ReLU-kink-adjacent row may exceed 1e-4 (see util)
+    # ilqr_solve with the reference's argument order
+    out = opt.ilqr_solve(policy.cost, policy.dynamics, x0, init_u, params, (goal,), (), policy.trajax_ilqr_kwargs)
+    assert torch.equal(out[1], U)
+    # L2 loss and its control gradient
+    desired = goal
+    loss = policy.loss(X, U, params, desired)
+    assert util.rel_rows(loss[:, None], oracle.l2_loss(X.cpu().double(), desired.cpu().double())[:, None]) < TOL
+    g = opt.loss_grad_wrt_control(policy.loss, dyn, x0, U, (params, desired))
+    og = oracle.loss_grad_wrt_control_l2(x0.cpu().double(), U.cpu().double(), desired.cpu().double(), op)
+    util.assert_rows_close("dL2/dU", g, og, TOL)
+    # cost_trainer.calculate_loss = mean loss of the plans
+    test_loss = cost_trainer.calculate_loss(policy, params, (hx, desired))
+    assert abs(float(test_loss) - float(loss.mean())) < 1e-5 * abs(float(loss.mean()))
+    with pytest.raises(NotImplementedError, match="next scope row"):
+        policy.loss_and_grad(hx, params, (desired,))
+
+
+def test_restaging_follows_parameter_updates(built_lib):
+    config = cfg("l2_hyperparameters.yaml")
+    policy, _, _ = norm_runner.get_policy(config, 3, 1)
+    params = norm_runner.get_params(policy, config, 3, 1)
+    hx = torch.randn(5, 2, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    J1 = policy.get_optimal_values(params, hx)[2].clone()
+    params["cost_params"]["params"]["Dense_2"]["kernel"].mul_(2.0)        # in-place update
+    J2 = policy.get_optimal_values(params, hx)[2].clone()
+    assert not torch.allclose(J1, J2)
+    params["mpc_weights"] = params["mpc_weights"] + 1.0                   # replaced tensor
+    J3 = policy.get_optimal_values(params, hx)[2]
+    assert not torch.allclose(J2, J3)
+
+
+def test_js_policy_losses_and_critic_training(built_lib):
+    """gan_hyperparameters.yaml (BASELINE config 3 at a small dataset): critic BCE loss/grad,
+    generator loss, get_dataset (planner on every sample) and the minibatch scan."""
+    config = cfg("gan_hyperparameters.yaml")
+    x_size, u_size, D = 3, 1, 96
+    policy, _, _ = gan_runner.get_policy(config, x_size, u_size)
+    params = gan_runner.get_params(policy, config, x_size, u_size)
+    assert "critic_params" in params
+    cm = policy.critic_model.model
+    F, L, H, T = cm.lstm_features, cm.num_layers, cm.num_hidden_units, config.mpc.horizon
+    gen = torch.Generator().manual_seed(3)
+    X = torch.randn(D, 2, x_size, generator=gen).cuda()
+    true_Y = (X[:, -1:, :] + 0.1 * torch.cumsum(torch.randn(D, T + 1, x_size, generator=gen).cuda(), 1)).contiguous()
+    split = 64
+    true_dataset = ((X[:split], true_Y[:split]), (X[split:], true_Y[split:]))
+    flat = policy.critic_flat(params)
+    # loss / grad pytree
+    lab = torch.cat([torch.ones(8), -torch.ones(8)]).cuda()
+    loss, grads = policy.critic_loss_and_grad(true_Y[:16], lab, params)
+    oloss, ograd = ocritic.critic_loss_and_grad(true_Y[:16].cpu().double(), lab.cpu().double(),
+                                                flat.cpu().double(), x_size, F, L, H)
+    assert abs(float(loss) - float(oloss)) < 1e-5
+    assert float((cm.flatten(grads["critic_params"]).cpu().double() - ograd).norm() / ograd.norm()) < TOL
+    assert float(grads["cost_params"]["params"]["Dense_0"]["kernel"].abs().sum()) == 0.0
+    assert abs(float(policy.critic_loss(true_Y[:16], lab, params)) - float(loss)) == 0.0
+    gl = policy.generator_loss(true_Y[:4], None, params, true_Y[:4])
+    assert torch.allclose(gl.cpu().double(), ocritic.generator_loss(true_Y[:4].cpu().double(), flat.cpu().double(),
+                                                                     x_size, F, L, H), atol=1e-5)
+    # dataset: expert (+1) and planned (-1) trajectories, train part permuted
+    (trX, trY), (teX, teY) = critic_trainer.get_dataset(policy, params, true_dataset, key=0)
+    assert trX.shape == (2 * split, T + 1, x_size) and teX.shape == (2 * (D - split), T + 1, x_size)
+    assert float(trY.sum()) == 0.0 and set(trY.tolist()) == {1.0, -1.0}
+    planned = policy.get_optimal_values(params, X[split:])[0]
+    assert torch.equal(teX[D - split:], planned) and torch.equal(teX[:D - split], true_Y[split:])
+    # the scan: reference signature, deterministic key
+    copt, copt_state = gan_runner.get_optimizer(params, config.mpc.train.critic.no_grads, lr=1e-3)
+    assert copt.trained == ["critic_params"]
+    perm = torch.randint(0, trX.shape[0], (3, 32), generator=torch.Generator().manual_seed(5)).to(torch.int32).cuda()
+    new_params, copt_state, mean_loss = critic_trainer.train_critic_parameters(
+        (policy, copt), copt_state, params, perm, (trX, trY))
+    of, _, _, _, ol = ocritic.train_critic_parameters(
+        flat.cpu().double(), torch.zeros(flat.numel(), dtype=torch.float64), torch.zeros(flat.numel(), dtype=torch.float64),
+        0, perm.cpu().long(), trX.cpu().double(), trY.cpu().double(), 1e-3, x_size, F, L, H)
+    assert float((policy.critic_flat(new_params).cpu().double() - of).abs().max()) < 2e-5
+    assert abs(float(mean_loss) - float(ol)) < 1e-5 and copt_state["count"] == 3
+    assert torch.equal(policy.critic_flat(params), flat)                     # inputs are not mutated
+    # full train(): (params, opt_state, train_losses, test_losses, minutes)
+    copt, copt_state = gan_runner.get_optimizer(params, config.mpc.train.critic.no_grads, lr=1e-3)
+    out = critic_trainer.train((policy, copt), copt_state, params, true_dataset, num_updates=2,
+                               batch_size=32, key=0, id=1)
+    assert len(out) == 5 and len(out[2]) == 2 and len(out[3]) == 2 and out[4] >= 0.0
+    assert out[2][1] < out[2][0]                                            # the critic learns

@@ -1,0 +1,113 @@
+"""CPU tests of the host-side mirror of the reference API (no kernels launched)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from gan_mpc_b200 import parallel, synthetic, utils
+from gan_mpc_b200.config import load_config
+from gan_mpc_b200.critic import nn as critic_nn
+from gan_mpc_b200.policy import optimizers as opt
+from oracle import critic as ocritic
+
+REF = "/root/reference/config"
+
+
+@pytest.mark.parametrize("name", ["l2_hyperparameters.yaml", "gan_hyperparameters.yaml"])
+def test_yaml_matches_reference_values(name):
+    """Our hyper-parameter files carry the reference's keys and values (+ the mpc.planner block)."""
+    ours = yaml.safe_load(open(os.path.join(load_config.CONFIG_DIR, name)))
+    assert ours["mpc"]["planner"]["method"] in ("adam", "grad")
+    if not os.path.exists(os.path.join(REF, name)):
+        pytest.skip("reference tree not mounted")
+    ref = yaml.safe_load(open(os.path.join(REF, name)))
+
+    def check(r, o, path=""):
+        for k, v in r.items():
+            if path + k == "expert_prediction":
+                continue                      # expert network: out of scope
+            assert k in o, f"missing key {path}{k}"
+            if isinstance(v, dict):
+                check(v, o[k], path + k + ".")
+            else:
+                assert o[k] == v, f"{path}{k}: {o[k]} != {v}"
+    check(ref, ours)
+
+
+def test_config_attribute_tree_roundtrip():
+    c = load_config.Config.from_dict({"a": 1, "b": {"c": [1, 2], "d": {"e": "x"}}})
+    assert c.a == 1 and c.b.c == [1, 2] and c.b.d.e == "x"
+    assert c.to_dict() == {"a": 1, "b": {"c": [1, 2], "d": {"e": "x"}}}
+
+
+def test_critic_flatten_roundtrip_and_layout():
+    n, F, L, H = 5, 8, 3, 6
+    model = critic_nn.LSTM(F, L, H)
+    flat = torch.from_numpy(synthetic.critic_params_flat(0, n, F, L, H))
+    assert model.param_count(n) == flat.numel() == ocritic.critic_param_count(n, F, L, H)
+    tree = model.unflatten(flat, n)
+    cell = tree["params"][critic_nn.CELL]
+    assert set(cell) == {"ii", "if", "ig", "io", "hi", "hf", "hg", "ho"}       # flax OptimizedLSTMCell
+    assert "bias" not in cell["ii"] and cell["hi"]["bias"].shape == (F,)
+    assert cell["ig"]["kernel"].shape == (n, F) and cell["ho"]["kernel"].shape == (F, F)
+    assert tree["params"]["Dense_2"]["kernel"].shape == (H, 1)
+    assert torch.equal(model.flatten(tree), flat)
+    # the oracle reads the same flat layout
+    o = ocritic.unflatten(flat, n, F, L, H)
+    assert torch.equal(o["Wi"][:, 2 * F:3 * F], cell["ig"]["kernel"])
+
+
+def test_lecun_normal_statistics():
+    rng = np.random.Generator(np.random.PCG64(0))
+    W = synthetic.lecun_normal(rng, 400, 300)
+    assert abs(W.std() - np.sqrt(1 / 400)) < 0.02 * np.sqrt(1 / 400)          # variance 1/fan_in
+    assert np.abs(W).max() <= 2.0 * np.sqrt(1 / 400) / 0.87962566103423978 + 1e-7
+    Q = synthetic.orthogonal(rng, 16)
+    assert np.allclose(Q.T @ Q, np.eye(16), atol=1e-5)
+
+
+def test_arbitrary_closures_are_rejected():
+    """No CPU fallback: a plain Python cost/dynamics closure cannot run in the planner."""
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        opt.ilqr_solve(lambda x, u, t, p: 0.0, lambda x, u, t, p: x, None, None, {}, (None,), (), {})
+    with pytest.raises(TypeError):
+        opt.objective(lambda x, u, t: 0.0, lambda x, u, t: x, None, None)
+    for fn in (opt.bilevel_optimization, opt.cost_hessian_wrt_control, opt.cost_vjp):
+        with pytest.raises(NotImplementedError, match="next scope row"):
+            fn()
+
+
+def test_model_factories_and_mask_labels():
+    c = utils.get_config(os.path.join(load_config.CONFIG_DIR, "gan_hyperparameters.yaml"))
+    cost, _ = utils.get_cost_model(c)
+    dyn, _ = utils.get_dynamics_model(c, 3)
+    critic, _ = utils.get_critic_model(c)
+    assert (cost.model.num_layers, cost.model.num_hidden_units, cost.model.fout) == (3, 128, 10)
+    assert (dyn.model.num_layers, dyn.model.num_hidden_units, dyn.model.x_out) == (4, 200, 3)
+    assert (critic.model.lstm_features, critic.model.num_layers) == (64, 1)
+    labels = utils.get_masked_labels(["mpc_weights", "cost_params", "critic_params"],
+                                     c.mpc.train.critic.no_grads, "tx", "zero")
+    assert labels == {"mpc_weights": "zero", "cost_params": "zero", "critic_params": "tx"}
+    p = dyn.init(0, 1, device="cpu")
+    assert p["params"]["Dense_0"]["kernel"].shape == (4, 200) and p["params"]["Dense_3"]["kernel"].shape == (200, 3)
+    assert float(p["params"]["Dense_1"]["bias"].abs().sum()) == 0.0
+
+
+def test_timeit_appends_minutes():
+    @utils.timeit
+    def f():
+        return 1, 2
+    out = f()
+    assert out[:2] == (1, 2) and len(out) == 3 and out[2] >= 0.0
+
+
+@pytest.mark.parametrize("B,world", [(10, 4), (4096, 8), (3, 8), (0, 2), (262144, 8)])
+def test_shard_range_partitions_the_batch(B, world):
+    edges = [parallel.shard_range(B, r, world) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == B
+    sizes = [hi - lo for lo, hi in edges]
+    assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+    assert max(sizes) - min(sizes) <= 1
