@@ -61,6 +61,7 @@ _SIGS = {
     "gmpc_l2_loss": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.c_void_p]),
     "gmpc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "gmpc_tc_probe": (C.c_int, [C.c_int] * 4 + [C.c_uint32] * 11 + [C.c_void_p] * 3),
+    "gmpc_tc_mma_bench": (C.c_int, [C.c_int] * 5 + [C.c_uint32] * 7 + [C.c_int, C.POINTER(C.c_double)]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -308,3 +309,12 @@ def tc_probe(A, B, a_major, a_lbo, a_sbo, a_s1, a_s2, a_kstep, b_lbo, b_sbo, b_s
                                 a_s1, a_s2, a_kstep, b_lbo, b_sbo, b_s1, b_s2, a_bytes,
                                 smem_bytes, A.ctypes.data, B.ctypes.data, D.ctypes.data))
     return D
+
+
+def tc_mma_bench(N, ksteps, reps, a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, layout_type=0,
+                 two_mma=0, grid=1, device=0):
+    """cycles per tcgen05.mma (M=128, N, K=8 tf32) for the given operand layout."""
+    out = C.c_double(0.0)
+    _check(load().gmpc_tc_mma_bench(int(device), grid, N, ksteps, reps, a_lbo, a_sbo, a_kstep,
+                                    b_lbo, b_sbo, b_kstep, layout_type, two_mma, C.byref(out)))
+    return float(out.value)

@@ -91,3 +91,72 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(
 }
 
 }  // namespace gmpc
+
+namespace gmpc {
+
+// tcgen05.mma issue/execute-rate microbenchmark (timing only; operand contents are arbitrary).
+// One elected thread issues `reps` rounds of `ksteps` MMAs (M=128, N, K=8 tf32), walking the A
+// descriptor through a `ksteps`-deep image exactly like the planner does, then commits and waits.
+// layout_type 0 = SWIZZLE_NONE (lbo/sbo as given), 2 = SWIZZLE_128B.  out[blockIdx] = cycles.
+__global__ void __launch_bounds__(128) tc_mma_bench_kernel(long long* out, int N, int ksteps,
+                                                           int reps, uint32_t a_lbo, uint32_t a_sbo,
+                                                           uint32_t a_kstep, uint32_t b_lbo,
+                                                           uint32_t b_sbo, uint32_t b_kstep,
+                                                           uint32_t layout_type, int two_mma) {
+  extern __shared__ __align__(1024) uint8_t bsm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<float*>(bsm)[i] = 1.0f;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  long long cyc = 0;
+  if (warp == 1) {
+    const uint32_t idesc = umma_idesc_tf32(N, 0), idesc2 = umma_idesc_tf32(N / 2, 0);
+    const uint32_t a_base = smem_u32(bsm), b_base = smem_u32(bsm) + 112 * 1024;
+    const uint64_t lt = (uint64_t)layout_type << 61;
+    const long long t0 = clock64();
+    if (elect_one()) {
+      // descriptors are advanced by adding (bytes >> 4) to the low word: one add per operand
+      const uint64_t ad0 = umma_smem_desc(a_base, a_lbo, a_sbo) | lt;
+      const uint64_t bd0 = umma_smem_desc(b_base, b_lbo, b_sbo) | lt;
+      const uint64_t a_inc = a_kstep >> 4, b_inc = b_kstep >> 4;
+      for (int r = 0; r < reps; ++r) {
+        uint64_t ad = ad0, bd = bd0;
+        uint32_t acc = 0;
+#pragma unroll 4
+        for (int s = 0; s < ksteps; ++s) {
+          // two_mma <= 1: same accumulator every time (+ optional dependent half-width MMA);
+          // two_mma >= 2: cycle through `two_mma` independent accumulators (TMEM column ranges)
+          umma_tf32(tmem_base + acc, ad, bd, idesc, 1u);
+          if (two_mma == 1) umma_tf32(tmem_base + N / 2, ad, bd, idesc2, 1u);
+          if (two_mma >= 2) acc = (acc + N >= (uint32_t)(two_mma * N)) ? 0u : acc + N;
+          ad += a_inc;
+          bd += b_inc;
+        }
+      }
+      umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    cyc = clock64() - t0;
+    if ((tid & 31) == 0) out[blockIdx.x] = cyc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace gmpc

@@ -640,3 +640,27 @@ extern "C" int gmpc_tc_probe(int device, int K, int NB, int a_major, uint32_t a_
   if (e != cudaSuccess) return fail(GMPC_E_CUDA, std::string("gmpc_tc_probe: ") + cudaGetErrorString(e));
   return GMPC_OK;
 }
+
+extern "C" int gmpc_tc_mma_bench(int device, int grid, int N, int ksteps, int reps, uint32_t a_lbo,
+                                 uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo,
+                                 uint32_t b_kstep, uint32_t layout_type, int two_mma,
+                                 double* cycles_per_mma) {
+  if (!cycles_per_mma || grid < 1 || grid > 1024 || N < 16 || N > 256 || N % 16 || ksteps < 1 || reps < 1)
+    return fail(GMPC_E_ARG, "gmpc_tc_mma_bench: bad argument");
+  CU_CHECK(cudaSetDevice(device));
+  long long* d = nullptr;
+  CU_CHECK(cudaMalloc(&d, sizeof(long long) * grid));
+  CU_CHECK(cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  for (int rep = 0; rep < 2; ++rep)
+    tc_mma_bench_kernel<<<grid, 128, 200 * 1024>>>(d, N, ksteps, reps, a_lbo, a_sbo, a_kstep, b_lbo,
+                                                   b_sbo, b_kstep, layout_type, two_mma);
+  cudaError_t e = cudaDeviceSynchronize();
+  std::vector<long long> h(grid);
+  if (e == cudaSuccess) e = cudaMemcpy(h.data(), d, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(GMPC_E_CUDA, std::string("gmpc_tc_mma_bench: ") + cudaGetErrorString(e));
+  long long mx = 0;
+  for (long long v : h) mx = std::max(mx, v);
+  *cycles_per_mma = (double)mx / ((double)reps * ksteps * (two_mma == 1 ? 2 : 1));
+  return GMPC_OK;
+}

@@ -24,6 +24,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <string>
 #include <vector>
 
@@ -36,8 +39,8 @@ namespace gmpc {
 constexpr int TC_NB = 32;              // trajectories per tile
 constexpr int TC_THREADS = 320;        // producer warp + MMA warp + 8 compute warps
 constexpr int TC_COMPUTE = 256;
-constexpr int TC_SLOT_BYTES = 16384;   // weight ring slot
-constexpr int TC_NSLOT = 6;
+constexpr int TC_SLOT_BYTES = 26624;   // weight ring slot: two k-steps of a 200-row layer (2 x 12800 B)
+constexpr int TC_NSLOT = 4;
 constexpr int TC_RING_PAD = 4096;      // MMA row blocks may read (never use) past a short image
 constexpr int TC_SB_FEATS = 32;        // small operand buffer: q=[x;u], lambda, dy (<= 32 features)
 constexpr uint32_t TC_LBO_B = 2 * TC_NB * 16 + 16;  // B operand k-chunk slab: 32 hi + 32 lo rows, +16 B pad
@@ -71,6 +74,7 @@ struct TcParams {
   float *U_out, *X_out, *J_out, *dU_out, *lam_out;
   float *ws_X, *ws_G, *ws_U, *ws_M, *ws_V;
   uint32_t* ws_mask;
+  long long* dbg;  // optional [grid][16] cycle counters (phase breakdown), nullptr = off
 };
 
 __device__ __forceinline__ int tc_pass_kind(const TcParams& P, int p) {
@@ -102,7 +106,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int hb_chunks) {
   s.hb = TC_NSLOT * TC_SLOT_BYTES + TC_RING_PAD;
   s.sb = s.hb + (uint32_t)hb_chunks * TC_LBO_B;
   s.small = s.sb + (TC_SB_FEATS / 4) * TC_LBO_B;
-  s.bars = s.small + 5 * TC_SB_FEATS * TC_SROW * 4;  // x_s, lam_s, dq_s, y_s, x0_s
+  s.bars = s.small + 10 * TC_SB_FEATS * TC_SROW * 4;  // x_s, lam_s, dq_s, y_s, x0_s + 5 staging arrays
   s.total = s.bars + 256;
   return s;
 }
@@ -127,6 +131,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
   float* dq_s = lam_s + TC_SB_FEATS * TC_SROW;
   float* y_s = dq_s + TC_SB_FEATS * TC_SROW;
   float* x0_s = y_s + TC_SB_FEATS * TC_SROW;
+  // per-step staging of the L2-resident trajectory scratch (prefetched during the MMA phase)
+  float* pu_s = x0_s + TC_SB_FEATS * TC_SROW;  // U[t]
+  float* pg_s = pu_s + TC_SB_FEATS * TC_SROW;  // goal[t]
+  float* px_s = pg_s + TC_SB_FEATS * TC_SROW;  // X[t]
+  float* pm_s = px_s + TC_SB_FEATS * TC_SROW;  // Adam first moment [t]
+  float* pv_s = pm_s + TC_SB_FEATS * TC_SROW;  // Adam second moment [t]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tsm + L.bars);
   uint64_t* empty_bar = full_bar + TC_NSLOT;
   uint64_t* acc_bar = empty_bar + TC_NSLOT;
@@ -135,16 +145,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = P.n, m = P.m, T = P.T;
+  // cluster: the CTAs of a cluster share every weight stage (each loads 1/C and multicasts it)
+  const uint32_t C = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << C) - 1u);
+  const int n_iter = (P.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;  // uniform per cluster
 
   // zero all operand / scratch memory once: padded features must stay finite
   for (uint32_t i = tid * 4; i < L.bars; i += TC_THREADS * 4) *reinterpret_cast<uint32_t*>(tsm + i) = 0u;
   if (tid == 0) {
     for (int s = 0; s < TC_NSLOT; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], C);  // one tcgen05.commit arrival from every CTA of the cluster
     }
     mbar_init(acc_bar, 1);
-    mbar_init(act_bar, TC_COMPUTE);
+    mbar_init(act_bar, TC_COMPUTE / 32);  // one arrival per compute warp
     mbar_fence_init();
   }
   __syncwarp();
@@ -152,14 +166,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();  // peers' barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
     // ================================================================== weight-stage producer
-    if (lane == 0) {
+    {
       uint32_t cnt = 0;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      for (int ti = 0; ti < n_iter; ++ti) {  // every CTA of a cluster streams every iteration
         for (int p = 0;; ++p) {
           const int kind = tc_pass_kind(P, p);
           if (kind == DIR_END) break;
@@ -170,10 +185,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
               const uint32_t slot = cnt % TC_NSLOT, ph = (cnt / TC_NSLOT) & 1;
               const int ks = min(Y.kps, Y.red_steps - s * Y.kps);
               const uint32_t bytes = (uint32_t)ks * Y.kstep_bytes;
-              mbar_wait(&empty_bar[slot], ph ^ 1);
-              mbar_arrive_expect_tx(&full_bar[slot], bytes);
-              bulk_copy_g2s(ring + slot * TC_SLOT_BYTES,
-                            Y.gsrc + (size_t)s * Y.kps * Y.kstep_bytes, bytes, &full_bar[slot]);
+              const uint32_t part = bytes / C;  // kstep_bytes is a multiple of 64
+              mbar_wait(&empty_bar[slot], ph ^ 1);  // all C CTAs released the slot
+              const uint8_t* src = Y.gsrc + (size_t)s * Y.kps * Y.kstep_bytes + crank * part;
+              uint8_t* dst = ring + slot * TC_SLOT_BYTES + crank * part;
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[slot], bytes);
+                if (C > 1)
+                  bulk_copy_g2s_mc(dst, src, part, &full_bar[slot], cmask);
+                else
+                  bulk_copy_g2s(dst, src, part, &full_bar[slot]);
+              }
+              __syncwarp();
             }
           }
         }
@@ -181,43 +204,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
+    {
       uint32_t cnt = 0, act_ph = 0;
+      long long t_act = 0, t_full = 0, t_issue = 0, tt;
       const uint32_t idesc64 = umma_idesc_tf32(2 * TC_NB, 0), idesc32 = umma_idesc_tf32(TC_NB, 0);
       const uint32_t ring_a = smem_u32(ring), hb_a = smem_u32(HB), sb_a = smem_u32(SB);
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      for (int ti = 0; ti < n_iter; ++ti) {
+        const bool live = (int)blockIdx.x + ti * (int)gridDim.x < P.ntiles;
         for (int p = 0;; ++p) {
           const int kind = tc_pass_kind(P, p);
           if (kind == DIR_END) break;
           const TcDir& D = P.dir[kind];
           for (int l = 0; l < D.L; ++l) {
             const TcLayer& Y = D.layer[l];
+            if (!live) {  // no tile this round: keep the cluster's ring protocol going
+              for (int s = 0; s < Y.nstages; ++s, ++cnt) {
+                const uint32_t slot = cnt % TC_NSLOT, ph = (cnt / TC_NSLOT) & 1;
+                mbar_wait(&full_bar[slot], ph);
+                if (elect_one()) umma_commit_mc(&empty_bar[slot], cmask);
+                __syncwarp();
+              }
+              continue;
+            }
             const uint32_t b_base = (l == 0) ? sb_a : hb_a;
+            tt = clock64();
             mbar_wait(act_bar, act_ph);
+            t_act += clock64() - tt;
             act_ph ^= 1;
             tc_fence_after();
             int kstep = 0;
             for (int s = 0; s < Y.nstages; ++s, ++cnt) {
               const uint32_t slot = cnt % TC_NSLOT, ph = (cnt / TC_NSLOT) & 1;
+              tt = clock64();
               mbar_wait(&full_bar[slot], ph);
+              t_full += clock64() - tt;
               tc_fence_after();
               const int ks = min(Y.kps, Y.red_steps - s * Y.kps);
-              for (int j = 0; j < ks; ++j, ++kstep) {
-                const uint32_t a0 = ring_a + slot * TC_SLOT_BYTES + j * Y.kstep_bytes;
-                const uint64_t bd = umma_smem_desc(b_base + kstep * 2 * TC_LBO_B, TC_LBO_B, 128);
-                for (int b = 0; b < Y.nblk; ++b) {
-                  const uint64_t ah = umma_smem_desc(a0 + b * 2048, Y.lbo, 128);
-                  const uint64_t al = umma_smem_desc(a0 + Y.hi_bytes + b * 2048, Y.lbo, 128);
-                  const uint32_t d = tmem_base + b * (2 * TC_NB);
-                  umma_tf32(d, ah, bd, idesc64, kstep > 0 ? 1u : 0u);  // [D1|D2] (+)= Wh x [ah;al]
-                  umma_tf32(d + TC_NB, al, bd, idesc32, 1u);           // D2 += Wl x ah
+              tt = clock64();
+              if (elect_one()) {
+                // descriptors advance by adding (bytes >> 4) to the low word: a handful of
+                // uniform adds per MMA instead of rebuilding the 64-bit descriptor
+                uint64_t ah = umma_smem_desc(ring_a + slot * TC_SLOT_BYTES, Y.lbo, 128);
+                uint64_t bd = umma_smem_desc(b_base + kstep * 2 * TC_LBO_B, TC_LBO_B, 128);
+                const uint64_t lo_off = Y.hi_bytes >> 4, a_step = Y.kstep_bytes >> 4;
+                for (int j = 0; j < ks; ++j) {
+                  const uint32_t acc = (kstep + j) > 0 ? 1u : 0u;
+                  umma_tf32(tmem_base, ah, bd, idesc64, acc);                   // [D1|D2] (+)= Wh x [ah;al]
+                  umma_tf32(tmem_base + TC_NB, ah + lo_off, bd, idesc32, 1u);   // D2 += Wl x ah
+                  if (Y.nblk > 1) {
+                    umma_tf32(tmem_base + 2 * TC_NB, ah + (2048 >> 4), bd, idesc64, acc);
+                    umma_tf32(tmem_base + 3 * TC_NB, ah + (2048 >> 4) + lo_off, bd, idesc32, 1u);
+                  }
+                  ah += a_step;
+                  bd += (2 * TC_LBO_B) >> 4;
                 }
+                if (C > 1)
+                  umma_commit_mc(&empty_bar[slot], cmask);
+                else
+                  umma_commit(&empty_bar[slot]);
               }
-              umma_commit(&empty_bar[slot]);
+              __syncwarp();
+              t_issue += clock64() - tt;
+              kstep += ks;
             }
-            umma_commit(acc_bar);
+            if (elect_one()) umma_commit(acc_bar);
+            __syncwarp();
           }
         }
+      }
+      if (P.dbg != nullptr && lane == 0) {
+        P.dbg[blockIdx.x * 16 + 0] = t_act;
+        P.dbg[blockIdx.x * 16 + 1] = t_full;
+        P.dbg[blockIdx.x * 16 + 2] = t_issue;
       }
     }
   } else {
@@ -228,6 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
     const int c0 = half * (TC_NB / 2);
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     uint32_t acc_ph = 0;
+    long long t_acc = 0, t_epi = 0, t_fin = 0, t_total0 = clock64(), tq;
     const bool cost_mode = (P.mode == MODE_PLAN || P.mode == MODE_OBJGRAD);
     float w0 = 0.f, w1 = 0.f, w2 = 0.f;
     if (cost_mode) {
@@ -247,11 +306,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
     uint32_t* wsMask = P.ws_mask + (size_t)blockIdx.x * ((size_t)T * (Ld - 1) + (Lc - 1)) * TC_COMPUTE;
     uint32_t* costMask = wsMask + (size_t)T * (Ld - 1) * TC_COMPUTE;
 
-    // signal "operand of the next layer is in shared memory" (all 256 compute threads)
+    // signal "operand of the next layer is in shared memory": every writer fences its own
+    // generic-proxy stores for the async proxy, then one lane per warp arrives (count 8)
     auto publish = [&]() {
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(act_bar);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(act_bar);
     };
     // write `cnt` features of trajectory ct from a [f][TC_SROW] array into the small operand
     auto sb_from = [&](const float* src, int cnt) {
@@ -259,49 +320,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
         for (int f = 0; f < cnt; ++f) tc_store_op(SB, f, ct, src[f * TC_SROW + ct]);
     };
     // hidden layer: TMEM -> (+bias, relu, mask) or (mask gate) -> hi/lo -> HB
+    const int f0 = q * 32 + lane;  // this thread's feature in row block 0 (block 1: +128)
     auto hidden_epilogue = [&](const TcLayer& Y, bool fwd, uint32_t* maskp) {
+      // operands that do not depend on the accumulator are fetched before the wait
+      uint32_t mw = fwd ? 0u : maskp[ct];
+      float bias[2] = {0.f, 0.f};
+      if (fwd) {
+        if (f0 < Y.M_true) bias[0] = Y.bias[f0];
+        if (f0 + 128 < Y.M_true) bias[1] = Y.bias[f0 + 128];
+      }
+      tq = clock64();
       mbar_wait(acc_bar, acc_ph);
+      t_acc += clock64() - tq;
+      tq = clock64();
       acc_ph ^= 1;
       tc_fence_after();
-      uint32_t mw = fwd ? 0u : maskp[ct];
-      for (int b = 0; b < Y.nblk; ++b) {
-        const int f = b * 128 + q * 32 + lane;
-        float d1[16], d2[16];
-        tmem_ld16(tmem_base + t_lane + b * (2 * TC_NB) + c0, d1);
-        tmem_ld16(tmem_base + t_lane + b * (2 * TC_NB) + TC_NB + c0, d2);
-        if (f < Y.next_kpad) {
-          const bool live = f < Y.M_true;
-          const float bias = (fwd && live) ? Y.bias[f] : 0.f;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            float z = live ? (d1[c] + d2[c]) + bias : 0.f;
-            if (fwd) {
-              if (z > 0.f) mw |= 1u << (b * 16 + c);
-              z = fmaxf(z, 0.f);
-            } else {
-              z = ((mw >> (b * 16 + c)) & 1u) ? z : 0.f;
+      for (int b = 0; b < 2; ++b) {
+        if (b < Y.nblk) {
+          uint32_t d[1][2][16];
+          tmem_ld16_issue(tmem_base + t_lane + b * (2 * TC_NB) + c0, d[0][0]);
+          tmem_ld16_issue(tmem_base + t_lane + b * (2 * TC_NB) + TC_NB + c0, d[0][1]);
+          tmem_ld_wait();
+          const int f = b * 128 + f0;
+          if (f < Y.next_kpad) {
+            const bool live = f < Y.M_true;
+            uint8_t* base = HB + (f >> 2) * TC_LBO_B + (f & 3) * 4 + c0 * 16;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              float z = live ? (__uint_as_float(d[0][0][c]) + __uint_as_float(d[0][1][c])) + bias[b] : 0.f;
+              if (fwd) {
+                if (z > 0.f) mw |= 1u << (b * 16 + c);
+                z = fmaxf(z, 0.f);
+              } else {
+                z = ((mw >> (b * 16 + c)) & 1u) ? z : 0.f;
+              }
+              float hi, lo;
+              split_tf32(z, hi, lo);
+              uint8_t* p = base + (c >> 3) * 128 + (c & 7) * 16;
+              *reinterpret_cast<float*>(p) = hi;
+              *reinterpret_cast<float*>(p + (TC_NB / 8) * 128) = lo;
             }
-            tc_store_op(HB, f, c0 + c, z);
           }
         }
       }
       if (fwd) maskp[ct] = mw;
       publish();
+      t_epi += clock64() - tq;
     };
     // last layer of a pass: <= 32 output features, lanes of quadrant 0 only -> small fp32 array
     auto final_epilogue = [&](const TcLayer& Y, bool fwd, float* out, bool resid, float* gout) {
+      float bias = 0.f;
+      if (q == 0 && fwd && lane < Y.M_true) bias = Y.bias[lane];
+      tq = clock64();
       mbar_wait(acc_bar, acc_ph);
+      t_fin += clock64() - tq;
       acc_ph ^= 1;
       tc_fence_after();
       if (q == 0) {
-        float d1[16], d2[16];
-        tmem_ld16(tmem_base + t_lane + c0, d1);
-        tmem_ld16(tmem_base + t_lane + TC_NB + c0, d2);
+        uint32_t d1[16], d2[16];
+        tmem_ld16_issue(tmem_base + t_lane + c0, d1);
+        tmem_ld16_issue(tmem_base + t_lane + TC_NB + c0, d2);
+        tmem_ld_wait();
         if (lane < Y.M_true) {
-          const float bias = fwd ? Y.bias[lane] : 0.f;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            float v = (d1[c] + d2[c]) + bias;
+            float v = (__uint_as_float(d1[c]) + __uint_as_float(d2[c])) + bias;
             if (resid) v += out[lane * TC_SROW + c0 + c];
             out[lane * TC_SROW + c0 + c] = v;
             if (gout) gout[lane * TC_NB + c0 + c] = v;
@@ -312,7 +396,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
       named_bar_sync(1, TC_COMPUTE);
     };
 
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+    const bool adam = (P.mode == MODE_PLAN && P.method == 1);
+    const bool need_goal = cost_mode || P.mode == MODE_L2GRAD;
+    // stage step t's slices of the per-CTA scratch in shared memory (all 256 threads, coalesced);
+    // issued while the tensor pipe works so the per-trajectory code never waits on L2
+    auto prefetch = [&](int t, bool bwd) {
+      for (int e = ct; e < m * TC_NB; e += TC_COMPUTE) {
+        const int j = e / TC_NB, r = e - j * TC_NB;
+        pu_s[j * TC_SROW + r] = wsU[t * m * TC_NB + e];
+        if (bwd && adam) {
+          pm_s[j * TC_SROW + r] = wsM[t * m * TC_NB + e];
+          pv_s[j * TC_SROW + r] = wsV[t * m * TC_NB + e];
+        }
+      }
+      if (need_goal) {
+        for (int e = ct; e < n * TC_NB; e += TC_COMPUTE) {
+          const int i = e / TC_NB, r = e - i * TC_NB;
+          pg_s[i * TC_SROW + r] = wsG[t * n * TC_NB + e];
+          if (bwd) px_s[i * TC_SROW + r] = wsX[t * n * TC_NB + e];
+        }
+      }
+    };
+
+    for (int ti = 0; ti < n_iter; ++ti) {
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+      if (tile >= P.ntiles) break;
       const long long q0 = (long long)tile * TC_NB;
       named_bar_sync(1, TC_COMPUTE);
       // ---------------------------------------------------------------- stage the tile
@@ -350,12 +458,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
         const bool last = (it == P.iters);
         if (last && !P.final_fwd) break;
         // -------------------------------------------------------------- forward rollout
+        named_bar_sync(1, TC_COMPUTE);  // the previous sweep's last update (warp 2) is complete
         for (int e = ct; e < n * TC_NB; e += TC_COMPUTE) {
           const int i = e / TC_NB, r = e - i * TC_NB;
           x_s[i * TC_SROW + r] = x0_s[i * TC_SROW + r];
           wsX[e] = x0_s[i * TC_SROW + r];
         }
         Jr = 0.f;
+        prefetch(0, false);
         named_bar_sync(1, TC_COMPUTE);
         for (int t = 0; t < T; ++t) {
           if (ct < TC_NB) {
@@ -363,7 +473,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
             float uu = 0.f;
 #pragma unroll 4
             for (int j = 0; j < m; ++j) {
-              const float u = wsU[(t * m + j) * TC_NB + r];
+              const float u = pu_s[j * TC_SROW + r];
               tc_store_op(SB, n + j, r, u);
               uu = fmaf(u, u, uu);
             }
@@ -372,8 +482,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
             for (int i = 0; i < n; ++i) {
               const float x = x_s[i * TC_SROW + r];
               tc_store_op(SB, i, r, x);
-              if (cost_mode || P.mode == MODE_L2GRAD) {
-                const float d = x - wsG[(t * n + i) * TC_NB + r];
+              if (need_goal) {
+                const float d = x - pg_s[i * TC_SROW + r];
                 dd = fmaf(d, d, dd);
               }
             }
@@ -384,8 +494,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
           }
           publish();
           const TcDir& D = P.dir[DIR_DYN_F];
-          for (int l = 0; l < D.L - 1; ++l)
+          if (D.L == 1) named_bar_sync(1, TC_COMPUTE);  // staging is free once warp 2 is past the pre-step
+          for (int l = 0; l < D.L - 1; ++l) {
             hidden_epilogue(D.layer[l], true, wsMask + ((size_t)t * (Ld - 1) + l) * TC_COMPUTE);
+            // every warp has published layer 0's operand => the pre-step reads are done: refill
+            if (l == 0 && t + 1 < T) prefetch(t + 1, false);
+          }
+          if (D.L == 1 && t + 1 < T) prefetch(t + 1, false);
           final_epilogue(D.layer[D.L - 1], true, x_s, true, wsX + (size_t)(t + 1) * n * TC_NB);
         }
         // -------------------------------------------------------------- terminal cost
@@ -441,9 +556,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
           sb_from(lam_s, n);
           publish();
           const TcDir& D = P.dir[DIR_DYN_B];
-          for (int lb = 0; lb < D.L - 1; ++lb)
+          if (D.L == 1) named_bar_sync(1, TC_COMPUTE);
+          for (int lb = 0; lb < D.L - 1; ++lb) {
             hidden_epilogue(D.layer[lb], false,
                             wsMask + ((size_t)t * (Ld - 1) + (D.L - 2 - lb)) * TC_COMPUTE);
+            if (lb == 0) prefetch(t, true);  // previous post-step (warp 2) finished before it published
+          }
+          if (D.L == 1) prefetch(t, true);
           final_epilogue(D.layer[D.L - 1], false, dq_s, false, nullptr);
           if (ct < TC_NB) {
             const int r = ct;
@@ -452,12 +571,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
               float uu = 0.f, dd = 0.f;
 #pragma unroll 4
               for (int j = 0; j < m; ++j) {
-                const float u = wsU[(t * m + j) * TC_NB + r];
+                const float u = pu_s[j * TC_SROW + r];
                 uu = fmaf(u, u, uu);
               }
 #pragma unroll 4
               for (int i = 0; i < n; ++i) {
-                const float d = wsX[(t * n + i) * TC_NB + r] - wsG[(t * n + i) * TC_NB + r];
+                const float d = px_s[i * TC_SROW + r] - pg_s[i * TC_SROW + r];
                 dd = fmaf(d, d, dd);
               }
               su = sqrtf(uu + a2);
@@ -466,15 +585,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
 #pragma unroll 2
             for (int j = 0; j < m; ++j) {
               const int ix = (t * m + j) * TC_NB + r;
-              float u = wsU[ix];
+              float u = pu_s[j * TC_SROW + r];
               float g = dq_s[(n + j) * TC_SROW + r];
               if (cost_mode) g = (w0 * u) / su + g;
               if (P.mode == MODE_PLAN) {
                 if (P.method == 0) {
                   u = u - P.lr * g;
                 } else {
-                  const float mo = P.b1 * wsM[ix] + (1.f - P.b1) * g;
-                  const float ve = P.b2 * wsV[ix] + (1.f - P.b2) * g * g;
+                  const float mo = P.b1 * pm_s[j * TC_SROW + r] + (1.f - P.b1) * g;
+                  const float ve = P.b2 * pv_s[j * TC_SROW + r] + (1.f - P.b2) * g * g;
                   wsM[ix] = mo;
                   wsV[ix] = ve;
                   u = u - P.lr * (mo / bc1) / (sqrtf(ve / bc2) + P.eps);
@@ -486,7 +605,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
             }
 #pragma unroll 2
             for (int i = 0; i < n; ++i) {
-              const float d = wsX[(t * n + i) * TC_NB + r] - wsG[(t * n + i) * TC_NB + r];
+              const float d = px_s[i * TC_SROW + r] - pg_s[i * TC_SROW + r];
               const float c = cost_mode ? (w1 * d) / sd : l2scale * d;
               const float lam = (c + lam_s[i * TC_SROW + r]) + dq_s[i * TC_SROW + r];
               lam_s[i * TC_SROW + r] = lam;
@@ -516,9 +635,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
         }
       }
     }
+    if (P.dbg != nullptr && ct == 0) {
+      P.dbg[blockIdx.x * 16 + 4] = t_acc;
+      P.dbg[blockIdx.x * 16 + 5] = t_epi;
+      P.dbg[blockIdx.x * 16 + 6] = t_fin;
+      P.dbg[blockIdx.x * 16 + 7] = clock64() - t_total0;
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
   if (warp == 0) {
     __syncwarp();
     tmem_dealloc(tmem_base, 128);
@@ -556,6 +682,10 @@ struct TcState {
   int hb_chunks = 0;
   size_t smem_bytes = 0;
   int num_sms = 0;
+  int cluster = 4;                 // requested CTAs per cluster (1, 2 or 4)
+  int max_clusters[5] = {0, 0, 0, 0, 0};  // co-resident clusters per cluster size
+  int last_cluster = 1;
+  long long* d_dbg = nullptr;  // GMPC_DEBUG: per-CTA phase cycle counters
 };
 
 inline int rup(int v, int a) { return (v + a - 1) / a * a; }
@@ -637,6 +767,33 @@ inline int tc_create(TcState& S, const gmpc_config& c, const int* dyn_dims, cons
   if (cudaFuncSetAttribute(plan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)S.smem_bytes) != cudaSuccess)
     return GMPC_E_CUDA;
+  for (int C = 2; C <= 4; C *= 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(prop.multiProcessorCount / C * C);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = S.smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, plan_tc_kernel, &cfg) != cudaSuccess) nc = 0;
+    S.max_clusters[C] = nc;
+  }
+  if (const char* env = getenv("GMPC_TC_CLUSTER")) S.cluster = atoi(env);
+  if (S.cluster != 1 && S.cluster != 2 && S.cluster != 4) S.cluster = 4;
+  while (S.cluster > 1 && S.max_clusters[S.cluster] <= 0) S.cluster >>= 1;
+  if (getenv("GMPC_DEBUG")) {
+    cudaMalloc(&S.d_dbg, sizeof(long long) * 16 * 1024);
+    cudaMemset(S.d_dbg, 0, sizeof(long long) * 16 * 1024);
+  }
+  if (getenv("GMPC_DEBUG"))
+    fprintf(stderr, "[gmpc] tc: smem %zu B, max co-resident clusters: x2=%d x4=%d, using cluster=%d (%s)\n",
+            S.smem_bytes, S.max_clusters[2], S.max_clusters[4], S.cluster, cudaGetErrorString(cudaGetLastError()));
   S.supported = true;
   S.why = "";
   return GMPC_OK;
@@ -695,11 +852,37 @@ inline int tc_launch(TcState& S, const PlanParams& P, cudaStream_t st, int64_t* 
   Q.U_out = P.U_out; Q.X_out = P.X_out; Q.J_out = P.J_out; Q.dU_out = P.dU_out; Q.lam_out = P.lam_out;
   Q.ws_X = P.ws_X; Q.ws_G = P.ws_G; Q.ws_U = P.ws_U; Q.ws_M = P.ws_M; Q.ws_V = P.ws_V;
   Q.ws_mask = P.ws_mask;
-  const int grid = std::min(Q.ntiles, S.num_sms);
-  if (grid <= 0) return GMPC_OK;
-  plan_tc_kernel<<<grid, TC_THREADS, S.smem_bytes, st>>>(Q);
+  Q.dbg = S.d_dbg;
+  if (Q.ntiles <= 0) return GMPC_OK;
+  // cluster size: share each weight stage among up to 4 CTAs (multicast) when there are tiles for them
+  int C = S.cluster;
+  while (C > 1 && Q.ntiles < C) C >>= 1;
+  const int max_ctas = C > 1 ? S.max_clusters[C] * C : S.num_sms;
+  int grid = std::min((Q.ntiles + C - 1) / C * C, max_ctas);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = S.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, plan_tc_kernel, Q);
   ++*launches;
-  return cudaGetLastError() == cudaSuccess ? GMPC_OK : GMPC_E_CUDA;
+  S.last_cluster = C;
+  if (S.d_dbg != nullptr && e == cudaSuccess) {
+    long long hdbg[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hdbg, S.d_dbg, sizeof(hdbg), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[gmpc] tc CTA0 cycles: mma-warp wait_act %lld wait_full %lld issue %lld | compute wait_acc(hidden) %lld epilogue %lld wait_acc(final) %lld total %lld\n",
+            hdbg[0], hdbg[1], hdbg[2], hdbg[4], hdbg[5], hdbg[6], hdbg[7]);
+  }
+  return e == cudaSuccess ? GMPC_OK : GMPC_E_CUDA;
 }
 
 }  // namespace gmpc

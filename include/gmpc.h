@@ -171,6 +171,12 @@ int gmpc_tc_probe(int device, int K, int NB, int a_major, uint32_t a_lbo, uint32
                   uint32_t b_s1, uint32_t b_s2, uint32_t a_bytes, uint32_t smem_bytes,
                   const float* A_host, const float* B_host, float* D_host);
 
+/* Diagnostics: tcgen05.mma (M=128, N, K=8 tf32) cycles per instruction for a given operand
+ * layout, issued the way the planner issues them (timing only). */
+int gmpc_tc_mma_bench(int device, int grid, int N, int ksteps, int reps, uint32_t a_lbo,
+                      uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo,
+                      uint32_t b_kstep, uint32_t layout_type, int two_mma, double* cycles_per_mma);
+
 #ifdef __cplusplus
 }
 #endif
