@@ -106,7 +106,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int hb_chunks) {
   s.hb = TC_NSLOT * TC_SLOT_BYTES + TC_RING_PAD;
   s.sb = s.hb + (uint32_t)hb_chunks * TC_LBO_B;
   s.small = s.sb + (TC_SB_FEATS / 4) * TC_LBO_B;
-  s.bars = s.small + 10 * TC_SB_FEATS * TC_SROW * 4;  // x_s, lam_s, dq_s, y_s, x0_s + 5 staging arrays
+  s.bars = s.small + 11 * TC_SB_FEATS * TC_SROW * 4;  // x_s, lam_s, dq_s, y_s, x0_s, 5 staging arrays, scalars
   s.total = s.bars + 256;
   return s;
 }
@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
   float* px_s = pg_s + TC_SB_FEATS * TC_SROW;  // X[t]
   float* pm_s = px_s + TC_SB_FEATS * TC_SROW;  // Adam first moment [t]
   float* pv_s = pm_s + TC_SB_FEATS * TC_SROW;  // Adam second moment [t]
+  float* scal_s = pv_s + TC_SB_FEATS * TC_SROW;  // per-trajectory scalars of the current step
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tsm + L.bars);
   uint64_t* empty_bar = full_bar + TC_NSLOT;
   uint64_t* acc_bar = empty_bar + TC_NSLOT;
@@ -319,6 +320,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
       if (ct < TC_NB)
         for (int f = 0; f < cnt; ++f) tc_store_op(SB, f, ct, src[f * TC_SROW + ct]);
     };
+    // same, spread over all 256 threads (caller guarantees src is visible to all of them)
+    auto sb_from_all = [&](const float* src, int cnt) {
+      for (int e = ct; e < cnt * TC_NB; e += TC_COMPUTE) {
+        const int f = e / TC_NB, r = e - f * TC_NB;
+        tc_store_op(SB, f, r, src[f * TC_SROW + r]);
+      }
+    };
     // hidden layer: TMEM -> (+bias, relu, mask) or (mask gate) -> hi/lo -> HB
     const int f0 = q * 32 + lane;  // this thread's feature in row block 0 (block 1: +128)
     auto hidden_epilogue = [&](const TcLayer& Y, bool fwd, uint32_t* maskp) {
@@ -468,28 +476,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
         prefetch(0, false);
         named_bar_sync(1, TC_COMPUTE);
         for (int t = 0; t < T; ++t) {
-          if (ct < TC_NB) {
+          // q = [x ; u_t] -> operand buffer, all threads; staging cost by one thread per trajectory
+          for (int e = ct; e < (n + m) * TC_NB; e += TC_COMPUTE) {
+            const int f = e / TC_NB, r = e - f * TC_NB;
+            tc_store_op(SB, f, r, f < n ? x_s[f * TC_SROW + r] : pu_s[(f - n) * TC_SROW + r]);
+          }
+          if (ct < TC_NB && need_goal) {
             const int r = ct;
-            float uu = 0.f;
+            float uu = 0.f, dd = 0.f;
 #pragma unroll 4
             for (int j = 0; j < m; ++j) {
               const float u = pu_s[j * TC_SROW + r];
-              tc_store_op(SB, n + j, r, u);
               uu = fmaf(u, u, uu);
             }
-            float dd = 0.f;
 #pragma unroll 4
             for (int i = 0; i < n; ++i) {
-              const float x = x_s[i * TC_SROW + r];
-              tc_store_op(SB, i, r, x);
-              if (need_goal) {
-                const float d = x - pg_s[i * TC_SROW + r];
-                dd = fmaf(d, d, dd);
-              }
+              const float d = x_s[i * TC_SROW + r] - pg_s[i * TC_SROW + r];
+              dd = fmaf(d, d, dd);
             }
             if (cost_mode)
               Jr += w0 * (sqrtf(uu + a2) - ALPHA) + w1 * (sqrtf(dd + a2) - ALPHA);
-            else if (P.mode == MODE_L2GRAD)
+            else
               Jr += dd;
           }
           publish();
@@ -505,7 +512,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
         }
         // -------------------------------------------------------------- terminal cost
         if (P.use_cost) {
-          sb_from(x_s, n);
+          sb_from_all(x_s, n);
           publish();
           const TcDir& D = P.dir[DIR_COST_F];
           for (int l = 0; l < D.L - 1; ++l)
@@ -544,73 +551,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) plan_tc_kernel(const __grid_con
           for (int i = 0; i < n; ++i)
             lam_s[i * TC_SROW + ct] = l2scale * (x_s[i * TC_SROW + ct] - wsG[(T * n + i) * TC_NB + ct]);
         }
-        if (P.lam_out != nullptr && rvalid)
-          for (int i = 0; i < n; ++i) P.lam_out[(qr * (T + 1) + T) * n + i] = lam_s[i * TC_SROW + ct];
+        if (!P.use_cost) named_bar_sync(1, TC_COMPUTE);  // L2 seed was written by warp 2 only
+        for (int e = ct; e < n * TC_NB; e += TC_COMPUTE) {
+          const int i = e / TC_NB, r = e - i * TC_NB;
+          const float lam = lam_s[i * TC_SROW + r];
+          tc_store_op(SB, i, r, lam);
+          if (P.lam_out != nullptr && q0 + r < P.NQ) P.lam_out[((q0 + r) * (T + 1) + T) * n + i] = lam;
+        }
         float bc1 = 1.f, bc2 = 1.f;
-        if (P.mode == MODE_PLAN && P.method == 1) {
+        if (adam) {
           bc1 = (float)(1.0 - pow((double)P.b1, (double)(it + 1)));
           bc2 = (float)(1.0 - pow((double)P.b2, (double)(it + 1)));
         }
         // -------------------------------------------------------------- adjoint sweep + update
         for (int t = T - 1; t >= 0; --t) {
-          sb_from(lam_s, n);
-          publish();
+          publish();  // lambda_{t+1} is in the operand buffer
           const TcDir& D = P.dir[DIR_DYN_B];
           if (D.L == 1) named_bar_sync(1, TC_COMPUTE);
           for (int lb = 0; lb < D.L - 1; ++lb) {
             hidden_epilogue(D.layer[lb], false,
                             wsMask + ((size_t)t * (Ld - 1) + (D.L - 2 - lb)) * TC_COMPUTE);
-            if (lb == 0) prefetch(t, true);  // previous post-step (warp 2) finished before it published
+            if (lb == 0) prefetch(t, true);  // every warp is past the previous step's update
           }
           if (D.L == 1) prefetch(t, true);
           final_epilogue(D.layer[D.L - 1], false, dq_s, false, nullptr);
-          if (ct < TC_NB) {
+          // phase 1: per-trajectory norms of the staging cost (one thread per trajectory)
+          if (ct < TC_NB && cost_mode) {
             const int r = ct;
-            float su = 0.f, sd = 0.f;
-            if (cost_mode) {
-              float uu = 0.f, dd = 0.f;
+            float uu = 0.f, dd = 0.f;
 #pragma unroll 4
-              for (int j = 0; j < m; ++j) {
-                const float u = pu_s[j * TC_SROW + r];
-                uu = fmaf(u, u, uu);
-              }
-#pragma unroll 4
-              for (int i = 0; i < n; ++i) {
-                const float d = px_s[i * TC_SROW + r] - pg_s[i * TC_SROW + r];
-                dd = fmaf(d, d, dd);
-              }
-              su = sqrtf(uu + a2);
-              sd = sqrtf(dd + a2);
-            }
-#pragma unroll 2
             for (int j = 0; j < m; ++j) {
-              const int ix = (t * m + j) * TC_NB + r;
-              float u = pu_s[j * TC_SROW + r];
-              float g = dq_s[(n + j) * TC_SROW + r];
-              if (cost_mode) g = (w0 * u) / su + g;
-              if (P.mode == MODE_PLAN) {
-                if (P.method == 0) {
-                  u = u - P.lr * g;
-                } else {
-                  const float mo = P.b1 * pm_s[j * TC_SROW + r] + (1.f - P.b1) * g;
-                  const float ve = P.b2 * pv_s[j * TC_SROW + r] + (1.f - P.b2) * g * g;
-                  wsM[ix] = mo;
-                  wsV[ix] = ve;
-                  u = u - P.lr * (mo / bc1) / (sqrtf(ve / bc2) + P.eps);
-                }
-                wsU[ix] = u;
-              } else if (P.dU_out != nullptr && rvalid) {
-                P.dU_out[(qr * T + t) * m + j] = g;
-              }
+              const float u = pu_s[j * TC_SROW + r];
+              uu = fmaf(u, u, uu);
             }
-#pragma unroll 2
+#pragma unroll 4
             for (int i = 0; i < n; ++i) {
               const float d = px_s[i * TC_SROW + r] - pg_s[i * TC_SROW + r];
-              const float c = cost_mode ? (w1 * d) / sd : l2scale * d;
-              const float lam = (c + lam_s[i * TC_SROW + r]) + dq_s[i * TC_SROW + r];
-              lam_s[i * TC_SROW + r] = lam;
-              if (P.lam_out != nullptr && rvalid) P.lam_out[(qr * (T + 1) + t) * n + i] = lam;
+              dd = fmaf(d, d, dd);
             }
+            scal_s[r] = sqrtf(uu + a2);
+            scal_s[TC_SROW + r] = sqrtf(dd + a2);
+          }
+          named_bar_sync(1, TC_COMPUTE);
+          // phase 2: action gradient + update and adjoint update, one (feature, trajectory) per thread
+          for (int e = ct; e < m * TC_NB; e += TC_COMPUTE) {
+            const int j = e / TC_NB, r = e - j * TC_NB;
+            const int ix = t * m * TC_NB + e;
+            float u = pu_s[j * TC_SROW + r];
+            float g = dq_s[(n + j) * TC_SROW + r];
+            if (cost_mode) g = (w0 * u) / scal_s[r] + g;
+            if (P.mode == MODE_PLAN) {
+              if (P.method == 0) {
+                u = u - P.lr * g;
+              } else {
+                const float mo = P.b1 * pm_s[j * TC_SROW + r] + (1.f - P.b1) * g;
+                const float ve = P.b2 * pv_s[j * TC_SROW + r] + (1.f - P.b2) * g * g;
+                wsM[ix] = mo;
+                wsV[ix] = ve;
+                u = u - P.lr * (mo / bc1) / (sqrtf(ve / bc2) + P.eps);
+              }
+              wsU[ix] = u;
+            } else if (P.dU_out != nullptr && q0 + r < P.NQ) {
+              P.dU_out[((q0 + r) * T + t) * m + j] = g;
+            }
+          }
+          for (int e = ct; e < n * TC_NB; e += TC_COMPUTE) {
+            const int i = e / TC_NB, r = e - i * TC_NB;
+            const float d = px_s[i * TC_SROW + r] - pg_s[i * TC_SROW + r];
+            const float c = cost_mode ? (w1 * d) / scal_s[TC_SROW + r] : l2scale * d;
+            const float lam = (c + lam_s[i * TC_SROW + r]) + dq_s[i * TC_SROW + r];
+            lam_s[i * TC_SROW + r] = lam;
+            tc_store_op(SB, i, r, lam);  // operand of the next adjoint step
+            if (P.lam_out != nullptr && q0 + r < P.NQ) P.lam_out[((q0 + r) * (T + 1) + t) * n + i] = lam;
           }
         }
         if (P.mode != MODE_PLAN) break;
