@@ -15,6 +15,7 @@
 #include "diag.cuh"
 #include "plan_ffma.cuh"
 #include "plan_tc.cuh"
+#include "plan_h16.cuh"
 
 using namespace gmpc;
 
@@ -71,8 +72,9 @@ struct gmpc_handle {
   float* d_losses = nullptr;
   size_t losses_cap = 0;
   int critic_grid = 0;
-  // tensor-core path state
+  // tensor-core path state (3xTF32 kernel and the fp16-split kernel)
   TcState tc;
+  H16State h16;
 };
 
 extern "C" const char* gmpc_last_error(void) { return g_err.c_str(); }
@@ -230,10 +232,10 @@ extern "C" int gmpc_create(const gmpc_config* cfg, gmpc_handle** out) {
     return fail(GMPC_E_CUDA, std::string("gmpc_create: ") + cudaGetErrorString(e));
   }
   int rc = tc_create(h->tc, c, h->dyn.dims, h->cost.dims, prop);
+  if (rc == GMPC_OK) rc = h16_create(h->h16, c, h->dyn.dims, h->cost.dims, prop);
   if (rc != GMPC_OK) {
-    std::string msg = g_err;
     gmpc_destroy(h);
-    return fail(rc, msg);
+    return fail(rc, "gmpc_create: tensor-core path setup failed (CUDA error)");
   }
   *out = h;
   return GMPC_OK;
@@ -243,6 +245,7 @@ extern "C" int gmpc_destroy(gmpc_handle* h) {
   if (!h) return GMPC_OK;
   cudaSetDevice(h->cfg.device);
   tc_destroy(h->tc);
+  h16_destroy(h->h16);
   cudaFree(h->d_wpack); cudaFree(h->d_mpcw);
   cudaFree(h->ws_X); cudaFree(h->ws_G); cudaFree(h->ws_U); cudaFree(h->ws_M); cudaFree(h->ws_V);
   cudaFree(h->ws_mask); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -256,9 +259,11 @@ extern "C" int64_t gmpc_critic_param_count(const gmpc_handle* h) {
 }
 
 extern "C" int gmpc_set_path(gmpc_handle* h, int path) {
-  if (!h || path < GMPC_PATH_AUTO || path > GMPC_PATH_TC) return fail(GMPC_E_ARG, "gmpc_set_path: bad argument");
+  if (!h || path < GMPC_PATH_AUTO || path > GMPC_PATH_TC16) return fail(GMPC_E_ARG, "gmpc_set_path: bad argument");
   if (path == GMPC_PATH_TC && !h->tc.supported)
     return fail(GMPC_E_UNSUPPORTED, "gmpc_set_path: tensor-core path unsupported for this shape: " + h->tc.why);
+  if (path == GMPC_PATH_TC16 && !h->h16.supported)
+    return fail(GMPC_E_UNSUPPORTED, "gmpc_set_path: tensor-core path unsupported for this shape: " + h->h16.why);
   h->path = path;
   return GMPC_OK;
 }
@@ -293,15 +298,19 @@ extern "C" int gmpc_set_weights(gmpc_handle* h, const float* const* dyn_W,
   CU_CHECK(cudaMemcpyAsync(h->d_mpcw, mpc_weights, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   rc = tc_set_weights(h->tc, dyn_W, dyn_b, cost_W, cost_b, st, &h->launches);
   if (rc) return rc;
+  rc = h16_set_weights(h->h16, dyn_W, dyn_b, cost_W, cost_b, st, &h->launches);
+  if (rc) return rc;
   CU_CHECK(cudaGetLastError());
   h->have_weights = true;
   return GMPC_OK;
 }
 
-static bool use_tc(gmpc_handle* h, int64_t NQ) {
-  if (h->path == GMPC_PATH_FFMA) return false;
-  if (h->path == GMPC_PATH_TC) return true;
-  return h->tc.supported && tc_worthwhile(h->tc, NQ);
+// Which kernel family serves a call: explicit choice, else the fp16-split tensor-core kernel when
+// the tile is a real dense contraction, else the fp32 CUDA-core kernel.
+static int pick_path(gmpc_handle* h, int64_t NQ) {
+  if (h->path != GMPC_PATH_AUTO) return h->path;
+  if (h->h16.supported && h16_worthwhile(h->h16, NQ)) return GMPC_PATH_TC16;
+  return GMPC_PATH_FFMA;
 }
 
 // Fill the parts of PlanParams shared by every mode and launch the planner kernel of the
@@ -319,10 +328,12 @@ static int launch_ffma(gmpc_handle* h, PlanParams& P, cudaStream_t st) {
   P.ntiles = (int)((P.NQ + RT - 1) / RT);
   const int grid = std::min(P.ntiles, h->num_sms);
   if (grid <= 0) return GMPC_OK;
-  if (use_tc(h, P.NQ)) {
-    int rc = tc_launch(h->tc, P, st, &h->launches);
+  const int path = pick_path(h, P.NQ);
+  if (path == GMPC_PATH_TC || path == GMPC_PATH_TC16) {
+    int rc = path == GMPC_PATH_TC ? tc_launch(h->tc, P, st, &h->launches)
+                                  : h16_launch(h->h16, P, st, &h->launches);
     if (rc) return fail(rc, "tensor-core planner launch failed");
-    h->last_path = GMPC_PATH_TC;
+    h->last_path = path;
     return GMPC_OK;
   }
   if (h->maxt == 1)

@@ -1,0 +1,1116 @@
+// plan_h16.cuh -- fused rollout + cost + adjoint + update kernel on the 5th-gen tensor cores,
+// kind::f16 split-precision operands (see h16_common.cuh), software-pipelined layer chain.
+//
+// One persistent CTA per SM plans a tile of 32 trajectories at a time; the whole planning loop
+// (N x {T forward steps, terminal-cost MLP, adjoint seed, T adjoint steps with the fused
+// gradient/Adam update}, final evaluation) runs inside the kernel.  The contraction is issued as
+//     out^T[features x 32 traj] = W^T[features x K] * act^T[K x 32 traj]
+// with the WEIGHTS as the A operand (128 output features per block, <= 2 blocks) and the
+// trajectories as the N dimension, so B = 4096 start states fill 128 SMs with full-height MMAs.
+//
+// What is different from plan_tc.cuh (3xTF32), each justified by tools/mma_rate.cu on B200:
+//  * an M=128 MMA with a small N is bound by the 4 KB read of A from shared memory (>= 40
+//    cycles), not by the tensor pipe: fp16 operands cover K = 16 per MMA instead of 8, halving the
+//    MMA count and the streamed weight bytes for the same 22-bit effective mantissa;
+//  * the weight stream is block-major (all k-steps of output block 0, then block 1) with one
+//    commit per block, TMEM accumulators and the hidden operand buffer are double-buffered, so the
+//    epilogue of block 0 runs under the MMAs of block 1 and the next layer starts on the features
+//    block 0 produced while block 1's epilogue is still running;
+//  * the B operand is MN-major: an epilogue thread (one feature, 16 trajectories) stores four
+//    16-byte vectors per block instead of 32 scalar stores;
+//  * the step boundary is handled by the two warps that can read the <= 32 valid accumulator
+//    lanes: they add the residual / adjoint terms and write the next step's operand directly.
+//
+// Restates the same reference lines as plan_ffma.cuh (dynamics/nn.py:27-34, cost/nn.py:23-29,
+// cost/cost_model.py:20-42, policy/optimizers.py:24-31 and :78-83; optax adam of norm/runner.py:53).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <string>
+#include <type_traits>
+
+#include "../../include/gmpc.h"
+#include "common.cuh"
+#include "h16_common.cuh"
+#include "plan_tc.cuh"  // tc_pass_kind, TcParams-independent helpers (rup)
+
+namespace gmpc {
+
+constexpr int H_THREADS = 352;  // producer warp + MMA warp + 8 compute warps + second producer warp
+constexpr int H_PRODUCER2 = 10; // warp index of the second producer
+constexpr int H_COMPUTE = 256;
+constexpr int H_BK_BYTES = 8192;     // one block-k-step: hi unit + lo unit
+constexpr int H_GROUP_BYTES = 2 * H_BK_BYTES;  // ring slot = one bulk copy = two k-steps of one block
+constexpr int H_SLOT_BYTES = H_GROUP_BYTES;
+constexpr int H_MAX_SLOTS = 12;
+constexpr int H_SROW = H_NB + 1;     // padded row of the small fp32 arrays
+constexpr int H_SB_BYTES = 4096;     // small operand: <= 32 features
+#ifndef H_POLL_NS
+#define H_POLL_NS 100
+#endif
+
+struct HLayer {
+  const uint8_t* gsrc;     // [block][k-step][hi unit | lo unit]
+  const float* bias;       // forward only
+  const float* inv_scale;  // device scalar: 1 / (power-of-two weight scale of this layer)
+  int M_true;              // output features of this (possibly transposed) layer
+  int nblk;                // 128-row blocks
+  int ksteps;              // reduction length / 16
+  int next_kpad;           // round_up(M_true, 16): features the epilogue defines in the next operand
+};
+struct HDir {
+  HLayer layer[MAXL];
+  int L;
+  int pad_;
+};
+
+struct HParams {
+  HDir dir[4];
+  int n, m, T, K;
+  int fout, mode, method, iters, use_cost, final_fwd, ntiles, nslot;
+  uint32_t hb_bytes, exp_;  // exp_: timing experiments (GMPC_H16_EXP), results are garbage when set
+  long long NQ;
+  float lr, b1, b2, eps;
+  const float *x0, *U_in, *goal, *mpcw;
+  float *U_out, *X_out, *J_out, *dU_out, *lam_out;
+  float *ws_X, *ws_G, *ws_U, *ws_M, *ws_V;
+  uint32_t* ws_mask;
+  long long* dbg;
+};
+
+__device__ __forceinline__ int h_pass_kind(const HParams& P, int p) {
+  const int period = 2 * P.T + (P.use_cost ? 2 : 0);
+  const int nb = P.iters * period;
+  if (p < nb) {
+    const int pp = p % period;
+    if (pp < P.T) return DIR_DYN_F;
+    if (P.use_cost) {
+      if (pp == P.T) return DIR_COST_F;
+      if (pp == P.T + 1) return DIR_COST_B;
+    }
+    return DIR_DYN_B;
+  }
+  if (!P.final_fwd) return DIR_END;
+  const int pp = p - nb;
+  if (pp < P.T) return DIR_DYN_F;
+  if (P.use_cost && pp == P.T) return DIR_COST_F;
+  return DIR_END;
+}
+
+// Shared-memory carve-up (byte offsets from the 128-aligned dynamic base).
+struct HSmem {
+  uint32_t ring, hb0, hb1, sb, small, bars, total;
+  // rows of the small fp32 arrays, in units of H_SROW floats
+  int r_x, r_lam, r_dq, r_y, r_x0, r_pu, r_pg, r_px, r_pm, r_pv, r_sc, rows;
+};
+__host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int n, int m, int fout) {
+  HSmem s;
+  s.ring = 0;
+  s.hb0 = (uint32_t)nslot * H_SLOT_BYTES;
+  s.hb1 = s.hb0 + hb_bytes;
+  s.sb = s.hb1 + hb_bytes;
+  s.small = s.sb + H_SB_BYTES;
+  int r = 0;
+  s.r_x = r; r += n;
+  s.r_lam = r; r += n;
+  s.r_dq = r; r += n + m;
+  s.r_y = r; r += fout;
+  s.r_x0 = r; r += n;
+  s.r_pu = r; r += m;
+  s.r_pg = r; r += n;
+  s.r_px = r; r += n;
+  s.r_pm = r; r += m;
+  s.r_pv = r; r += m;
+  s.r_sc = r; r += 5;  // sqrt(uu+a2), sqrt(dd+a2), 1/scale in flight, scale for the next operand, spare
+  s.rows = r;
+  s.bars = s.small + (uint32_t)r * H_SROW * 4;
+  s.bars = (s.bars + 15u) & ~15u;
+  s.total = s.bars + 512;
+  return s;
+}
+
+template <bool TIMED>
+__global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_constant__ HParams P) {
+  extern __shared__ __align__(128) uint8_t hsm[];
+  const HSmem L = h_smem_layout(P.nslot, P.hb_bytes, P.n, P.m, P.fout);
+  uint8_t* ring = hsm + L.ring;
+  uint8_t* HB0 = hsm + L.hb0;
+  uint8_t* HB1 = hsm + L.hb1;
+  uint8_t* SB = hsm + L.sb;
+  float* small = reinterpret_cast<float*>(hsm + L.small);
+  float* x_s = small + L.r_x * H_SROW;
+  float* lam_s = small + L.r_lam * H_SROW;
+  float* dq_s = small + L.r_dq * H_SROW;
+  float* y_s = small + L.r_y * H_SROW;
+  float* x0_s = small + L.r_x0 * H_SROW;
+  float* pu_s = small + L.r_pu * H_SROW;  // U[t]
+  float* pg_s = small + L.r_pg * H_SROW;  // goal[t]
+  float* px_s = small + L.r_px * H_SROW;  // X[t]
+  float* pm_s = small + L.r_pm * H_SROW;  // Adam first moment [t]
+  float* pv_s = small + L.r_pv * H_SROW;  // Adam second moment [t]
+  float* su_s = small + L.r_sc * H_SROW;  // sqrt(|u|^2 + a^2)
+  float* sd_s = su_s + H_SROW;            // sqrt(|x - goal|^2 + a^2)
+  float* isc_s = sd_s + H_SROW;           // 1 / scale of the adjoint operand in flight
+  float* snx_s = isc_s + H_SROW;          // scale for the next adjoint operand
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(hsm + L.bars);
+  uint64_t* empty_bar = full_bar + H_MAX_SLOTS;
+  uint64_t* acc_bar = empty_bar + H_MAX_SLOTS;  // [2]: accumulator block b complete
+  uint64_t* act_bar = acc_bar + 2;              // [2]: operand part b (features [128b, 128b+128)) ready
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(act_bar + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = P.n, m = P.m, T = P.T, NS = P.nslot;
+  const uint32_t C = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << C) - 1u);
+  const int n_iter = (P.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;  // uniform per cluster
+
+  // zero all operand / scratch memory once: padded features must stay finite
+  for (uint32_t i = tid * 4; i < L.bars; i += H_THREADS * 4) *reinterpret_cast<uint32_t*>(hsm + i) = 0u;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], C);  // one tcgen05.commit arrival from every CTA of the cluster
+    }
+    mbar_init(&acc_bar[0], 1);
+    mbar_init(&acc_bar[1], 1);
+    mbar_init(&act_bar[0], H_COMPUTE / 32);  // one arrival per compute warp
+    mbar_init(&act_bar[1], H_COMPUTE / 32);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_holder, 256);  // 2 buffers x 2 blocks x (32 + 32) fp32 columns
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (C > 1) cluster_sync_all();  // peers' barriers exist before anything is multicast to them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0 || warp == H_PRODUCER2) {
+    // ================================================================== weight-stream producers
+    // tools/bulk_copy_rate.cu: one cp.async.bulk blocks its issuing thread ~460 cycles whatever the
+    // size, but copies issued by several lanes of one instruction cost only ~67 cycles each.  The
+    // stream is therefore cut into 16 KB groups (two k-steps of one block, hi+lo units), and two
+    // producer warps x 4 lanes issue 8 group copies per round: lane k of producer w owns the
+    // groups G = 8r + 4w + k.  Every pass (all layers of one direction) is one contiguous image.
+    const int w = (warp == 0) ? 0 : 1;
+    if (lane < 4 && !(P.exp_ & 1)) {
+      uint32_t ngk[4];
+      const uint8_t* basek[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t ng = 0;
+        for (int l = 0; l < P.dir[k].L; ++l) ng += (uint32_t)(P.dir[k].layer[l].nblk * P.dir[k].layer[l].ksteps) >> 1;
+        ngk[k] = ng;
+        basek[k] = P.dir[k].layer[0].gsrc;
+      }
+      const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), ring_a = smem_u32(ring);
+      const uint32_t part = H_GROUP_BYTES / C;
+      const uint32_t G0 = 4u * w + lane;
+      uint32_t slot = G0 % (uint32_t)NS, ph = (G0 / (uint32_t)NS) & 1u;
+      uint32_t gi = G0;  // group index relative to the start of pass p (may run past its end)
+      int ti = 0, p = 0, kind = h_pass_kind(P, 0);
+      while (true) {
+        while (kind != DIR_END && gi >= ngk[kind]) {
+          gi -= ngk[kind];
+          kind = h_pass_kind(P, ++p);
+        }
+        if (kind == DIR_END) {
+          if (++ti == n_iter) break;
+          p = 0;
+          kind = h_pass_kind(P, 0);
+          continue;
+        }
+        const uint32_t bar = full_a + slot * 8;
+        mbar_wait_a(empty_a + slot * 8, ph ^ 1);  // all C CTAs released the slot
+        const uint32_t dst = ring_a + slot * H_GROUP_BYTES + crank * part;
+        const uint8_t* src = basek[kind] + (size_t)gi * H_GROUP_BYTES + crank * part;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)H_GROUP_BYTES) : "memory");
+        if (C > 1)
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+              "[%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src), "r"(part), "r"(bar), "h"(cmask) : "memory");
+        else
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+              ::"r"(dst), "l"(src), "r"(part), "r"(bar) : "memory");
+        gi += 8;
+        slot += 8;
+        while (slot >= (uint32_t)NS) { slot -= (uint32_t)NS; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    // ONE thread runs the whole role.  It is instruction-latency bound if written naively (ncu: ~66
+    // dependent SASS instructions per block-k-step vs 88 cycles of tensor work), so the work is
+    // issued in fully unrolled chunks of two groups (four k-steps): the full barriers are probed
+    // back to back, descriptors are plain adds of running 32-bit words, the split at k-step 8
+    // (operand part 1) is hoisted out, and the timers exist only in the TIMED instantiation.
+    if (elect_one()) {
+      uint32_t act_ph0 = 0, act_ph1 = 0, lc = 0;
+      long long t_act = 0, t_full = 0, tt = 0;
+      const uint32_t i64 = h16_idesc(2 * H_NB, 0, 1), i32 = h16_idesc(H_NB, 0, 1);
+      const uint32_t hb_a[2] = {smem_u32(HB0), smem_u32(HB1)}, sb_a = smem_u32(SB);
+      const uint64_t a_desc0 = umma_smem_desc(smem_u32(ring), H_A_LBO, H_A_SBO);
+      const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
+      const uint32_t full_a = smem_u32(full_bar);
+      constexpr uint32_t EMPTY_OFF = H_MAX_SLOTS * 8;  // empty_bar[s] sits EMPTY_OFF bytes after full_bar[s]
+      constexpr uint32_t KS = H_B_KSTEP >> 4;          // B descriptor advance per k-step
+      const uint32_t acc_a = smem_u32(acc_bar), act_a = smem_u32(act_bar);
+      // ring cursor: barrier address, A descriptor low word, groups left before the wrap, parity
+      uint32_t fb = full_a, a_lo = a_lo0, left = (uint32_t)NS, ph = 0;
+      const bool nostream = P.exp_ & 1;
+      // issue U consecutive groups (2U k-steps) of one block, fully unrolled
+      auto chunk = [&](auto Utag, uint32_t d0, uint32_t b_lo, uint32_t b_hi, uint32_t acc) {
+        constexpr int U = decltype(Utag)::value;
+        uint32_t fbu[U], au[U], phu[U];
+        bool oku[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          fbu[u] = fb; au[u] = a_lo; phu[u] = ph;
+          fb += 8;
+          a_lo += (H_GROUP_BYTES >> 4);
+          if (--left == 0) { fb = full_a; a_lo = a_lo0; left = (uint32_t)NS; ph ^= 1; }
+        }
+        if (!nostream) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) oku[u] = mbar_try_wait_a(fbu[u], phu[u]);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (!oku[u]) {
+              if (TIMED) tt = clock64();
+              mbar_wait_a(fbu[u], phu[u]);
+              if (TIMED) t_full += clock64() - tt;
+            }
+        }
+        tc_fence_after();
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint64_t ad = ((uint64_t)a_hi << 32) | au[u];
+          const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + u * 2 * KS);
+          umma_f16(d0, ad, bd, i64, (u == 0) ? acc : 1u);                             // [D1|D2] (+)= Wh x [ah;al]
+          umma_f16(d0 + H_NB, ad + (H_UNIT >> 4), bd, i32, 1u);                        // D2 += Wl x ah
+          umma_f16(d0, ad + (H_BK_BYTES >> 4), bd + KS, i64, 1u);                      // second k-step of the group
+          umma_f16(d0 + H_NB, ad + ((H_BK_BYTES + H_UNIT) >> 4), bd + KS, i32, 1u);
+          if (C > 1)
+            umma_commit_mc_a(fbu[u] + EMPTY_OFF, cmask);
+          else
+            umma_commit_a(fbu[u] + EMPTY_OFF);
+        }
+      };
+      // issue groups [g0, g1) of one block: d0 = accumulator columns, b_lo = B descriptor of group g0
+      auto issue = [&](int g0, int g1, uint32_t d0, uint32_t b_lo, uint32_t b_hi, uint32_t acc_first) {
+        uint32_t acc = acc_first;
+        int g = g0;
+        for (; g + 2 <= g1; g += 2, b_lo += 4 * KS, acc = 1u)
+          chunk(std::integral_constant<int, 2>{}, d0, b_lo, b_hi, acc);
+        if (g < g1) chunk(std::integral_constant<int, 1>{}, d0, b_lo, b_hi, acc);
+      };
+      for (int ti = 0; ti < n_iter; ++ti) {
+        const bool live = (int)blockIdx.x + ti * (int)gridDim.x < P.ntiles;
+        for (int p = 0;; ++p) {
+          const int kind = h_pass_kind(P, p);
+          if (kind == DIR_END) break;
+          const HDir& D = P.dir[kind];
+          int prev_nblk = 1;
+          for (int l = 0; l < D.L; ++l, ++lc) {
+            const HLayer& Y = D.layer[l];
+            const int ngrp = Y.ksteps >> 1, nblk = Y.nblk;
+            if (!live) {  // no tile this round: keep the cluster's ring protocol going
+              for (int i = 0; i < nblk * ngrp; ++i) {
+                mbar_wait_a(fb, ph);
+                umma_commit_mc_a(fb + EMPTY_OFF, cmask);
+                fb += 8;
+                a_lo += (H_GROUP_BYTES >> 4);
+                if (--left == 0) { fb = full_a; a_lo = a_lo0; left = (uint32_t)NS; ph ^= 1; }
+              }
+              continue;
+            }
+            const bool two_parts = (l > 0) && (prev_nblk > 1);
+            prev_nblk = nblk;
+            const uint64_t b_desc0 = umma_smem_desc((l == 0) ? sb_a : hb_a[(l - 1) & 1], H_B_LBO, H_B_SBO);
+            const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
+            const uint32_t d_base = tmem_base + (lc & 1) * 128;
+            if (TIMED) tt = clock64();
+            mbar_wait_a(act_a, act_ph0);
+            if (TIMED) t_act += clock64() - tt;
+            act_ph0 ^= 1;
+            // block 0: groups [0, 4) (k-steps 0..7) need operand part 0 only; the rest need part 1
+            const int gsplit = two_parts ? 4 : ngrp;
+            issue(0, gsplit, d_base, b_lo0, b_hi, 0u);
+            if (two_parts) {
+              if (TIMED) tt = clock64();
+              mbar_wait_a(act_a + 8, act_ph1);
+              if (TIMED) t_act += clock64() - tt;
+              act_ph1 ^= 1;
+              issue(4, ngrp, d_base, b_lo0 + 8 * KS, b_hi, 1u);
+            }
+            umma_commit_a(acc_a);
+            if (nblk > 1) {
+              issue(0, ngrp, d_base + 64, b_lo0, b_hi, 0u);
+              umma_commit_a(acc_a + 8);
+            }
+          }
+        }
+      }
+      if (TIMED) {
+        P.dbg[blockIdx.x * 16 + 0] = t_act;
+        P.dbg[blockIdx.x * 16 + 1] = t_full;
+        P.dbg[blockIdx.x * 16 + 2] = 0;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================== epilogue / elementwise
+    const int ct = tid - 64;               // 0..255
+    const int q = warp & 3;                // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;      // which 16 of the 32 trajectory columns
+    const int c0 = half * (H_NB / 2);
+    const bool fwarp = (q == 0);           // owns accumulator lanes 0..31: the <= 32-feature outputs
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    uint32_t acc_ph0 = 0, acc_ph1 = 0, lc = 0;
+    long long t_acc = 0, t_epi = 0, t_fin = 0, t_bnd = 0, t_total0 = clock64(), tq = 0, tb0 = 0;
+    constexpr bool timed = TIMED;
+    const bool cost_mode = (P.mode == MODE_PLAN || P.mode == MODE_OBJGRAD);
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+    if (cost_mode) {
+      w0 = 1.f / (1.f + expf(-P.mpcw[0]));
+      w1 = 1.f / (1.f + expf(-P.mpcw[1]));
+      w2 = 1.f / (1.f + expf(-P.mpcw[2]));
+    }
+    const float a2 = ALPHA * ALPHA;
+    const float l2scale = 2.f / (float)(T + 1);
+    const int Ld = P.dir[DIR_DYN_F].L;
+    const int Lc = P.use_cost ? P.dir[DIR_COST_F].L : 1;
+    float* wsX = P.ws_X + (size_t)blockIdx.x * (T + 1) * n * H_NB;
+    float* wsG = P.ws_G + (size_t)blockIdx.x * (T + 1) * n * H_NB;
+    float* wsU = P.ws_U + (size_t)blockIdx.x * T * m * H_NB;
+    float* wsM = P.ws_M + (size_t)blockIdx.x * T * m * H_NB;
+    float* wsV = P.ws_V + (size_t)blockIdx.x * T * m * H_NB;
+    uint32_t* wsMask = P.ws_mask + (size_t)blockIdx.x * ((size_t)T * (Ld - 1) + (Lc - 1)) * H_COMPUTE;
+    uint32_t* costMask = wsMask + (size_t)T * (Ld - 1) * H_COMPUTE;
+    const bool adam = (P.mode == MODE_PLAN && P.method == 1);
+    const bool need_goal = cost_mode || P.mode == MODE_L2GRAD;
+
+    // "operand part `part` of the next layer is in shared memory": every writer fences its own
+    // generic-proxy stores for the async proxy, then one lane per warp arrives (count 8)
+    auto publish = [&](int part) {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&act_bar[part]);
+    };
+    // 16 values of feature f (trajectories c0 .. c0+15), already scaled -> operand buffer `dst`
+    auto store_row16 = [&](uint8_t* dst, int f, const float (&v)[16]) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) split_h2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+      uint8_t* p = dst + (f >> 3) * H_B_LBO + (f & 7) * 16 + (c0 >> 3) * H_B_SBO;
+      *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(p + H_B_SBO) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      *reinterpret_cast<uint4*>(p + 4 * H_B_SBO) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(p + 5 * H_B_SBO) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    };
+    // hidden layer li of a pass: TMEM -> (+bias, relu, mask) or (mask gate) -> hi/lo -> HB[li & 1]
+    const int f0 = q * 32 + lane;  // this thread's feature in row block 0 (block 1: +128)
+    auto hidden_epilogue = [&](const HLayer& Y, int li, bool fwd, uint32_t* maskp) {
+      uint8_t* dst = (li & 1) ? HB1 : HB0;
+      const uint32_t d_base = tmem_base + (lc & 1) * 128 + t_lane + c0;
+      uint32_t mw = fwd ? 0u : maskp[ct];
+      const float inv = *Y.inv_scale;
+      float bias[2] = {0.f, 0.f};
+      if (fwd) {
+        if (f0 < Y.M_true) bias[0] = Y.bias[f0];
+        if (f0 + 128 < Y.M_true) bias[1] = Y.bias[f0 + 128];
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (b < Y.nblk) {
+          if (timed) tq = clock64();
+          if (b == 0) { mbar_wait_sleep(&acc_bar[0], acc_ph0, H_POLL_NS); acc_ph0 ^= 1; }
+          else        { mbar_wait_sleep(&acc_bar[1], acc_ph1, H_POLL_NS); acc_ph1 ^= 1; }
+          if (timed) { const long long t1 = clock64(); t_acc += t1 - tq; tq = t1; }
+          tc_fence_after();
+          uint32_t d1[16], d2[16];
+          tmem_ld16_issue(d_base + b * 64, d1);
+          tmem_ld16_issue(d_base + b * 64 + H_NB, d2);
+          tmem_ld_wait();
+          const int f = b * 128 + f0;
+          if (f < Y.next_kpad) {
+            const bool live = f < Y.M_true;
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              float z = live ? fmaf(__uint_as_float(d1[c]) + __uint_as_float(d2[c]), inv, bias[b]) : 0.f;
+              if (fwd) {
+                if (z > 0.f) mw |= 1u << (b * 16 + c);
+                z = fmaxf(z, 0.f);
+              } else {
+                z = ((mw >> (b * 16 + c)) & 1u) ? z : 0.f;
+              }
+              v[c] = z;
+            }
+            if (!(P.exp_ & 2)) store_row16(dst, f, v);
+          }
+          publish(b);
+          if (timed) t_epi += clock64() - tq;
+        }
+      }
+      if (fwd) maskp[ct] = mw;
+      ++lc;
+    };
+    // last layer of a pass (<= 32 output features): every warp keeps the barrier phase, the two
+    // f-warps load their 16 columns of the accumulator: out[c] = (d1 + d2) * inv_scale
+    auto final_load = [&](const HLayer& Y, float (&out)[16]) {
+      const uint32_t d_base = tmem_base + (lc & 1) * 128 + t_lane + c0;
+      const float inv = *Y.inv_scale;
+      if (timed) tq = clock64();
+      mbar_wait_sleep(&acc_bar[0], acc_ph0, H_POLL_NS);
+      acc_ph0 ^= 1;
+      if (timed) t_fin += clock64() - tq;
+      tc_fence_after();
+      if (fwarp) {
+        uint32_t d1[16], d2[16];
+        tmem_ld16_issue(d_base, d1);
+        tmem_ld16_issue(d_base + H_NB, d2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) out[c] = (__uint_as_float(d1[c]) + __uint_as_float(d2[c])) * inv;
+      }
+      ++lc;
+    };
+    // stage step t's slices of the per-CTA scratch in shared memory (all 256 threads, coalesced)
+    auto prefetch = [&](int t, bool bwd) {
+      if (P.exp_ & 4) return;
+      for (int e = ct; e < m * H_NB; e += H_COMPUTE) {
+        const int j = e / H_NB, r = e - j * H_NB;
+        pu_s[j * H_SROW + r] = wsU[t * m * H_NB + e];
+        if (bwd && adam) {
+          pm_s[j * H_SROW + r] = wsM[t * m * H_NB + e];
+          pv_s[j * H_SROW + r] = wsV[t * m * H_NB + e];
+        }
+      }
+      if (need_goal) {
+        for (int e = ct; e < n * H_NB; e += H_COMPUTE) {
+          const int i = e / H_NB, r = e - i * H_NB;
+          pg_s[i * H_SROW + r] = wsG[t * n * H_NB + e];
+          if (bwd) px_s[i * H_SROW + r] = wsX[t * n * H_NB + e];
+        }
+      }
+    };
+    // u rows (features n .. n+m-1) of the forward operand q = [x ; u], from the staged U[t]
+    auto sb_u_rows = [&]() {
+      for (int e = ct; e < m * H_NB; e += H_COMPUTE) {
+        const int j = e / H_NB, r = e - j * H_NB;
+        h16_store_op(SB, n + j, r, pu_s[j * H_SROW + r]);
+      }
+    };
+
+    for (int ti = 0; ti < n_iter; ++ti) {
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+      if (tile >= P.ntiles) break;
+      const long long q0 = (long long)tile * H_NB;
+      named_bar_sync(1, H_COMPUTE);
+      // ---------------------------------------------------------------- stage the tile
+      for (int e = ct; e < H_NB * n; e += H_COMPUTE) {
+        const int r = e / n, i = e - r * n;
+        const long long qq = q0 + r;
+        x0_s[i * H_SROW + r] = (qq < P.NQ) ? P.x0[(qq / P.K) * n + i] : 0.f;
+      }
+      if (P.goal != nullptr) {
+        const int per = (T + 1) * n;
+        for (int e = ct; e < H_NB * per; e += H_COMPUTE) {
+          const int r = e / per, rest = e - r * per;
+          const long long qq = q0 + r;
+          wsG[rest * H_NB + r] = (qq < P.NQ) ? P.goal[(qq / P.K) * per + rest] : 0.f;
+        }
+      }
+      {
+        const int per = T * m;
+        for (int e = ct; e < H_NB * per; e += H_COMPUTE) {
+          const int r = e / per, rest = e - r * per;
+          const long long qq = q0 + r;
+          wsU[rest * H_NB + r] = (qq < P.NQ) ? P.U_in[qq * per + rest] : 0.f;
+          if (adam) {
+            wsM[rest * H_NB + r] = 0.f;
+            wsV[rest * H_NB + r] = 0.f;
+          }
+        }
+      }
+      named_bar_sync(1, H_COMPUTE);
+      const long long qr = q0 + ct;
+      const bool rvalid = (ct < H_NB) && (qr < P.NQ);
+      float Jr = 0.f;
+
+      for (int it = 0;; ++it) {
+        const bool last = (it == P.iters);
+        if (last && !P.final_fwd) break;
+        // -------------------------------------------------------------- forward rollout
+        named_bar_sync(1, H_COMPUTE);  // the previous sweep's last update is complete
+        for (int e = ct; e < n * H_NB; e += H_COMPUTE) {
+          const int i = e / H_NB, r = e - i * H_NB;
+          const float v = x0_s[i * H_SROW + r];
+          x_s[i * H_SROW + r] = v;
+          wsX[e] = v;
+          h16_store_op(SB, i, r, v);
+        }
+        Jr = 0.f;
+        prefetch(0, false);
+        named_bar_sync(1, H_COMPUTE);
+        sb_u_rows();
+        publish(0);
+        for (int t = 0; t < T; ++t) {
+          // staging cost of step t (one thread per trajectory); x_s, pu_s, pg_s are visible
+          if (ct < H_NB && need_goal) {
+            const int r = ct;
+            float uu = 0.f, dd = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < m; ++j) {
+              const float u = pu_s[j * H_SROW + r];
+              uu = fmaf(u, u, uu);
+            }
+#pragma unroll 4
+            for (int i = 0; i < n; ++i) {
+              const float d = x_s[i * H_SROW + r] - pg_s[i * H_SROW + r];
+              dd = fmaf(d, d, dd);
+            }
+            if (cost_mode)
+              Jr += w0 * (sqrtf(uu + a2) - ALPHA) + w1 * (sqrtf(dd + a2) - ALPHA);
+            else
+              Jr += dd;
+          }
+          const HDir& D = P.dir[DIR_DYN_F];
+          for (int l = 0; l < D.L - 1; ++l) {
+            hidden_epilogue(D.layer[l], l, true, wsMask + ((size_t)t * (Ld - 1) + l) * H_COMPUTE);
+            if (l == 0 && t + 1 < T) {
+              // layer 0 has consumed SB and every warp is past the staging cost: refill
+              named_bar_sync(1, H_COMPUTE);
+              prefetch(t + 1, false);
+              named_bar_sync(1, H_COMPUTE);
+              sb_u_rows();
+            }
+          }
+          // step boundary: x_{t+1} = x_t + Dense(h) ; the f-warps write the next operand rows
+          if (timed) tb0 = clock64();
+          float o[16];
+          const HLayer& Yf = D.layer[D.L - 1];
+          const float bias = (fwarp && lane < n) ? Yf.bias[lane] : 0.f;
+          float xo[16];
+          if (fwarp && lane < n) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) xo[c] = x_s[lane * H_SROW + c0 + c];
+          }
+          final_load(Yf, o);
+          const bool more = (t + 1 < T) || P.use_cost;
+          if (fwarp && lane < n) {
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              v[c] = (o[c] + bias) + xo[c];
+              x_s[lane * H_SROW + c0 + c] = v[c];
+            }
+            if (more) store_row16(SB, lane, v);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) wsX[(size_t)(t + 1) * n * H_NB + lane * H_NB + c0 + c] = v[c];
+          }
+          if (more) publish(0);
+          named_bar_sync(1, H_COMPUTE);  // x_s of step t+1 visible
+          if (timed) t_bnd += clock64() - tb0;
+        }
+        // -------------------------------------------------------------- terminal cost
+        if (P.use_cost) {
+          const HDir& D = P.dir[DIR_COST_F];
+          for (int l = 0; l < D.L - 1; ++l)
+            hidden_epilogue(D.layer[l], l, true, costMask + (size_t)l * H_COMPUTE);
+          float o[16];
+          const HLayer& Yf = D.layer[D.L - 1];
+          const float bias = (fwarp && lane < P.fout) ? Yf.bias[lane] : 0.f;
+          final_load(Yf, o);
+          if (fwarp && lane < P.fout) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) y_s[lane * H_SROW + c0 + c] = o[c] + bias;
+          }
+          named_bar_sync(1, H_COMPUTE);
+          if (ct < H_NB) {
+            float yy = 0.f, mx = 0.f;
+            const float s2 = 2.f * w2;
+            for (int oo = 0; oo < P.fout; ++oo) {
+              const float y = y_s[oo * H_SROW + ct];
+              yy = fmaf(y, y, yy);
+              mx = fmaxf(mx, fabsf(s2 * y));
+            }
+            Jr += w2 * yy;
+            if (!last) {  // adjoint seed dJ/dy = 2 w2 y, scaled per trajectory into fp16 range
+              const float sc = pow2_scale_to_8(mx);
+              isc_s[ct] = 1.f / sc;
+              for (int oo = 0; oo < P.fout; ++oo) h16_store_op(SB, oo, ct, s2 * y_s[oo * H_SROW + ct] * sc);
+            }
+          }
+        } else if (P.mode == MODE_L2GRAD) {
+          if (ct < H_NB) {
+            float dd = 0.f;
+            for (int i = 0; i < n; ++i) {
+              const float d = x_s[i * H_SROW + ct] - wsG[(T * n + i) * H_NB + ct];
+              dd = fmaf(d, d, dd);
+            }
+            Jr = (Jr + dd) / (float)(T + 1);
+          }
+        }
+        if (last) break;
+        // -------------------------------------------------------------- adjoint seed lambda_T
+        if (P.use_cost) {
+          named_bar_sync(1, H_COMPUTE);  // isc_s of the seed is visible to the f-warps
+          publish(0);  // seed operand of the cost MLP's backward pass
+          const HDir& D = P.dir[DIR_COST_B];
+          for (int lb = 0; lb < D.L - 1; ++lb)
+            hidden_epilogue(D.layer[lb], lb, false, costMask + (size_t)(D.L - 2 - lb) * H_COMPUTE);
+          float o[16];
+          final_load(D.layer[D.L - 1], o);
+          if (fwarp && lane < n) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) lam_s[lane * H_SROW + c0 + c] = o[c] * isc_s[c0 + c];
+          }
+        } else if (ct < H_NB) {
+          for (int i = 0; i < n; ++i)
+            lam_s[i * H_SROW + ct] = l2scale * (x_s[i * H_SROW + ct] - wsG[(T * n + i) * H_NB + ct]);
+        }
+        named_bar_sync(1, H_COMPUTE);
+        if (ct < H_NB) {  // exact per-trajectory scale of lambda_T
+          float mx = 0.f;
+          for (int i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(lam_s[i * H_SROW + ct]));
+          const float sc = pow2_scale_to_8(mx);
+          snx_s[ct] = sc;
+        }
+        named_bar_sync(1, H_COMPUTE);
+        for (int e = ct; e < n * H_NB; e += H_COMPUTE) {
+          const int i = e / H_NB, r = e - i * H_NB;
+          const float lam = lam_s[i * H_SROW + r];
+          h16_store_op(SB, i, r, lam * snx_s[r]);
+          if (P.lam_out != nullptr && q0 + r < P.NQ) P.lam_out[((q0 + r) * (T + 1) + T) * n + i] = lam;
+        }
+        named_bar_sync(1, H_COMPUTE);
+        if (ct < H_NB) isc_s[ct] = 1.f / snx_s[ct];  // scale in flight; snx_s stays the lagged estimate
+        float bc1 = 1.f, bc2 = 1.f;
+        if (adam) {
+          bc1 = (float)(1.0 - pow((double)P.b1, (double)(it + 1)));
+          bc2 = (float)(1.0 - pow((double)P.b2, (double)(it + 1)));
+        }
+        publish(0);  // lambda_T operand of the first adjoint step
+        // -------------------------------------------------------------- adjoint sweep + update
+        for (int t = T - 1; t >= 0; --t) {
+          const HDir& D = P.dir[DIR_DYN_B];
+          for (int lb = 0; lb < D.L - 1; ++lb) {
+            hidden_epilogue(D.layer[lb], lb, false,
+                            wsMask + ((size_t)t * (Ld - 1) + (D.L - 2 - lb)) * H_COMPUTE);
+            if (lb == 0) {
+              named_bar_sync(1, H_COMPUTE);  // every warp is past the previous step's update
+              prefetch(t, true);
+              named_bar_sync(1, H_COMPUTE);
+              if (ct < H_NB && cost_mode) {  // per-trajectory norms of the staging cost
+                const int r = ct;
+                float uu = 0.f, dd = 0.f;
+#pragma unroll 4
+                for (int j = 0; j < m; ++j) {
+                  const float u = pu_s[j * H_SROW + r];
+                  uu = fmaf(u, u, uu);
+                }
+#pragma unroll 4
+                for (int i = 0; i < n; ++i) {
+                  const float d = px_s[i * H_SROW + r] - pg_s[i * H_SROW + r];
+                  dd = fmaf(d, d, dd);
+                }
+                su_s[r] = sqrtf(uu + a2);
+                sd_s[r] = sqrtf(dd + a2);
+              }
+              named_bar_sync(1, H_COMPUTE);
+            }
+          }
+          // step boundary: lambda_t = l_x + lambda_{t+1} + dq_x ; u gradient kept for the update
+          if (timed) tb0 = clock64();
+          float base[16], isc[16], snx[16];
+          if (fwarp && lane < n + m) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) isc[c] = isc_s[c0 + c];
+            if (lane < n) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float d = px_s[lane * H_SROW + c0 + c] - pg_s[lane * H_SROW + c0 + c];
+                const float cc = cost_mode ? (w1 * d) / sd_s[c0 + c] : l2scale * d;
+                base[c] = cc + lam_s[lane * H_SROW + c0 + c];
+                snx[c] = snx_s[c0 + c];
+              }
+            }
+          }
+          float o[16];
+          final_load(D.layer[D.L - 1], o);
+          if (fwarp && lane < n + m) {
+            if (lane < n) {
+              float v[16];
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float lam = base[c] + o[c] * isc[c];
+                lam_s[lane * H_SROW + c0 + c] = lam;
+                v[c] = lam * snx[c];
+              }
+              if (t > 0) store_row16(SB, lane, v);
+              if (P.lam_out != nullptr) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                  if (q0 + c0 + c < P.NQ)
+                    P.lam_out[((q0 + c0 + c) * (T + 1) + t) * n + lane] = lam_s[lane * H_SROW + c0 + c];
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) dq_s[lane * H_SROW + c0 + c] = o[c] * isc[c];
+            }
+          }
+          if (t > 0) publish(0);
+          named_bar_sync(1, H_COMPUTE);
+          if (timed) t_bnd += clock64() - tb0;
+          // action gradient + update, one (feature, trajectory) per thread
+          for (int e = ct; e < m * H_NB; e += H_COMPUTE) {
+            const int j = e / H_NB, r = e - j * H_NB;
+            const int ix = t * m * H_NB + e;
+            float u = pu_s[j * H_SROW + r];
+            float g = dq_s[(n + j) * H_SROW + r];
+            if (cost_mode) g = (w0 * u) / su_s[r] + g;
+            if (P.mode == MODE_PLAN) {
+              if (P.method == 0) {
+                u = u - P.lr * g;
+              } else {
+                const float mo = P.b1 * pm_s[j * H_SROW + r] + (1.f - P.b1) * g;
+                const float ve = P.b2 * pv_s[j * H_SROW + r] + (1.f - P.b2) * g * g;
+                wsM[ix] = mo;
+                wsV[ix] = ve;
+                u = u - P.lr * (mo / bc1) / (sqrtf(ve / bc2) + P.eps);
+              }
+              wsU[ix] = u;
+            } else if (P.dU_out != nullptr && q0 + r < P.NQ) {
+              P.dU_out[((q0 + r) * T + t) * m + j] = g;
+            }
+          }
+          // the operand just written used snx_s; the next one uses the scale of lambda_t
+          if (ct >= 32 && ct < 32 + H_NB && t > 0) {
+            const int r = ct - 32;
+            float mx = 0.f;
+            for (int i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(lam_s[i * H_SROW + r]));
+            isc_s[r] = 1.f / snx_s[r];
+            snx_s[r] = pow2_scale_to_8(mx);
+          }
+        }
+        if (P.mode != MODE_PLAN) break;
+      }
+      named_bar_sync(1, H_COMPUTE);
+      // ---------------------------------------------------------------- write the tile out
+      if (P.J_out != nullptr && rvalid) P.J_out[qr] = Jr;
+      if (P.U_out != nullptr) {
+        const int per = T * m;
+        for (int e = ct; e < H_NB * per; e += H_COMPUTE) {
+          const int r = e / per, rest = e - r * per;
+          const long long qq = q0 + r;
+          if (qq < P.NQ) P.U_out[qq * per + rest] = wsU[rest * H_NB + r];
+        }
+      }
+      if (P.X_out != nullptr) {
+        const int per = (T + 1) * n;
+        for (int e = ct; e < H_NB * per; e += H_COMPUTE) {
+          const int r = e / per, rest = e - r * per;
+          const long long qq = q0 + r;
+          if (qq < P.NQ) P.X_out[qq * per + rest] = wsX[rest * H_NB + r];
+        }
+      }
+    }
+    if (TIMED && ct == 0) {
+      P.dbg[blockIdx.x * 16 + 4] = t_acc;
+      P.dbg[blockIdx.x * 16 + 5] = t_epi;
+      P.dbg[blockIdx.x * 16 + 6] = t_fin;
+      P.dbg[blockIdx.x * 16 + 7] = clock64() - t_total0;
+      P.dbg[blockIdx.x * 16 + 8] = t_bnd;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (C > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// max |W| of one layer -> absmax[0] (float bits compare as unsigned for non-negative values)
+__global__ void h16_absmax_kernel(const float* __restrict__ W, int count, uint32_t* absmax) {
+  float mx = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    mx = fmaxf(mx, fabsf(W[i]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+  if ((threadIdx.x & 31) == 0 && isfinite(mx)) atomicMax(absmax, __float_as_uint(mx));
+}
+
+// Pack one Dense kernel W[K][N] (flax layout) into the block-major unit stream of one direction,
+// scaled by the power of two that puts max |W| in [2^10, 2^11).
+//   transposed == 0 (forward):  A rows r = output feature n, reduction kk = input feature k.
+//   transposed == 1 (adjoint):  A rows r = input feature k,  reduction kk = output feature n.
+__global__ void h16_pack_kernel(const float* __restrict__ W, int K, int N, int transposed,
+                                uint8_t* dst, int ksteps, const uint32_t* absmax, float* inv_scale) {
+  const float mx = __uint_as_float(*absmax);
+  float sc = 1.f;
+  if (mx > 0.f) {
+    const int e = (int)((__float_as_uint(mx) >> 23) & 0xFF) - 127;
+    int k = 10 - e;
+    k = k > 60 ? 60 : (k < -60 ? -60 : k);
+    sc = __uint_as_float((uint32_t)(k + 127) << 23);
+  }
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) *inv_scale = 1.f / sc;
+  if (idx >= K * N) return;
+  const int k = idx / N, o = idx - k * N;
+  const int r = transposed ? k : o, kk = transposed ? o : k;
+  __half hi, lo;
+  split_h1(W[idx] * sc, hi, lo);
+  const int b = r >> 7, rr = r & 127, j = kk >> 4, k16 = kk & 15;
+  uint8_t* p = dst + ((size_t)(b * ksteps + j) * 2) * H_UNIT + (k16 >> 3) * H_A_LBO + (rr >> 3) * H_A_SBO +
+               (rr & 7) * 16 + (k16 & 7) * 2;
+  *reinterpret_cast<__half*>(p) = hi;
+  *reinterpret_cast<__half*>(p + H_UNIT) = lo;
+}
+
+// ------------------------------------------------------------------------------------- host side
+struct H16State {
+  bool supported = false;
+  std::string why = "not initialised";
+  int dyn_dims[MAXL + 1], cost_dims[MAXL + 1], Ld = 0, Lc = 0;
+  uint8_t* d_stream = nullptr;
+  size_t stream_bytes = 0;
+  HDir dir[4];
+  float* d_bias = nullptr;     // forward biases, packed
+  float* d_scale = nullptr;    // [Ld + Lc] inverse weight scales
+  uint32_t* d_absmax = nullptr;
+  uint32_t hb_bytes = 0;
+  int nslot = 0;
+  size_t smem_bytes = 0;
+  int num_sms = 0;
+  int n = 0, m = 0, fout = 0;
+  int cluster = 4;
+  int max_clusters[5] = {0, 0, 0, 0, 0};
+  int last_cluster = 1;
+  long long* d_dbg = nullptr;
+};
+
+inline void h16_layer_geom(HLayer& Y, int M_true, int red_true) {
+  Y.M_true = M_true;
+  Y.nblk = (M_true + 127) / 128;
+  Y.ksteps = rup(red_true, 32) / 16;  // even: a ring group is two k-steps of one block
+  Y.next_kpad = rup(M_true, 16);
+  Y.bias = nullptr;
+  Y.gsrc = nullptr;
+  Y.inv_scale = nullptr;
+}
+
+inline size_t h16_build_geometry(H16State& S) {
+  size_t off = 0;
+  auto one = [&](const int* dims, int Ln, HDir& F, HDir& Bw) {
+    F.L = Bw.L = Ln;
+    F.pad_ = Bw.pad_ = 0;
+    for (int l = 0; l < Ln; ++l) {
+      h16_layer_geom(F.layer[l], dims[l + 1], dims[l]);
+      F.layer[l].gsrc = reinterpret_cast<const uint8_t*>(off);
+      off += (size_t)F.layer[l].nblk * F.layer[l].ksteps * H_BK_BYTES;
+    }
+    for (int i = 0; i < Ln; ++i) {
+      const int lt = Ln - 1 - i;
+      h16_layer_geom(Bw.layer[i], dims[lt], dims[lt + 1]);
+      Bw.layer[i].gsrc = reinterpret_cast<const uint8_t*>(off);
+      off += (size_t)Bw.layer[i].nblk * Bw.layer[i].ksteps * H_BK_BYTES;
+    }
+  };
+  one(S.dyn_dims, S.Ld, S.dir[DIR_DYN_F], S.dir[DIR_DYN_B]);
+  one(S.cost_dims, S.Lc, S.dir[DIR_COST_F], S.dir[DIR_COST_B]);
+  return off;
+}
+
+inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, const int* cost_dims,
+                      const cudaDeviceProp& prop) {
+  S.Ld = c.dyn_layers;
+  S.Lc = c.cost_layers;
+  for (int i = 0; i <= S.Ld; ++i) S.dyn_dims[i] = dyn_dims[i];
+  for (int i = 0; i <= S.Lc; ++i) S.cost_dims[i] = cost_dims[i];
+  S.num_sms = prop.multiProcessorCount;
+  S.n = c.n; S.m = c.m; S.fout = c.cost_fout;
+  int hmax = 16;
+  for (int i = 1; i < S.Ld; ++i) hmax = std::max(hmax, dyn_dims[i]);
+  for (int i = 1; i < S.Lc; ++i) hmax = std::max(hmax, cost_dims[i]);
+  S.supported = false;
+  if (S.Ld < 2) { S.why = "dynamics MLP has no hidden layer"; return GMPC_OK; }
+  if (hmax > 256) { S.why = "hidden width > 256 (two 128-row MMA blocks)"; return GMPC_OK; }
+  if (c.n + c.m > 32 || c.cost_fout > 32) { S.why = "n+m or fout > 32"; return GMPC_OK; }
+  S.hb_bytes = (uint32_t)(rup(hmax, 32) / 8) * H_B_LBO;
+  const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 256;
+  const HSmem L0 = h_smem_layout(0, S.hb_bytes, c.n, c.m, c.cost_fout);
+  int nslot = (int)((budget - std::min(budget, (size_t)L0.total + 128)) / H_SLOT_BYTES);
+  nslot = std::min(nslot, H_MAX_SLOTS);
+  if (const char* env = getenv("GMPC_H16_SLOTS")) nslot = std::min(nslot, std::max(2, atoi(env)));
+  if (nslot < 3) { S.why = "shared memory"; return GMPC_OK; }
+  S.nslot = nslot;
+  S.smem_bytes = h_smem_layout(nslot, S.hb_bytes, c.n, c.m, c.cost_fout).total + 128;
+  S.stream_bytes = h16_build_geometry(S);
+  size_t nbias = 0;
+  for (int l = 0; l < S.Ld; ++l) nbias += rup(dyn_dims[l + 1], 4);
+  for (int l = 0; l < S.Lc; ++l) nbias += rup(cost_dims[l + 1], 4);
+  if (cudaMalloc(&S.d_stream, S.stream_bytes + 4096) != cudaSuccess) return GMPC_E_CUDA;
+  if (cudaMemset(S.d_stream, 0, S.stream_bytes + 4096) != cudaSuccess) return GMPC_E_CUDA;
+  if (cudaMalloc(&S.d_bias, nbias * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
+  if (cudaMalloc(&S.d_scale, (S.Ld + S.Lc) * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
+  if (cudaMalloc(&S.d_absmax, (S.Ld + S.Lc) * sizeof(uint32_t)) != cudaSuccess) return GMPC_E_CUDA;
+  float* bp = S.d_bias;
+  for (int d = 0; d < 4; ++d)
+    for (int l = 0; l < S.dir[d].L; ++l)
+      S.dir[d].layer[l].gsrc = S.d_stream + reinterpret_cast<size_t>(S.dir[d].layer[l].gsrc);
+  for (int l = 0; l < S.Ld; ++l) {
+    S.dir[DIR_DYN_F].layer[l].bias = bp; bp += rup(dyn_dims[l + 1], 4);
+    S.dir[DIR_DYN_F].layer[l].inv_scale = S.d_scale + l;
+    S.dir[DIR_DYN_B].layer[S.Ld - 1 - l].inv_scale = S.d_scale + l;
+  }
+  for (int l = 0; l < S.Lc; ++l) {
+    S.dir[DIR_COST_F].layer[l].bias = bp; bp += rup(cost_dims[l + 1], 4);
+    S.dir[DIR_COST_F].layer[l].inv_scale = S.d_scale + S.Ld + l;
+    S.dir[DIR_COST_B].layer[S.Lc - 1 - l].inv_scale = S.d_scale + S.Ld + l;
+  }
+  if (cudaFuncSetAttribute(plan_h16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)S.smem_bytes) != cudaSuccess ||
+      cudaFuncSetAttribute(plan_h16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)S.smem_bytes) != cudaSuccess)
+    return GMPC_E_CUDA;
+  for (int C = 2; C <= 4; C *= 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(prop.multiProcessorCount / C * C);
+    cfg.blockDim = dim3(H_THREADS);
+    cfg.dynamicSmemBytes = S.smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, plan_h16_kernel<false>, &cfg) != cudaSuccess) nc = 0;
+    S.max_clusters[C] = nc;
+  }
+  cudaGetLastError();
+  if (const char* env = getenv("GMPC_TC_CLUSTER")) S.cluster = atoi(env);
+  if (S.cluster != 1 && S.cluster != 2 && S.cluster != 4) S.cluster = 4;
+  while (S.cluster > 1 && S.max_clusters[S.cluster] <= 0) S.cluster >>= 1;
+  if (getenv("GMPC_DEBUG")) {
+    cudaMalloc(&S.d_dbg, sizeof(long long) * 16 * 1024);
+    cudaMemset(S.d_dbg, 0, sizeof(long long) * 16 * 1024);
+    fprintf(stderr, "[gmpc] h16: smem %zu B, %d ring slots, max co-resident clusters: x2=%d x4=%d, using cluster=%d\n",
+            S.smem_bytes, S.nslot, S.max_clusters[2], S.max_clusters[4], S.cluster);
+  }
+  S.supported = true;
+  S.why = "";
+  return GMPC_OK;
+}
+
+inline void h16_destroy(H16State& S) {
+  cudaFree(S.d_stream);
+  cudaFree(S.d_bias);
+  cudaFree(S.d_scale);
+  cudaFree(S.d_absmax);
+  cudaFree(S.d_dbg);
+  S.d_stream = nullptr;
+  S.d_bias = nullptr;
+  S.d_scale = nullptr;
+  S.d_absmax = nullptr;
+  S.d_dbg = nullptr;
+}
+
+inline int h16_set_weights(H16State& S, const float* const* dyn_W, const float* const* dyn_b,
+                           const float* const* cost_W, const float* const* cost_b, cudaStream_t st,
+                           int64_t* launches) {
+  if (!S.supported) return GMPC_OK;
+  cudaMemsetAsync(S.d_absmax, 0, (S.Ld + S.Lc) * sizeof(uint32_t), st);
+  cudaMemsetAsync(S.d_stream, 0, S.stream_bytes, st);
+  auto one = [&](const int* dims, int Ln, const float* const* W, const float* const* b, HDir& F,
+                 HDir& Bw, int sbase) {
+    for (int l = 0; l < Ln; ++l) {
+      const int K = dims[l], N = dims[l + 1], blocks = (K * N + 255) / 256;
+      const HLayer& f = F.layer[l];
+      const HLayer& r = Bw.layer[Ln - 1 - l];
+      h16_absmax_kernel<<<std::min(blocks, 64), 256, 0, st>>>(W[l], K * N, S.d_absmax + sbase + l);
+      h16_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 0, const_cast<uint8_t*>(f.gsrc), f.ksteps,
+                                              S.d_absmax + sbase + l, S.d_scale + sbase + l);
+      h16_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 1, const_cast<uint8_t*>(r.gsrc), r.ksteps,
+                                              S.d_absmax + sbase + l, S.d_scale + sbase + l);
+      *launches += 3;
+      cudaMemcpyAsync(const_cast<float*>(f.bias), b[l], sizeof(float) * N, cudaMemcpyDeviceToDevice, st);
+    }
+  };
+  one(S.dyn_dims, S.Ld, dyn_W, dyn_b, S.dir[DIR_DYN_F], S.dir[DIR_DYN_B], 0);
+  one(S.cost_dims, S.Lc, cost_W, cost_b, S.dir[DIR_COST_F], S.dir[DIR_COST_B], S.Ld);
+  return cudaGetLastError() == cudaSuccess ? GMPC_OK : GMPC_E_CUDA;
+}
+
+// The tensor-core path needs a real dense contraction: at least two full tiles of trajectories
+// (batch tile >= 64) and hidden width >= 64 (north star).
+inline bool h16_worthwhile(const H16State& S, int64_t NQ) {
+  int hmin = 1 << 30;
+  for (int i = 1; i < S.Ld; ++i) hmin = std::min(hmin, S.dyn_dims[i]);
+  return NQ >= 64 && S.Ld > 1 && hmin >= 64;
+}
+
+inline int h16_launch(H16State& S, const PlanParams& P, cudaStream_t st, int64_t* launches) {
+  HParams Q;
+  memset(&Q, 0, sizeof(Q));
+  for (int d = 0; d < 4; ++d) Q.dir[d] = S.dir[d];
+  Q.n = P.n; Q.m = P.m; Q.T = P.T; Q.K = P.K;
+  Q.fout = P.fout; Q.mode = P.mode; Q.method = P.method; Q.iters = P.iters;
+  Q.use_cost = P.use_cost; Q.final_fwd = P.final_fwd;
+  Q.nslot = S.nslot;
+  Q.hb_bytes = S.hb_bytes;
+  if (const char* env = getenv("GMPC_H16_EXP")) Q.exp_ = (uint32_t)atoi(env);
+  Q.NQ = P.NQ;
+  Q.ntiles = (int)((P.NQ + H_NB - 1) / H_NB);
+  Q.lr = P.lr; Q.b1 = P.b1; Q.b2 = P.b2; Q.eps = P.eps;
+  Q.x0 = P.x0; Q.U_in = P.U_in; Q.goal = P.goal; Q.mpcw = P.mpcw;
+  Q.U_out = P.U_out; Q.X_out = P.X_out; Q.J_out = P.J_out; Q.dU_out = P.dU_out; Q.lam_out = P.lam_out;
+  Q.ws_X = P.ws_X; Q.ws_G = P.ws_G; Q.ws_U = P.ws_U; Q.ws_M = P.ws_M; Q.ws_V = P.ws_V;
+  Q.ws_mask = P.ws_mask;
+  Q.dbg = S.d_dbg;
+  if (Q.ntiles <= 0) return GMPC_OK;
+  int C = S.cluster;
+  while (C > 1 && Q.ntiles < C) C >>= 1;
+  const int max_ctas = C > 1 ? S.max_clusters[C] * C : S.num_sms;
+  int grid = std::min((Q.ntiles + C - 1) / C * C, max_ctas);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(H_THREADS);
+  cfg.dynamicSmemBytes = S.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = S.d_dbg != nullptr ? cudaLaunchKernelEx(&cfg, plan_h16_kernel<true>, Q)
+                                     : cudaLaunchKernelEx(&cfg, plan_h16_kernel<false>, Q);
+  ++*launches;
+  S.last_cluster = C;
+  if (S.d_dbg != nullptr && e == cudaSuccess) {
+    long long hdbg[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hdbg, S.d_dbg, sizeof(hdbg), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[gmpc] h16 CTA0 cycles: mma-warp wait_act %lld wait_full %lld issue %lld | compute wait_acc(hidden) %lld epilogue %lld wait_acc(final) %lld boundary %lld total %lld\n",
+            hdbg[0], hdbg[1], hdbg[2], hdbg[4], hdbg[5], hdbg[6], hdbg[8], hdbg[7]);
+  }
+  return e == cudaSuccess ? GMPC_OK : GMPC_E_CUDA;
+}
+
+}  // namespace gmpc

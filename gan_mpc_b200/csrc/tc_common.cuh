@@ -56,6 +56,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Address-based variants for hot loops: the caller converts the barrier pointer to a shared-window
+// address once (smem_u32) instead of paying the generic->shared conversion on every call.
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_a(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+// Polite wait for the many-thread consumers (epilogue warps): back off between probes so that
+// 256 polling threads do not flood the barrier unit that also has to retire the TMA complete_tx
+// and tcgen05.commit arrivals the tensor pipe is waiting behind.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  const uint32_t a = smem_u32(bar);
+  if (mbar_try_wait_a(a, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_a(a, parity)) {
+    __nanosleep(ns);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // ------------------------------------------------------------------------------ bulk copy (TMA engine, 1-D)
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
                                               uint64_t* bar) {
@@ -186,6 +222,18 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_a(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
 }
 
 // Same, arriving on the mbarrier at the same offset in every CTA of `cta_mask` (cluster).

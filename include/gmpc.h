@@ -41,6 +41,7 @@ extern "C" {
 #define GMPC_PATH_AUTO 0 /* tcgen05 when the tile is a real dense contraction, else FFMA */
 #define GMPC_PATH_FFMA 1 /* fp32 CUDA-core path (exact fp32 FMA arithmetic) */
 #define GMPC_PATH_TC 2   /* tcgen05 3xTF32 tensor-core path (error if shape unsupported) */
+#define GMPC_PATH_TC16 3 /* tcgen05 fp16-split (hi/lo, 3 products, fp32 accumulate) path, pipelined */
 
 typedef struct gmpc_config {
   int32_t n;             /* state size x_size                       (dynamics/nn.py:13 x_out) */
@@ -73,7 +74,7 @@ int64_t gmpc_critic_param_count(const gmpc_handle* h);
 
 /* Select the contraction path (GMPC_PATH_*).  Default AUTO. */
 int gmpc_set_path(gmpc_handle* h, int path);
-/* Which path the last plan/objective call actually used (GMPC_PATH_FFMA or GMPC_PATH_TC). */
+/* Which path the last plan/objective call actually used (GMPC_PATH_FFMA, _TC or _TC16). */
 int gmpc_last_path(const gmpc_handle* h);
 
 /* Stage model weights (copied and re-packed inside the handle; safe to free after return of
