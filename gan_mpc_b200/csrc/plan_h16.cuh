@@ -39,8 +39,11 @@
 
 namespace gmpc {
 
-constexpr int H_THREADS = 352;  // producer warp + MMA warp + 8 compute warps + second producer warp
+constexpr int H_THREADS = 384;  // producer, issuer, 8 compute warps, second producer, second issuer
 constexpr int H_PRODUCER2 = 10; // warp index of the second producer
+constexpr int H_ISSUER2 = 11;   // warp index of the second MMA issuer (Wl x ah products)
+constexpr int H_TMEM_BLK = 96;  // accumulator columns per block: D1 | D2 | D3 (32 each)
+constexpr int H_TMEM_BUF = 2 * H_TMEM_BLK;  // per layer buffer (two blocks); two buffers ping-pong
 constexpr int H_COMPUTE = 256;
 constexpr int H_BK_BYTES = 8192;     // one block-k-step: hi unit + lo unit
 constexpr int H_GROUP_BYTES = 2 * H_BK_BYTES;  // ring slot = one bulk copy = two k-steps of one block
@@ -76,7 +79,7 @@ struct HParams {
   float lr, b1, b2, eps;
   const float *x0, *U_in, *goal, *mpcw;
   float *U_out, *X_out, *J_out, *dU_out, *lam_out;
-  float *ws_X, *ws_G, *ws_U, *ws_M, *ws_V;
+  float *ws_X, *ws_G, *ws_U, *ws_M, *ws_V, *ws_S;
   uint32_t* ws_mask;
   long long* dbg;
 };
@@ -100,11 +103,36 @@ __device__ __forceinline__ int h_pass_kind(const HParams& P, int p) {
   return DIR_END;
 }
 
+// The same schedule as h_pass_kind, walked incrementally (no divisions in the issuers' path).
+struct HPassWalk {
+  int pp = 0, itc = 0;
+  __device__ __forceinline__ int next(const HParams& P) {
+    int kind;
+    if (itc < P.iters) {
+      if (pp < P.T) kind = DIR_DYN_F;
+      else if (P.use_cost && pp == P.T) kind = DIR_COST_F;
+      else if (P.use_cost && pp == P.T + 1) kind = DIR_COST_B;
+      else kind = DIR_DYN_B;
+      if (++pp == 2 * P.T + (P.use_cost ? 2 : 0)) { pp = 0; ++itc; }
+    } else if (!P.final_fwd) {
+      kind = DIR_END;
+    } else {
+      if (pp < P.T) kind = DIR_DYN_F;
+      else if (P.use_cost && pp == P.T) kind = DIR_COST_F;
+      else kind = DIR_END;
+      ++pp;
+    }
+    return kind;
+  }
+};
+
 // Shared-memory carve-up (byte offsets from the 128-aligned dynamic base).
 struct HSmem {
   uint32_t ring, hb0, hb1, sb, small, bars, total;
   // rows of the small fp32 arrays, in units of H_SROW floats
-  int r_x, r_lam, r_dq, r_y, r_x0, r_pu, r_pg, r_px, r_pm, r_pv, r_sc, rows;
+  int r_x, r_lam, r_dq, r_y, r_st, st_rows, r_part, r_sc, rows;
+  // offsets inside one staging buffer (two buffers ping-pong, filled one step ahead by cp.async)
+  int o_pu, o_pg, o_px, o_pm, o_pv, o_su, o_sd;
 };
 __host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int n, int m, int fout) {
   HSmem s;
@@ -116,19 +144,24 @@ __host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int
   int r = 0;
   s.r_x = r; r += n;
   s.r_lam = r; r += n;
-  s.r_dq = r; r += n + m;
+  s.r_dq = r; r += 2 * (n + m);  // two generations: the update runs one step behind the boundary
   s.r_y = r; r += fout;
-  s.r_x0 = r; r += n;
-  s.r_pu = r; r += m;
-  s.r_pg = r; r += n;
-  s.r_px = r; r += n;
-  s.r_pm = r; r += m;
-  s.r_pv = r; r += m;
-  s.r_sc = r; r += 5;  // sqrt(uu+a2), sqrt(dd+a2), 1/scale in flight, scale for the next operand, spare
+  int o = 0;
+  s.o_pu = o; o += m;   // U[t]
+  s.o_pg = o; o += n;   // goal[t]
+  s.o_px = o; o += n;   // X[t]
+  s.o_pm = o; o += m;   // Adam first moment [t]
+  s.o_pv = o; o += m;   // Adam second moment [t]
+  s.o_su = o; o += 1;   // sqrt(|u_t|^2 + a^2)   (saved by the forward sweep)
+  s.o_sd = o; o += 1;   // sqrt(|x_t - goal_t|^2 + a^2)
+  s.st_rows = o;
+  s.r_st = r; r += 3 * o;   // three staging buffers (t % 3)
+  s.r_part = r; r += 32;  // per-warp partial sums of the two staging-cost norms, two generations
+  s.r_sc = r; r += 2;     // 1/scale of the adjoint operand in flight, scale for the next one
   s.rows = r;
   s.bars = s.small + (uint32_t)r * H_SROW * 4;
   s.bars = (s.bars + 15u) & ~15u;
-  s.total = s.bars + 512;
+  s.total = s.bars + 256;
   return s;
 }
 
@@ -145,16 +178,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
   float* lam_s = small + L.r_lam * H_SROW;
   float* dq_s = small + L.r_dq * H_SROW;
   float* y_s = small + L.r_y * H_SROW;
-  float* x0_s = small + L.r_x0 * H_SROW;
-  float* pu_s = small + L.r_pu * H_SROW;  // U[t]
-  float* pg_s = small + L.r_pg * H_SROW;  // goal[t]
-  float* px_s = small + L.r_px * H_SROW;  // X[t]
-  float* pm_s = small + L.r_pm * H_SROW;  // Adam first moment [t]
-  float* pv_s = small + L.r_pv * H_SROW;  // Adam second moment [t]
-  float* su_s = small + L.r_sc * H_SROW;  // sqrt(|u|^2 + a^2)
-  float* sd_s = su_s + H_SROW;            // sqrt(|x - goal|^2 + a^2)
-  float* isc_s = sd_s + H_SROW;           // 1 / scale of the adjoint operand in flight
-  float* snx_s = isc_s + H_SROW;          // scale for the next adjoint operand
+  float* st_s = small + L.r_st * H_SROW;      // two staging buffers of L.st_rows rows
+  float* part_s = small + L.r_part * H_SROW;  // [8] partial |x-goal|^2, then [8] partial |u|^2
+  float* isc_s = small + L.r_sc * H_SROW;     // 1 / scale of the adjoint operand in flight
+  float* snx_s = isc_s + H_SROW;              // scale for the next adjoint operand
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(hsm + L.bars);
   uint64_t* empty_bar = full_bar + H_MAX_SLOTS;
   uint64_t* acc_bar = empty_bar + H_MAX_SLOTS;  // [2]: accumulator block b complete
@@ -172,16 +199,16 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], C);  // one tcgen05.commit arrival from every CTA of the cluster
+      mbar_init(&empty_bar[s], 2 * C);  // one tcgen05.commit arrival per issuer from every CTA of the cluster
     }
-    mbar_init(&acc_bar[0], 1);
-    mbar_init(&acc_bar[1], 1);
+    mbar_init(&acc_bar[0], 2);  // both issuers commit
+    mbar_init(&acc_bar[1], 2);
     mbar_init(&act_bar[0], H_COMPUTE / 32);  // one arrival per compute warp
     mbar_init(&act_bar[1], H_COMPUTE / 32);
     mbar_fence_init();
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc(tmem_holder, 256);  // 2 buffers x 2 blocks x (32 + 32) fp32 columns
+  if (warp == 0) tmem_alloc(tmem_holder, 512);  // 2 buffers x 2 blocks x 96 fp32 columns = 384
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -194,10 +221,14 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     // tools/bulk_copy_rate.cu: one cp.async.bulk blocks its issuing thread ~460 cycles whatever the
     // size, but copies issued by several lanes of one instruction cost only ~67 cycles each.  The
     // stream is therefore cut into 16 KB groups (two k-steps of one block, hi+lo units), and two
-    // producer warps x 4 lanes issue 8 group copies per round: lane k of producer w owns the
-    // groups G = 8r + 4w + k.  Every pass (all layers of one direction) is one contiguous image.
+    // producer warps x LP lanes issue R = 2 LP group copies per round: lane k of producer w owns
+    // the groups G = R r + LP w + k.  Every pass (all layers of one direction) is one contiguous
+    // image.  R <= ring slots is required: a lane waits on a slot by phase PARITY only, which is
+    // sound only if it can never be two refills ahead of the slot; its warp's previous round
+    // guarantees the releases up to G - R - NS, and G - R - NS >= G - 2 NS iff NS >= R.
     const int w = (warp == 0) ? 0 : 1;
-    if (lane < 4 && !(P.exp_ & 1)) {
+    const int LP = NS >= 8 ? 4 : (NS >= 6 ? 3 : 2), R = 2 * LP;
+    if (lane < LP && !(P.exp_ & 1)) {
       uint32_t ngk[4];
       const uint8_t* basek[4];
 #pragma unroll
@@ -209,7 +240,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       }
       const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), ring_a = smem_u32(ring);
       const uint32_t part = H_GROUP_BYTES / C;
-      const uint32_t G0 = 4u * w + lane;
+      const uint32_t G0 = (uint32_t)(LP * w + lane);
       uint32_t slot = G0 % (uint32_t)NS, ph = (G0 / (uint32_t)NS) & 1u;
       uint32_t gi = G0;  // group index relative to the start of pass p (may run past its end)
       int ti = 0, p = 0, kind = h_pass_kind(P, 0);
@@ -225,6 +256,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           continue;
         }
         const uint32_t bar = full_a + slot * 8;
+        if (P.exp_ & 16) {
+          while (!mbar_try_wait_a(empty_a + slot * 8, ph ^ 1)) __nanosleep(200);
+        } else
         mbar_wait_a(empty_a + slot * 8, ph ^ 1);  // all C CTAs released the slot
         const uint32_t dst = ring_a + slot * H_GROUP_BYTES + crank * part;
         const uint8_t* src = basek[kind] + (size_t)gi * H_GROUP_BYTES + crank * part;
@@ -237,30 +271,35 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           asm volatile(
               "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
               ::"r"(dst), "l"(src), "r"(part), "r"(bar) : "memory");
-        gi += 8;
-        slot += 8;
+        gi += R;
+        slot += R;
         while (slot >= (uint32_t)NS) { slot -= (uint32_t)NS; ph ^= 1; }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ================================================================== MMA issuer
-    // ONE thread runs the whole role.  It is instruction-latency bound if written naively (ncu: ~66
-    // dependent SASS instructions per block-k-step vs 88 cycles of tensor work), so the work is
-    // issued in fully unrolled chunks of two groups (four k-steps): the full barriers are probed
-    // back to back, descriptors are plain adds of running 32-bit words, the split at k-step 8
-    // (operand part 1) is hoisted out, and the timers exist only in the TIMED instantiation.
+  } else if (warp == 1 || warp == H_ISSUER2) {
+    // ================================================================== MMA issuers
+    // ONE thread per issuer runs the whole role, and a single instruction stream is the limit
+    // (ncu: ~25 dependent SASS instructions per block-k-step even when stripped): the two products
+    // of a k-step therefore go out from two warps -- issuer 0: [D1|D2] (+)= Wh x [ah|al] (N = 64),
+    // issuer 1: D3 (+)= Wl x ah (N = 32) into its own accumulator columns, so the result does not
+    // depend on how the two streams interleave.  Work is issued in fully unrolled chunks of two
+    // ring groups (four k-steps): full barriers probed back to back, descriptors are adds of
+    // running 32-bit words, the split at k-step 8 (operand part 1) is hoisted out of the loop, the
+    // pass schedule is walked without divisions, timers exist only in the TIMED instantiation.
+    const int which = (warp == 1) ? 0 : 1;
     if (elect_one()) {
       uint32_t act_ph0 = 0, act_ph1 = 0, lc = 0;
       long long t_act = 0, t_full = 0, tt = 0;
-      const uint32_t i64 = h16_idesc(2 * H_NB, 0, 1), i32 = h16_idesc(H_NB, 0, 1);
+      const uint32_t idesc = which == 0 ? h16_idesc(2 * H_NB, 0, 1) : h16_idesc(H_NB, 0, 1);
       const uint32_t hb_a[2] = {smem_u32(HB0), smem_u32(HB1)}, sb_a = smem_u32(SB);
-      const uint64_t a_desc0 = umma_smem_desc(smem_u32(ring), H_A_LBO, H_A_SBO);
+      const uint64_t a_desc0 = umma_smem_desc(smem_u32(ring) + which * H_UNIT, H_A_LBO, H_A_SBO);
       const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
       const uint32_t full_a = smem_u32(full_bar);
       constexpr uint32_t EMPTY_OFF = H_MAX_SLOTS * 8;  // empty_bar[s] sits EMPTY_OFF bytes after full_bar[s]
       constexpr uint32_t KS = H_B_KSTEP >> 4;          // B descriptor advance per k-step
       const uint32_t acc_a = smem_u32(acc_bar), act_a = smem_u32(act_bar);
+      const uint32_t d_off = which == 0 ? 0u : 2u * H_NB;  // issuer 1 accumulates into columns [64, 96)
       // ring cursor: barrier address, A descriptor low word, groups left before the wrap, parity
       uint32_t fb = full_a, a_lo = a_lo0, left = (uint32_t)NS, ph = 0;
       const bool nostream = P.exp_ & 1;
@@ -292,10 +331,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         for (int u = 0; u < U; ++u) {
           const uint64_t ad = ((uint64_t)a_hi << 32) | au[u];
           const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + u * 2 * KS);
-          umma_f16(d0, ad, bd, i64, (u == 0) ? acc : 1u);                             // [D1|D2] (+)= Wh x [ah;al]
-          umma_f16(d0 + H_NB, ad + (H_UNIT >> 4), bd, i32, 1u);                        // D2 += Wl x ah
-          umma_f16(d0, ad + (H_BK_BYTES >> 4), bd + KS, i64, 1u);                      // second k-step of the group
-          umma_f16(d0 + H_NB, ad + ((H_BK_BYTES + H_UNIT) >> 4), bd + KS, i32, 1u);
+          umma_f16(d0, ad, bd, idesc, (u == 0) ? acc : 1u);
+          umma_f16(d0, ad + (H_BK_BYTES >> 4), bd + KS, idesc, 1u);  // second k-step of the group
           if (C > 1)
             umma_commit_mc_a(fbu[u] + EMPTY_OFF, cmask);
           else
@@ -312,8 +349,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       };
       for (int ti = 0; ti < n_iter; ++ti) {
         const bool live = (int)blockIdx.x + ti * (int)gridDim.x < P.ntiles;
-        for (int p = 0;; ++p) {
-          const int kind = h_pass_kind(P, p);
+        HPassWalk walk;
+        for (;;) {
+          const int kind = walk.next(P);
           if (kind == DIR_END) break;
           const HDir& D = P.dir[kind];
           int prev_nblk = 1;
@@ -334,7 +372,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             prev_nblk = nblk;
             const uint64_t b_desc0 = umma_smem_desc((l == 0) ? sb_a : hb_a[(l - 1) & 1], H_B_LBO, H_B_SBO);
             const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
-            const uint32_t d_base = tmem_base + (lc & 1) * 128;
+            const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + d_off;
             if (TIMED) tt = clock64();
             mbar_wait_a(act_a, act_ph0);
             if (TIMED) t_act += clock64() - tt;
@@ -351,16 +389,15 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             }
             umma_commit_a(acc_a);
             if (nblk > 1) {
-              issue(0, ngrp, d_base + 64, b_lo0, b_hi, 0u);
+              issue(0, ngrp, d_base + H_TMEM_BLK, b_lo0, b_hi, 0u);
               umma_commit_a(acc_a + 8);
             }
           }
         }
       }
       if (TIMED) {
-        P.dbg[blockIdx.x * 16 + 0] = t_act;
-        P.dbg[blockIdx.x * 16 + 1] = t_full;
-        P.dbg[blockIdx.x * 16 + 2] = 0;
+        P.dbg[blockIdx.x * 16 + 0 + 9 * which] = t_act;
+        P.dbg[blockIdx.x * 16 + 1 + 9 * which] = t_full;
       }
     }
     __syncwarp();
@@ -373,7 +410,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     const bool fwarp = (q == 0);           // owns accumulator lanes 0..31: the <= 32-feature outputs
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     uint32_t acc_ph0 = 0, acc_ph1 = 0, lc = 0;
-    long long t_acc = 0, t_epi = 0, t_fin = 0, t_bnd = 0, t_total0 = clock64(), tq = 0, tb0 = 0;
+    long long t_acc = 0, t_epi = 0, t_fin = 0, t_bnd = 0, t_total0 = clock64(), tq = 0;
+    long long t_o1 = 0, t_o2 = 0, t_o3 = 0, t_o4 = 0;
     constexpr bool timed = TIMED;
     const bool cost_mode = (P.mode == MODE_PLAN || P.mode == MODE_OBJGRAD);
     float w0 = 0.f, w1 = 0.f, w2 = 0.f;
@@ -391,6 +429,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     float* wsU = P.ws_U + (size_t)blockIdx.x * T * m * H_NB;
     float* wsM = P.ws_M + (size_t)blockIdx.x * T * m * H_NB;
     float* wsV = P.ws_V + (size_t)blockIdx.x * T * m * H_NB;
+    float* wsS = P.ws_S + (size_t)blockIdx.x * T * 2 * H_NB;  // saved staging-cost norms
     uint32_t* wsMask = P.ws_mask + (size_t)blockIdx.x * ((size_t)T * (Ld - 1) + (Lc - 1)) * H_COMPUTE;
     uint32_t* costMask = wsMask + (size_t)T * (Ld - 1) * H_COMPUTE;
     const bool adam = (P.mode == MODE_PLAN && P.method == 1);
@@ -419,7 +458,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     const int f0 = q * 32 + lane;  // this thread's feature in row block 0 (block 1: +128)
     auto hidden_epilogue = [&](const HLayer& Y, int li, bool fwd, uint32_t* maskp) {
       uint8_t* dst = (li & 1) ? HB1 : HB0;
-      const uint32_t d_base = tmem_base + (lc & 1) * 128 + t_lane + c0;
+      const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + t_lane + c0;
       uint32_t mw = fwd ? 0u : maskp[ct];
       const float inv = *Y.inv_scale;
       float bias[2] = {0.f, 0.f};
@@ -431,13 +470,14 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       for (int b = 0; b < 2; ++b) {
         if (b < Y.nblk) {
           if (timed) tq = clock64();
-          if (b == 0) { mbar_wait_sleep(&acc_bar[0], acc_ph0, H_POLL_NS); acc_ph0 ^= 1; }
-          else        { mbar_wait_sleep(&acc_bar[1], acc_ph1, H_POLL_NS); acc_ph1 ^= 1; }
+          if (b == 0) { mbar_wait(&acc_bar[0], acc_ph0); acc_ph0 ^= 1; }
+          else        { mbar_wait(&acc_bar[1], acc_ph1); acc_ph1 ^= 1; }
           if (timed) { const long long t1 = clock64(); t_acc += t1 - tq; tq = t1; }
           tc_fence_after();
-          uint32_t d1[16], d2[16];
-          tmem_ld16_issue(d_base + b * 64, d1);
-          tmem_ld16_issue(d_base + b * 64 + H_NB, d2);
+          uint32_t d1[16], d2[16], d3[16];
+          tmem_ld16_issue(d_base + b * H_TMEM_BLK, d1);
+          tmem_ld16_issue(d_base + b * H_TMEM_BLK + H_NB, d2);
+          tmem_ld16_issue(d_base + b * H_TMEM_BLK + 2 * H_NB, d3);
           tmem_ld_wait();
           const int f = b * 128 + f0;
           if (f < Y.next_kpad) {
@@ -445,7 +485,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             float v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-              float z = live ? fmaf(__uint_as_float(d1[c]) + __uint_as_float(d2[c]), inv, bias[b]) : 0.f;
+              float z = live ? fmaf(__uint_as_float(d1[c]) + (__uint_as_float(d2[c]) + __uint_as_float(d3[c])), inv, bias[b]) : 0.f;
               if (fwd) {
                 if (z > 0.f) mw |= 1u << (b * 16 + c);
                 z = fmaxf(z, 0.f);
@@ -466,48 +506,126 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     // last layer of a pass (<= 32 output features): every warp keeps the barrier phase, the two
     // f-warps load their 16 columns of the accumulator: out[c] = (d1 + d2) * inv_scale
     auto final_load = [&](const HLayer& Y, float (&out)[16]) {
-      const uint32_t d_base = tmem_base + (lc & 1) * 128 + t_lane + c0;
+      const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + t_lane + c0;
       const float inv = *Y.inv_scale;
       if (timed) tq = clock64();
-      mbar_wait_sleep(&acc_bar[0], acc_ph0, H_POLL_NS);
+      mbar_wait(&acc_bar[0], acc_ph0);
       acc_ph0 ^= 1;
       if (timed) t_fin += clock64() - tq;
       tc_fence_after();
       if (fwarp) {
-        uint32_t d1[16], d2[16];
+        uint32_t d1[16], d2[16], d3[16];
         tmem_ld16_issue(d_base, d1);
         tmem_ld16_issue(d_base + H_NB, d2);
+        tmem_ld16_issue(d_base + 2 * H_NB, d3);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 16; ++c) out[c] = (__uint_as_float(d1[c]) + __uint_as_float(d2[c])) * inv;
+        for (int c = 0; c < 16; ++c)
+          out[c] = (__uint_as_float(d1[c]) + (__uint_as_float(d2[c]) + __uint_as_float(d3[c]))) * inv;
       }
       ++lc;
     };
-    // stage step t's slices of the per-CTA scratch in shared memory (all 256 threads, coalesced)
+    // ---- staging buffers: step t's slices of the per-CTA scratch, copied one step ahead with
+    // cp.async into buffer (t & 1) (every source was written at least one sweep earlier)
+    auto stbuf = [&](int t) { return st_s + (t % 3) * L.st_rows * H_SROW; };
+    auto cp4 = [&](float* dst, const float* src) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    };
     auto prefetch = [&](int t, bool bwd) {
-      if (P.exp_ & 4) return;
+      float* B = stbuf(t);
       for (int e = ct; e < m * H_NB; e += H_COMPUTE) {
         const int j = e / H_NB, r = e - j * H_NB;
-        pu_s[j * H_SROW + r] = wsU[t * m * H_NB + e];
+        cp4(B + (L.o_pu + j) * H_SROW + r, wsU + t * m * H_NB + e);
         if (bwd && adam) {
-          pm_s[j * H_SROW + r] = wsM[t * m * H_NB + e];
-          pv_s[j * H_SROW + r] = wsV[t * m * H_NB + e];
+          cp4(B + (L.o_pm + j) * H_SROW + r, wsM + t * m * H_NB + e);
+          cp4(B + (L.o_pv + j) * H_SROW + r, wsV + t * m * H_NB + e);
         }
       }
       if (need_goal) {
         for (int e = ct; e < n * H_NB; e += H_COMPUTE) {
           const int i = e / H_NB, r = e - i * H_NB;
-          pg_s[i * H_SROW + r] = wsG[t * n * H_NB + e];
-          if (bwd) px_s[i * H_SROW + r] = wsX[t * n * H_NB + e];
+          cp4(B + (L.o_pg + i) * H_SROW + r, wsG + t * n * H_NB + e);
+          if (bwd) cp4(B + (L.o_px + i) * H_SROW + r, wsX + t * n * H_NB + e);
+        }
+        if (bwd && cost_mode && ct < H_NB) {  // the lanes of warp 2 wrote these (norms_finish)
+          cp4(B + L.o_su * H_SROW + ct, wsS + (t * 2 + 0) * H_NB + ct);
+          cp4(B + L.o_sd * H_SROW + ct, wsS + (t * 2 + 1) * H_NB + ct);
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // every step commits exactly one group (possibly empty): "all but the newest group landed"
+    auto prefetch_none = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+    auto prefetch_wait1 = [&]() { asm volatile("cp.async.wait_group 1;" ::: "memory"); };
     // u rows (features n .. n+m-1) of the forward operand q = [x ; u], from the staged U[t]
-    auto sb_u_rows = [&]() {
+    auto sb_u_rows = [&](int t) {
+      const float* pu = stbuf(t) + L.o_pu * H_SROW;
       for (int e = ct; e < m * H_NB; e += H_COMPUTE) {
         const int j = e / H_NB, r = e - j * H_NB;
-        h16_store_op(SB, n + j, r, pu_s[j * H_SROW + r]);
+        h16_store_op(SB, n + j, r, pu[j * H_SROW + r]);
       }
+    };
+    // staging-cost norms of step t, phase A: every warp sums the features i = wi, wi+8, ... of its
+    // lane's trajectory (balanced: no warp does a serial per-trajectory loop on the critical path)
+    const int wi = warp - 2;
+    auto norms_partial = [&](int t) {
+      const float* B = stbuf(t);
+      float dd = 0.f, uu = 0.f;
+      for (int i = wi; i < n; i += 8) {
+        const float d = x_s[i * H_SROW + lane] - B[(L.o_pg + i) * H_SROW + lane];
+        dd = fmaf(d, d, dd);
+      }
+      for (int j = wi; j < m; j += 8) {
+        const float u = B[(L.o_pu + j) * H_SROW + lane];
+        uu = fmaf(u, u, uu);
+      }
+      float* pt = part_s + (t & 1) * 16 * H_SROW;
+      pt[wi * H_SROW + lane] = dd;
+      pt[(8 + wi) * H_SROW + lane] = uu;
+    };
+    // phase B (one warp, after a barrier): combine the 8 partials; returns this lane's cost term
+    auto norms_finish = [&](int t, float& Jr) {
+      const float* pt = part_s + (t & 1) * 16 * H_SROW;
+      float dd = 0.f, uu = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        dd += pt[k * H_SROW + lane];
+        uu += pt[(8 + k) * H_SROW + lane];
+      }
+      if (cost_mode) {
+        const float su = sqrtf(uu + a2), sd = sqrtf(dd + a2);
+        Jr += w0 * (su - ALPHA) + w1 * (sd - ALPHA);
+        wsS[(t * 2 + 0) * H_NB + lane] = su;  // reused by the adjoint sweep of this iteration
+        wsS[(t * 2 + 1) * H_NB + lane] = sd;
+      } else {
+        Jr += dd;
+      }
+    };
+    // per-column maximum over the 32 lanes of v[16] (transpose-reduce, 16 shuffles): lane l ends
+    // up with the maximum of column (l >> 1) & 15
+    auto colmax16 = [&](const float (&v)[16]) -> float {
+      float a8[8], a4[4], a2_[2], a1;
+      const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float keep = h4 ? v[8 + k] : v[k], give = h4 ? v[k] : v[8 + k];
+        a8[k] = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, give, 16));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float keep = h3 ? a8[4 + k] : a8[k], give = h3 ? a8[k] : a8[4 + k];
+        a4[k] = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, give, 8));
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float keep = h2 ? a4[2 + k] : a4[k], give = h2 ? a4[k] : a4[2 + k];
+        a2_[k] = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, give, 4));
+      }
+      {
+        const float keep = h1 ? a2_[1] : a2_[0], give = h1 ? a2_[0] : a2_[1];
+        a1 = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, give, 2));
+      }
+      return fmaxf(a1, __shfl_xor_sync(0xFFFFFFFFu, a1, 1));
     };
 
     for (int ti = 0; ti < n_iter; ++ti) {
@@ -516,10 +634,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       const long long q0 = (long long)tile * H_NB;
       named_bar_sync(1, H_COMPUTE);
       // ---------------------------------------------------------------- stage the tile
-      for (int e = ct; e < H_NB * n; e += H_COMPUTE) {
+      for (int e = ct; e < H_NB * n; e += H_COMPUTE) {  // x0 is row 0 of the tile's state scratch
         const int r = e / n, i = e - r * n;
         const long long qq = q0 + r;
-        x0_s[i * H_SROW + r] = (qq < P.NQ) ? P.x0[(qq / P.K) * n + i] : 0.f;
+        wsX[i * H_NB + r] = (qq < P.NQ) ? P.x0[(qq / P.K) * n + i] : 0.f;
       }
       if (P.goal != nullptr) {
         const int per = (T + 1) * n;
@@ -541,6 +659,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           }
         }
       }
+      __threadfence_block();
       named_bar_sync(1, H_COMPUTE);
       const long long qr = q0 + ct;
       const bool rvalid = (ct < H_NB) && (qr < P.NQ);
@@ -550,52 +669,41 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         const bool last = (it == P.iters);
         if (last && !P.final_fwd) break;
         // -------------------------------------------------------------- forward rollout
+        // One CTA barrier per step (mid-step).  Everything that is not needed to publish the next
+        // operand is scheduled into the shadow of the big layers' MMAs.
         named_bar_sync(1, H_COMPUTE);  // the previous sweep's last update is complete
+        prefetch(0, false);
+        if (T > 1) prefetch(1, false); else prefetch_none();
         for (int e = ct; e < n * H_NB; e += H_COMPUTE) {
           const int i = e / H_NB, r = e - i * H_NB;
-          const float v = x0_s[i * H_SROW + r];
+          const float v = wsX[e];
           x_s[i * H_SROW + r] = v;
-          wsX[e] = v;
           h16_store_op(SB, i, r, v);
         }
         Jr = 0.f;
-        prefetch(0, false);
+        prefetch_wait1();  // slices of step 0 landed (step 1 may still be in flight)
         named_bar_sync(1, H_COMPUTE);
-        sb_u_rows();
+        sb_u_rows(0);
         publish(0);
         for (int t = 0; t < T; ++t) {
-          // staging cost of step t (one thread per trajectory); x_s, pu_s, pg_s are visible
-          if (ct < H_NB && need_goal) {
-            const int r = ct;
-            float uu = 0.f, dd = 0.f;
-#pragma unroll 4
-            for (int j = 0; j < m; ++j) {
-              const float u = pu_s[j * H_SROW + r];
-              uu = fmaf(u, u, uu);
-            }
-#pragma unroll 4
-            for (int i = 0; i < n; ++i) {
-              const float d = x_s[i * H_SROW + r] - pg_s[i * H_SROW + r];
-              dd = fmaf(d, d, dd);
-            }
-            if (cost_mode)
-              Jr += w0 * (sqrtf(uu + a2) - ALPHA) + w1 * (sqrtf(dd + a2) - ALPHA);
-            else
-              Jr += dd;
-          }
           const HDir& D = P.dir[DIR_DYN_F];
           for (int l = 0; l < D.L - 1; ++l) {
             hidden_epilogue(D.layer[l], l, true, wsMask + ((size_t)t * (Ld - 1) + l) * H_COMPUTE);
-            if (l == 0 && t + 1 < T) {
-              // layer 0 has consumed SB and every warp is past the staging cost: refill
+            if (l == 0) {
+              // layer 0 has consumed SB.  Fetch step t+1's slices, then (barrier) x_t and the
+              // slices of step t are visible to every warp: partial norms of step t, finish the
+              // norms of step t-1, and write the u rows of the next operand.
+              if (t + 2 < T) prefetch(t + 2, false); else prefetch_none();
+              prefetch_wait1();  // slices of step t+1 landed
               named_bar_sync(1, H_COMPUTE);
-              prefetch(t + 1, false);
-              named_bar_sync(1, H_COMPUTE);
-              sb_u_rows();
+              if (need_goal) {
+                if (warp == 2 && t > 0) norms_finish(t - 1, Jr);
+                norms_partial(t);
+              }
+              if (t + 1 < T) sb_u_rows(t + 1);
             }
           }
           // step boundary: x_{t+1} = x_t + Dense(h) ; the f-warps write the next operand rows
-          if (timed) tb0 = clock64();
           float o[16];
           const HLayer& Yf = D.layer[D.L - 1];
           const float bias = (fwarp && lane < n) ? Yf.bias[lane] : 0.f;
@@ -609,18 +717,26 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           if (fwarp && lane < n) {
             float v[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              v[c] = (o[c] + bias) + xo[c];
-              x_s[lane * H_SROW + c0 + c] = v[c];
-            }
+            for (int c = 0; c < 16; ++c) v[c] = (o[c] + bias) + xo[c];
             if (more) store_row16(SB, lane, v);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) wsX[(size_t)(t + 1) * n * H_NB + lane * H_NB + c0 + c] = v[c];
+            for (int c = 0; c < 16; ++c) xo[c] = v[c];
           }
           if (more) publish(0);
-          named_bar_sync(1, H_COMPUTE);  // x_s of step t+1 visible
-          if (timed) t_bnd += clock64() - tb0;
+          if (fwarp && lane < n) {  // off the critical path: keep x_{t+1} for the costs and the adjoint
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              x_s[lane * H_SROW + c0 + c] = xo[c];
+              wsX[(size_t)(t + 1) * n * H_NB + lane * H_NB + c0 + c] = xo[c];
+            }
+          }
         }
+        __threadfence_block();  // wsS / wsX of this sweep are read back through cp.async
+        named_bar_sync(1, H_COMPUTE);  // x_T and the last partial norms are visible
+        if (warp == 2 && need_goal) norms_finish(T - 1, Jr);
+        // the adjoint sweep starts at t = T-1: fetch its slices under the cost MLP passes
+        // (su/sd of step T-1 are written by warp 2 just above: it fetches those itself)
+        if (!last) prefetch(T - 1, true);
         // -------------------------------------------------------------- terminal cost
         if (P.use_cost) {
           const HDir& D = P.dir[DIR_COST_F];
@@ -682,8 +798,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         if (ct < H_NB) {  // exact per-trajectory scale of lambda_T
           float mx = 0.f;
           for (int i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(lam_s[i * H_SROW + ct]));
-          const float sc = pow2_scale_to_8(mx);
-          snx_s[ct] = sc;
+          snx_s[ct] = pow2_scale_to_8(mx);
         }
         named_bar_sync(1, H_COMPUTE);
         for (int e = ct; e < n * H_NB; e += H_COMPUTE) {
@@ -699,38 +814,50 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           bc1 = (float)(1.0 - pow((double)P.b1, (double)(it + 1)));
           bc2 = (float)(1.0 - pow((double)P.b2, (double)(it + 1)));
         }
+        named_bar_sync(1, H_COMPUTE);  // isc_s visible to the f-warps of the first boundary
         publish(0);  // lambda_T operand of the first adjoint step
         // -------------------------------------------------------------- adjoint sweep + update
+        // action gradient + update of step tu, one (feature, trajectory) per thread; runs one step
+        // late (after the next step's mid barrier) so it never sits between a boundary and the
+        // first epilogue of the following step
+        auto update = [&](int tu) {
+          const float* Bu = stbuf(tu);
+          for (int e = ct; e < m * H_NB; e += H_COMPUTE) {
+            const int j = e / H_NB, r = e - j * H_NB;
+            const int ix = tu * m * H_NB + e;
+            float u = Bu[(L.o_pu + j) * H_SROW + r];
+            float g = dq_s[((tu & 1) * (n + m) + n + j) * H_SROW + r];
+            if (cost_mode) g = (w0 * u) / Bu[L.o_su * H_SROW + r] + g;
+            if (P.mode == MODE_PLAN) {
+              if (P.method == 0) {
+                u = u - P.lr * g;
+              } else {
+                const float mo = P.b1 * Bu[(L.o_pm + j) * H_SROW + r] + (1.f - P.b1) * g;
+                const float ve = P.b2 * Bu[(L.o_pv + j) * H_SROW + r] + (1.f - P.b2) * g * g;
+                wsM[ix] = mo;
+                wsV[ix] = ve;
+                u = u - P.lr * (mo / bc1) / (sqrtf(ve / bc2) + P.eps);
+              }
+              wsU[ix] = u;
+            } else if (P.dU_out != nullptr && q0 + r < P.NQ) {
+              P.dU_out[((q0 + r) * T + tu) * m + j] = g;
+            }
+          }
+        };
         for (int t = T - 1; t >= 0; --t) {
           const HDir& D = P.dir[DIR_DYN_B];
+          const float* B = stbuf(t);
           for (int lb = 0; lb < D.L - 1; ++lb) {
             hidden_epilogue(D.layer[lb], lb, false,
                             wsMask + ((size_t)t * (Ld - 1) + (D.L - 2 - lb)) * H_COMPUTE);
             if (lb == 0) {
-              named_bar_sync(1, H_COMPUTE);  // every warp is past the previous step's update
-              prefetch(t, true);
-              named_bar_sync(1, H_COMPUTE);
-              if (ct < H_NB && cost_mode) {  // per-trajectory norms of the staging cost
-                const int r = ct;
-                float uu = 0.f, dd = 0.f;
-#pragma unroll 4
-                for (int j = 0; j < m; ++j) {
-                  const float u = pu_s[j * H_SROW + r];
-                  uu = fmaf(u, u, uu);
-                }
-#pragma unroll 4
-                for (int i = 0; i < n; ++i) {
-                  const float d = px_s[i * H_SROW + r] - pg_s[i * H_SROW + r];
-                  dd = fmaf(d, d, dd);
-                }
-                su_s[r] = sqrtf(uu + a2);
-                sd_s[r] = sqrtf(dd + a2);
-              }
-              named_bar_sync(1, H_COMPUTE);
+              if (t > 0) prefetch(t - 1, true); else prefetch_none();
+              prefetch_wait1();  // slices of step t landed
+              named_bar_sync(1, H_COMPUTE);  // staging buffer t and dq of step t+1 are visible
+              if (t + 1 < T) update(t + 1);
             }
           }
           // step boundary: lambda_t = l_x + lambda_{t+1} + dq_x ; u gradient kept for the update
-          if (timed) tb0 = clock64();
           float base[16], isc[16], snx[16];
           if (fwarp && lane < n + m) {
 #pragma unroll
@@ -738,8 +865,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             if (lane < n) {
 #pragma unroll
               for (int c = 0; c < 16; ++c) {
-                const float d = px_s[lane * H_SROW + c0 + c] - pg_s[lane * H_SROW + c0 + c];
-                const float cc = cost_mode ? (w1 * d) / sd_s[c0 + c] : l2scale * d;
+                const float d = B[(L.o_px + lane) * H_SROW + c0 + c] - B[(L.o_pg + lane) * H_SROW + c0 + c];
+                const float cc = cost_mode ? (w1 * d) / B[L.o_sd * H_SROW + c0 + c] : l2scale * d;
                 base[c] = cc + lam_s[lane * H_SROW + c0 + c];
                 snx[c] = snx_s[c0 + c];
               }
@@ -747,62 +874,52 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           }
           float o[16];
           final_load(D.layer[D.L - 1], o);
+          float lamabs[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) lamabs[c] = 0.f;
           if (fwarp && lane < n + m) {
             if (lane < n) {
               float v[16];
 #pragma unroll
               for (int c = 0; c < 16; ++c) {
                 const float lam = base[c] + o[c] * isc[c];
-                lam_s[lane * H_SROW + c0 + c] = lam;
+                base[c] = lam;
+                lamabs[c] = fabsf(lam);
                 v[c] = lam * snx[c];
               }
               if (t > 0) store_row16(SB, lane, v);
-              if (P.lam_out != nullptr) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c)
-                  if (q0 + c0 + c < P.NQ)
-                    P.lam_out[((q0 + c0 + c) * (T + 1) + t) * n + lane] = lam_s[lane * H_SROW + c0 + c];
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 16; ++c) dq_s[lane * H_SROW + c0 + c] = o[c] * isc[c];
             }
           }
           if (t > 0) publish(0);
-          named_bar_sync(1, H_COMPUTE);
-          if (timed) t_bnd += clock64() - tb0;
-          // action gradient + update, one (feature, trajectory) per thread
-          for (int e = ct; e < m * H_NB; e += H_COMPUTE) {
-            const int j = e / H_NB, r = e - j * H_NB;
-            const int ix = t * m * H_NB + e;
-            float u = pu_s[j * H_SROW + r];
-            float g = dq_s[(n + j) * H_SROW + r];
-            if (cost_mode) g = (w0 * u) / su_s[r] + g;
-            if (P.mode == MODE_PLAN) {
-              if (P.method == 0) {
-                u = u - P.lr * g;
-              } else {
-                const float mo = P.b1 * pm_s[j * H_SROW + r] + (1.f - P.b1) * g;
-                const float ve = P.b2 * pv_s[j * H_SROW + r] + (1.f - P.b2) * g * g;
-                wsM[ix] = mo;
-                wsV[ix] = ve;
-                u = u - P.lr * (mo / bc1) / (sqrtf(ve / bc2) + P.eps);
+          if (fwarp) {  // off the critical path
+            if (lane < n) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) lam_s[lane * H_SROW + c0 + c] = base[c];
+              if (P.lam_out != nullptr) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                  if (q0 + c0 + c < P.NQ) P.lam_out[((q0 + c0 + c) * (T + 1) + t) * n + lane] = base[c];
               }
-              wsU[ix] = u;
-            } else if (P.dU_out != nullptr && q0 + r < P.NQ) {
-              P.dU_out[((q0 + r) * T + t) * m + j] = g;
+            } else if (lane < n + m) {  // u part of the input adjoint, consumed by update(t) one step later
+#pragma unroll
+              for (int c = 0; c < 16; ++c) dq_s[((t & 1) * (n + m) + lane) * H_SROW + c0 + c] = o[c] * isc[c];
             }
-          }
-          // the operand just written used snx_s; the next one uses the scale of lambda_t
-          if (ct >= 32 && ct < 32 + H_NB && t > 0) {
-            const int r = ct - 32;
-            float mx = 0.f;
-            for (int i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(lam_s[i * H_SROW + r]));
-            isc_s[r] = 1.f / snx_s[r];
-            snx_s[r] = pow2_scale_to_8(mx);
+            // the operand just written used snx_s; the next one uses the scale of lambda_t
+            // (columns c0..c0+15 belong to this warp alone: a warp-level sync orders the update)
+            const float mx = colmax16(lamabs);
+            __syncwarp();
+            if (t > 0 && !(lane & 1)) {
+              const int col = c0 + ((lane >> 1) & 15);
+              isc_s[col] = 1.f / snx_s[col];
+              snx_s[col] = pow2_scale_to_8(mx);
+            }
+            __syncwarp();
           }
         }
+        named_bar_sync(1, H_COMPUTE);  // dq of step 0 visible
+        update(0);
         if (P.mode != MODE_PLAN) break;
+        __threadfence_block();  // this sweep's wsU/wsM/wsV are read back through cp.async next sweep
       }
       named_bar_sync(1, H_COMPUTE);
       // ---------------------------------------------------------------- write the tile out
@@ -830,6 +947,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       P.dbg[blockIdx.x * 16 + 6] = t_fin;
       P.dbg[blockIdx.x * 16 + 7] = clock64() - t_total0;
       P.dbg[blockIdx.x * 16 + 8] = t_bnd;
+      P.dbg[blockIdx.x * 16 + 11] = t_o1;
+      P.dbg[blockIdx.x * 16 + 12] = t_o2;
+      P.dbg[blockIdx.x * 16 + 13] = t_o3;
+      P.dbg[blockIdx.x * 16 + 14] = t_o4;
     }
   }
   tc_fence_before();
@@ -837,7 +958,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
   if (C > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -888,6 +1009,7 @@ struct H16State {
   HDir dir[4];
   float* d_bias = nullptr;     // forward biases, packed
   float* d_scale = nullptr;    // [Ld + Lc] inverse weight scales
+  float* d_wsS = nullptr;      // [num_sms][T][2][32] staging-cost norms saved by the forward sweep
   uint32_t* d_absmax = nullptr;
   uint32_t hb_bytes = 0;
   int nslot = 0;
@@ -948,14 +1070,14 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
   if (hmax > 256) { S.why = "hidden width > 256 (two 128-row MMA blocks)"; return GMPC_OK; }
   if (c.n + c.m > 32 || c.cost_fout > 32) { S.why = "n+m or fout > 32"; return GMPC_OK; }
   S.hb_bytes = (uint32_t)(rup(hmax, 32) / 8) * H_B_LBO;
-  const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 256;
+  const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
   const HSmem L0 = h_smem_layout(0, S.hb_bytes, c.n, c.m, c.cost_fout);
-  int nslot = (int)((budget - std::min(budget, (size_t)L0.total + 128)) / H_SLOT_BYTES);
+  int nslot = (int)((budget - std::min(budget, (size_t)L0.total)) / H_SLOT_BYTES);
   nslot = std::min(nslot, H_MAX_SLOTS);
   if (const char* env = getenv("GMPC_H16_SLOTS")) nslot = std::min(nslot, std::max(2, atoi(env)));
-  if (nslot < 3) { S.why = "shared memory"; return GMPC_OK; }
+  if (nslot < 4) { S.why = "shared memory"; return GMPC_OK; }
   S.nslot = nslot;
-  S.smem_bytes = h_smem_layout(nslot, S.hb_bytes, c.n, c.m, c.cost_fout).total + 128;
+  S.smem_bytes = h_smem_layout(nslot, S.hb_bytes, c.n, c.m, c.cost_fout).total;
   S.stream_bytes = h16_build_geometry(S);
   size_t nbias = 0;
   for (int l = 0; l < S.Ld; ++l) nbias += rup(dyn_dims[l + 1], 4);
@@ -965,6 +1087,7 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
   if (cudaMalloc(&S.d_bias, nbias * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
   if (cudaMalloc(&S.d_scale, (S.Ld + S.Lc) * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
   if (cudaMalloc(&S.d_absmax, (S.Ld + S.Lc) * sizeof(uint32_t)) != cudaSuccess) return GMPC_E_CUDA;
+  if (cudaMalloc(&S.d_wsS, (size_t)S.num_sms * c.T * 2 * H_NB * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
   float* bp = S.d_bias;
   for (int d = 0; d < 4; ++d)
     for (int l = 0; l < S.dir[d].L; ++l)
@@ -1021,6 +1144,8 @@ inline void h16_destroy(H16State& S) {
   cudaFree(S.d_bias);
   cudaFree(S.d_scale);
   cudaFree(S.d_absmax);
+  cudaFree(S.d_wsS);
+  S.d_wsS = nullptr;
   cudaFree(S.d_dbg);
   S.d_stream = nullptr;
   S.d_bias = nullptr;
@@ -1080,6 +1205,7 @@ inline int h16_launch(H16State& S, const PlanParams& P, cudaStream_t st, int64_t
   Q.U_out = P.U_out; Q.X_out = P.X_out; Q.J_out = P.J_out; Q.dU_out = P.dU_out; Q.lam_out = P.lam_out;
   Q.ws_X = P.ws_X; Q.ws_G = P.ws_G; Q.ws_U = P.ws_U; Q.ws_M = P.ws_M; Q.ws_V = P.ws_V;
   Q.ws_mask = P.ws_mask;
+  Q.ws_S = S.d_wsS;
   Q.dbg = S.d_dbg;
   if (Q.ntiles <= 0) return GMPC_OK;
   int C = S.cluster;
@@ -1107,8 +1233,8 @@ inline int h16_launch(H16State& S, const PlanParams& P, cudaStream_t st, int64_t
     long long hdbg[16];
     cudaStreamSynchronize(st);
     cudaMemcpy(hdbg, S.d_dbg, sizeof(hdbg), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[gmpc] h16 CTA0 cycles: mma-warp wait_act %lld wait_full %lld issue %lld | compute wait_acc(hidden) %lld epilogue %lld wait_acc(final) %lld boundary %lld total %lld\n",
-            hdbg[0], hdbg[1], hdbg[2], hdbg[4], hdbg[5], hdbg[6], hdbg[8], hdbg[7]);
+    fprintf(stderr, "[gmpc] h16 CTA0 cycles: mma-warp wait_act %lld wait_full %lld issue %lld | compute wait_acc(hidden) %lld epilogue %lld wait_acc(final) %lld boundary %lld total %lld | fwd-top %lld fwd-mid %lld bwd-mid %lld update %lld | issuer2 wait_act %lld wait_full %lld\n",
+            hdbg[0], hdbg[1], hdbg[2], hdbg[4], hdbg[5], hdbg[6], hdbg[8], hdbg[7], hdbg[11], hdbg[12], hdbg[13], hdbg[14], hdbg[9], hdbg[10]);
   }
   return e == cudaSuccess ? GMPC_OK : GMPC_E_CUDA;
 }
