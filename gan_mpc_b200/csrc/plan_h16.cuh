@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     const int which = (warp == 1) ? 0 : 1;
     if (elect_one()) {
       uint32_t act_ph0 = 0, act_ph1 = 0, lc = 0;
-      long long t_act = 0, t_full = 0, tt = 0;
+      long long t_act = 0, t_full = 0, tt = 0, t_actl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       const uint32_t idesc = which == 0 ? h16_idesc(2 * H_NB, 0, 1) : h16_idesc(H_NB, 0, 1);
       const uint32_t hb_a[2] = {smem_u32(HB0), smem_u32(HB1)}, sb_a = smem_u32(SB);
       const uint64_t a_desc0 = umma_smem_desc(smem_u32(ring) + which * H_UNIT, H_A_LBO, H_A_SBO);
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + d_off;
             if (TIMED) tt = clock64();
             mbar_wait_a(act_a, act_ph0);
-            if (TIMED) t_act += clock64() - tt;
+            if (TIMED) { const long long dt = clock64() - tt; t_act += dt; if (kind == DIR_DYN_F || kind == DIR_DYN_B) t_actl[l & 3] += dt; }
             act_ph0 ^= 1;
             // block 0: groups [0, 4) (k-steps 0..7) need operand part 0 only; the rest need part 1
             const int gsplit = two_parts ? 4 : ngrp;
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             if (two_parts) {
               if (TIMED) tt = clock64();
               mbar_wait_a(act_a + 8, act_ph1);
-              if (TIMED) t_act += clock64() - tt;
+              if (TIMED) { const long long dt = clock64() - tt; t_act += dt; if (kind == DIR_DYN_F || kind == DIR_DYN_B) t_actl[4 + (l & 3)] += dt; }
               act_ph1 ^= 1;
               issue(4, ngrp, d_base, b_lo0 + 8 * KS, b_hi, 1u);
             }
@@ -398,6 +398,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       if (TIMED) {
         P.dbg[blockIdx.x * 16 + 0 + 9 * which] = t_act;
         P.dbg[blockIdx.x * 16 + 1 + 9 * which] = t_full;
+        if (which == 0 && blockIdx.x == 0)
+          printf("[gmpc] h16 issuer wait_act by dyn layer (part0 | part1): %lld %lld %lld %lld | %lld %lld %lld %lld\n",
+                 t_actl[0], t_actl[1], t_actl[2], t_actl[3], t_actl[4], t_actl[5], t_actl[6], t_actl[7]);
       }
     }
     __syncwarp();
