@@ -31,6 +31,7 @@
 
 #include <string>
 #include <type_traits>
+#include <vector>
 
 #include "../../include/gmpc.h"
 #include "common.cuh"
@@ -61,8 +62,10 @@ struct HLayer {
   const float* inv_scale;  // device scalar: 1 / (power-of-two weight scale of this layer)
   int M_true;              // output features of this (possibly transposed) layer
   int nblk;                // 128-row blocks
-  int ksteps;              // reduction length / 16
+  int ksteps;              // reduction length / 16 (may be odd: the last group of a block is then one k-step)
   int next_kpad;           // round_up(M_true, 16): features the epilogue defines in the next operand
+  int rows[2];             // stored A rows of block 0 / 1 (multiple of 16, >= 32, <= 128): the MMA reads
+                           // 128 rows, the rows past rows[b] alias later bytes and land in unused lanes
 };
 struct HDir {
   HLayer layer[MAXL];
@@ -75,6 +78,8 @@ struct HParams {
   int n, m, T, K;
   int fout, mode, method, iters, use_cost, final_fwd, ntiles, nslot;
   uint32_t hb_bytes, exp_;  // exp_: timing experiments (GMPC_H16_EXP), results are garbage when set
+  const uint2* gtab[4];     // per pass: {byte offset in the pass image, bytes} of every ring group
+  uint32_t ngroups[4];
   long long NQ;
   float lr, b1, b2, eps;
   const float *x0, *U_in, *goal, *mpcw;
@@ -128,13 +133,13 @@ struct HPassWalk {
 
 // Shared-memory carve-up (byte offsets from the 128-aligned dynamic base).
 struct HSmem {
-  uint32_t ring, hb0, hb1, sb, small, bars, total;
+  uint32_t ring, hb0, hb1, sb, small, gtab, bars, total;
   // rows of the small fp32 arrays, in units of H_SROW floats
   int r_x, r_lam, r_dq, r_y, r_st, st_rows, r_part, r_sc, rows;
   // offsets inside one staging buffer (two buffers ping-pong, filled one step ahead by cp.async)
   int o_pu, o_pg, o_px, o_pm, o_pv, o_su, o_sd;
 };
-__host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int n, int m, int fout) {
+__host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int n, int m, int fout, int ngroups_total) {
   HSmem s;
   s.ring = 0;
   s.hb0 = (uint32_t)nslot * H_SLOT_BYTES;
@@ -159,7 +164,9 @@ __host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int
   s.r_part = r; r += 32;  // per-warp partial sums of the two staging-cost norms, two generations
   s.r_sc = r; r += 2;     // 1/scale of the adjoint operand in flight, scale for the next one
   s.rows = r;
-  s.bars = s.small + (uint32_t)r * H_SROW * 4;
+  s.gtab = s.small + (uint32_t)r * H_SROW * 4;
+  s.gtab = (s.gtab + 15u) & ~15u;
+  s.bars = s.gtab + (uint32_t)ngroups_total * 8;
   s.bars = (s.bars + 15u) & ~15u;
   s.total = s.bars + 256;
   return s;
@@ -168,7 +175,8 @@ __host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int
 template <bool TIMED>
 __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_constant__ HParams P) {
   extern __shared__ __align__(128) uint8_t hsm[];
-  const HSmem L = h_smem_layout(P.nslot, P.hb_bytes, P.n, P.m, P.fout);
+  const HSmem L = h_smem_layout(P.nslot, P.hb_bytes, P.n, P.m, P.fout,
+                                (int)(P.ngroups[0] + P.ngroups[1] + P.ngroups[2] + P.ngroups[3]));
   uint8_t* ring = hsm + L.ring;
   uint8_t* HB0 = hsm + L.hb0;
   uint8_t* HB1 = hsm + L.hb1;
@@ -195,7 +203,15 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
   const int n_iter = (P.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;  // uniform per cluster
 
   // zero all operand / scratch memory once: padded features must stay finite
-  for (uint32_t i = tid * 4; i < L.bars; i += H_THREADS * 4) *reinterpret_cast<uint32_t*>(hsm + i) = 0u;
+  for (uint32_t i = tid * 4; i < L.gtab; i += H_THREADS * 4) *reinterpret_cast<uint32_t*>(hsm + i) = 0u;
+  {  // group tables of the four passes -> shared memory (the producers index them every copy)
+    uint2* gt = reinterpret_cast<uint2*>(hsm + L.gtab);
+    uint32_t o = 0;
+    for (int k = 0; k < 4; ++k) {
+      for (uint32_t i = tid; i < P.ngroups[k]; i += H_THREADS) gt[o + i] = P.gtab[k][i];
+      o += P.ngroups[k];
+    }
+  }
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -231,15 +247,18 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     if (lane < LP && !(P.exp_ & 1)) {
       uint32_t ngk[4];
       const uint8_t* basek[4];
+      const uint2* gtk[4];
+      {
+        const uint2* gt = reinterpret_cast<const uint2*>(hsm + L.gtab);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t ng = 0;
-        for (int l = 0; l < P.dir[k].L; ++l) ng += (uint32_t)(P.dir[k].layer[l].nblk * P.dir[k].layer[l].ksteps) >> 1;
-        ngk[k] = ng;
-        basek[k] = P.dir[k].layer[0].gsrc;
+        for (int k = 0; k < 4; ++k) {
+          ngk[k] = P.ngroups[k];
+          basek[k] = P.dir[k].layer[0].gsrc;
+          gtk[k] = gt;
+          gt += P.ngroups[k];
+        }
       }
       const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), ring_a = smem_u32(ring);
-      const uint32_t part = H_GROUP_BYTES / C;
       const uint32_t G0 = (uint32_t)(LP * w + lane);
       uint32_t slot = G0 % (uint32_t)NS, ph = (G0 / (uint32_t)NS) & 1u;
       uint32_t gi = G0;  // group index relative to the start of pass p (may run past its end)
@@ -260,9 +279,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           while (!mbar_try_wait_a(empty_a + slot * 8, ph ^ 1)) __nanosleep(200);
         } else
         mbar_wait_a(empty_a + slot * 8, ph ^ 1);  // all C CTAs released the slot
+        const uint2 ge = gtk[kind][gi];         // {offset, bytes}; bytes is a multiple of 64 * C
+        const uint32_t part = ge.y / C;
         const uint32_t dst = ring_a + slot * H_GROUP_BYTES + crank * part;
-        const uint8_t* src = basek[kind] + (size_t)gi * H_GROUP_BYTES + crank * part;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)H_GROUP_BYTES) : "memory");
+        const uint8_t* src = basek[kind] + ge.x + crank * part;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ge.y) : "memory");
         if (C > 1)
           asm volatile(
               "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
@@ -290,22 +311,30 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     const int which = (warp == 1) ? 0 : 1;
     if (elect_one()) {
       uint32_t act_ph0 = 0, act_ph1 = 0, lc = 0;
-      long long t_act = 0, t_full = 0, tt = 0, t_actl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long t_act = 0, t_full = 0, tt = 0, t_actl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_iss1 = 0, n_iss1 = 0, tl0 = 0, t_b0a = 0, t_b0b = 0, t_p1 = 0, t_b1 = 0, tl1 = 0;
       const uint32_t idesc = which == 0 ? h16_idesc(2 * H_NB, 0, 1) : h16_idesc(H_NB, 0, 1);
       const uint32_t hb_a[2] = {smem_u32(HB0), smem_u32(HB1)}, sb_a = smem_u32(SB);
-      const uint64_t a_desc0 = umma_smem_desc(smem_u32(ring) + which * H_UNIT, H_A_LBO, H_A_SBO);
+      const uint64_t a_desc0 = umma_smem_desc(smem_u32(ring), 0, H_A_SBO);
       const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
       const uint32_t full_a = smem_u32(full_bar);
       constexpr uint32_t EMPTY_OFF = H_MAX_SLOTS * 8;  // empty_bar[s] sits EMPTY_OFF bytes after full_bar[s]
       constexpr uint32_t KS = H_B_KSTEP >> 4;          // B descriptor advance per k-step
       const uint32_t acc_a = smem_u32(acc_bar), act_a = smem_u32(act_bar);
       const uint32_t d_off = which == 0 ? 0u : 2u * H_NB;  // issuer 1 accumulates into columns [64, 96)
-      // ring cursor: barrier address, A descriptor low word, groups left before the wrap, parity
+      // ring cursor: barrier address, A descriptor low word of the slot start, slots left, parity
       uint32_t fb = full_a, a_lo = a_lo0, left = (uint32_t)NS, ph = 0;
       const bool nostream = P.exp_ & 1;
-      // issue U consecutive groups (2U k-steps) of one block, fully unrolled
-      auto chunk = [&](auto Utag, uint32_t d0, uint32_t b_lo, uint32_t b_hi, uint32_t acc) {
+      // loop invariants the compiler would otherwise re-derive from special registers / the
+      // constant bank inside every chunk (S2UR SR_CgaSize -> UIMAD -> LDCU chains in the SASS)
+      uint32_t NSr = (uint32_t)NS, mc = C > 1 ? 1u : 0u, cmask_r = cmask, full_r = full_a, alo0_r = a_lo0;
+      asm volatile("" : "+r"(NSr), "+r"(mc), "+r"(cmask_r), "+r"(full_r), "+r"(alo0_r));
+      // per-block A geometry (set by the layer loop): low-word addend that selects this issuer's unit
+      // and carries the LBO field, and the descriptor advance from the first to the second k-step
+      uint32_t a_blk = 0, a_k2 = 0;
+      // issue U consecutive groups of one block, fully unrolled; the last one holds NKL k-steps
+      auto chunk = [&](auto Utag, auto NKLtag, uint32_t d0, uint32_t b_lo, uint32_t b_hi, uint32_t acc) {
         constexpr int U = decltype(Utag)::value;
+        constexpr int NKL = decltype(NKLtag)::value;
         uint32_t fbu[U], au[U], phu[U];
         bool oku[U];
 #pragma unroll
@@ -313,7 +342,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           fbu[u] = fb; au[u] = a_lo; phu[u] = ph;
           fb += 8;
           a_lo += (H_GROUP_BYTES >> 4);
-          if (--left == 0) { fb = full_a; a_lo = a_lo0; left = (uint32_t)NS; ph ^= 1; }
+          if (--left == 0) { fb = full_r; a_lo = alo0_r; left = NSr; ph ^= 1; }
         }
         if (!nostream) {
 #pragma unroll
@@ -329,23 +358,26 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         tc_fence_after();
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const uint64_t ad = ((uint64_t)a_hi << 32) | au[u];
+          const uint64_t ad = ((uint64_t)a_hi << 32) | (au[u] + a_blk);
           const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + u * 2 * KS);
           umma_f16(d0, ad, bd, idesc, (u == 0) ? acc : 1u);
-          umma_f16(d0, ad + (H_BK_BYTES >> 4), bd + KS, idesc, 1u);  // second k-step of the group
-          if (C > 1)
-            umma_commit_mc_a(fbu[u] + EMPTY_OFF, cmask);
+          if (u + 1 < U || NKL == 2) umma_f16(d0, ad + a_k2, bd + KS, idesc, 1u);  // second k-step of the group
+          if (mc)
+            umma_commit_mc_a(fbu[u] + EMPTY_OFF, (uint16_t)cmask_r);
           else
             umma_commit_a(fbu[u] + EMPTY_OFF);
         }
       };
-      // issue groups [g0, g1) of one block: d0 = accumulator columns, b_lo = B descriptor of group g0
-      auto issue = [&](int g0, int g1, uint32_t d0, uint32_t b_lo, uint32_t b_hi, uint32_t acc_first) {
+      using I1 = std::integral_constant<int, 1>;
+      using I2 = std::integral_constant<int, 2>;
+      // issue groups [g0, g1) of one block; `half_tail`: the last of them holds a single k-step
+      auto issue = [&](int g0, int g1, bool half_tail, uint32_t d0, uint32_t b_lo, uint32_t b_hi, uint32_t acc_first) {
         uint32_t acc = acc_first;
         int g = g0;
-        for (; g + 2 <= g1; g += 2, b_lo += 4 * KS, acc = 1u)
-          chunk(std::integral_constant<int, 2>{}, d0, b_lo, b_hi, acc);
-        if (g < g1) chunk(std::integral_constant<int, 1>{}, d0, b_lo, b_hi, acc);
+        const int gfull = half_tail ? g1 - 1 : g1;
+        for (; g + 2 <= gfull; g += 2, b_lo += 4 * KS, acc = 1u) chunk(I2{}, I2{}, d0, b_lo, b_hi, acc);
+        if (g < gfull) { chunk(I1{}, I2{}, d0, b_lo, b_hi, acc); b_lo += 2 * KS; acc = 1u; }
+        if (half_tail) chunk(I1{}, I1{}, d0, b_lo, b_hi, acc);
       };
       for (int ti = 0; ti < n_iter; ++ti) {
         const bool live = (int)blockIdx.x + ti * (int)gridDim.x < P.ntiles;
@@ -357,7 +389,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           int prev_nblk = 1;
           for (int l = 0; l < D.L; ++l, ++lc) {
             const HLayer& Y = D.layer[l];
-            const int ngrp = Y.ksteps >> 1, nblk = Y.nblk;
+            const int ngrp = (Y.ksteps + 1) >> 1, nblk = Y.nblk;  // groups per block
+            const bool odd = Y.ksteps & 1;
             if (!live) {  // no tile this round: keep the cluster's ring protocol going
               for (int i = 0; i < nblk * ngrp; ++i) {
                 mbar_wait_a(fb, ph);
@@ -374,30 +407,47 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
             const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + d_off;
             if (TIMED) tt = clock64();
-            mbar_wait_a(act_a, act_ph0);
+            if (!(P.exp_ & 32)) mbar_wait_a(act_a, act_ph0);
             if (TIMED) { const long long dt = clock64() - tt; t_act += dt; if (kind == DIR_DYN_F || kind == DIR_DYN_B) t_actl[l & 3] += dt; }
             act_ph0 ^= 1;
+            if (TIMED) tl0 = clock64();
+            // block geometry: unit = rows x 32 B; this issuer's unit (hi or lo), LBO = rows x 16 B
+            auto set_block = [&](int rows) {
+              a_blk = (uint32_t)(which * rows * 32) >> 4 | ((uint32_t)(rows * 16) >> 4) << 16;
+              a_k2 = (uint32_t)(rows * 64) >> 4;
+            };
+            set_block(Y.rows[0]);
             // block 0: groups [0, 4) (k-steps 0..7) need operand part 0 only; the rest need part 1
-            const int gsplit = two_parts ? 4 : ngrp;
-            issue(0, gsplit, d_base, b_lo0, b_hi, 0u);
+            const bool probe = TIMED && kind == DIR_DYN_F && l == 2;
             if (two_parts) {
+              issue(0, 4, false, d_base, b_lo0, b_hi, 0u);
+              if (probe) { tl1 = clock64(); t_b0a += tl1 - tl0; }
               if (TIMED) tt = clock64();
-              mbar_wait_a(act_a + 8, act_ph1);
+              if (!(P.exp_ & 32)) mbar_wait_a(act_a + 8, act_ph1);
               if (TIMED) { const long long dt = clock64() - tt; t_act += dt; if (kind == DIR_DYN_F || kind == DIR_DYN_B) t_actl[4 + (l & 3)] += dt; }
               act_ph1 ^= 1;
-              issue(4, ngrp, d_base, b_lo0 + 8 * KS, b_hi, 1u);
+              if (probe) { const long long t1 = clock64(); t_p1 += t1 - tl1; tl1 = t1; }
+              issue(4, ngrp, odd, d_base, b_lo0 + 8 * KS, b_hi, 1u);
+              if (probe) { const long long t1 = clock64(); t_b0b += t1 - tl1; tl1 = t1; }
+            } else {
+              issue(0, ngrp, odd, d_base, b_lo0, b_hi, 0u);
             }
             umma_commit_a(acc_a);
             if (nblk > 1) {
-              issue(0, ngrp, d_base + H_TMEM_BLK, b_lo0, b_hi, 0u);
+              set_block(Y.rows[1]);
+              issue(0, ngrp, odd, d_base + H_TMEM_BLK, b_lo0, b_hi, 0u);
               umma_commit_a(acc_a + 8);
             }
+            if (probe) { const long long t1 = clock64(); t_b1 += t1 - tl1; t_iss1 += t1 - tl0; ++n_iss1; }
           }
         }
       }
       if (TIMED) {
         P.dbg[blockIdx.x * 16 + 0 + 9 * which] = t_act;
         P.dbg[blockIdx.x * 16 + 1 + 9 * which] = t_full;
+        if (blockIdx.x == 0)
+          printf("[gmpc] h16 issuer %d: dyn-fwd layer 2 issue spans: k0-7 %lld | wait part1 %lld | k8-12 %lld | block1 %lld | total %lld (avg cycles over %lld)\n",
+                 which, t_b0a / max(n_iss1, 1LL), t_p1 / max(n_iss1, 1LL), t_b0b / max(n_iss1, 1LL), t_b1 / max(n_iss1, 1LL), t_iss1 / max(n_iss1, 1LL), n_iss1);
         if (which == 0 && blockIdx.x == 0)
           printf("[gmpc] h16 issuer wait_act by dyn layer (part0 | part1): %lld %lld %lld %lld | %lld %lld %lld %lld\n",
                  t_actl[0], t_actl[1], t_actl[2], t_actl[3], t_actl[4], t_actl[5], t_actl[6], t_actl[7]);
@@ -414,7 +464,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     uint32_t acc_ph0 = 0, acc_ph1 = 0, lc = 0;
     long long t_acc = 0, t_epi = 0, t_fin = 0, t_bnd = 0, t_total0 = clock64(), tq = 0;
-    long long t_o1 = 0, t_o2 = 0, t_o3 = 0, t_o4 = 0;
+    long long t_o1 = 0, t_o2 = 0, t_o3 = 0, t_o4 = 0, t_b0done = 0;
     constexpr bool timed = TIMED;
     const bool cost_mode = (P.mode == MODE_PLAN || P.mode == MODE_OBJGRAD);
     float w0 = 0.f, w1 = 0.f, w2 = 0.f;
@@ -459,6 +509,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     };
     // hidden layer li of a pass: TMEM -> (+bias, relu, mask) or (mask gate) -> hi/lo -> HB[li & 1]
     const int f0 = q * 32 + lane;  // this thread's feature in row block 0 (block 1: +128)
+    bool probe_layer = false;
     auto hidden_epilogue = [&](const HLayer& Y, int li, bool fwd, uint32_t* maskp) {
       uint8_t* dst = (li & 1) ? HB1 : HB0;
       const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + t_lane + c0;
@@ -475,7 +526,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           if (timed) tq = clock64();
           if (b == 0) { mbar_wait(&acc_bar[0], acc_ph0); acc_ph0 ^= 1; }
           else        { mbar_wait(&acc_bar[1], acc_ph1); acc_ph1 ^= 1; }
-          if (timed) { const long long t1 = clock64(); t_acc += t1 - tq; tq = t1; }
+          if (timed) {
+            const long long t1 = clock64();
+            t_acc += t1 - tq;
+            tq = t1;
+            if (probe_layer) { if (b == 0) t_b0done = t1; else { t_o1 += t1 - t_b0done; ++t_o2; } }
+          }
           tc_fence_after();
           uint32_t d1[16], d2[16], d3[16];
           tmem_ld16_issue(d_base + b * H_TMEM_BLK, d1);
@@ -691,7 +747,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         for (int t = 0; t < T; ++t) {
           const HDir& D = P.dir[DIR_DYN_F];
           for (int l = 0; l < D.L - 1; ++l) {
+            probe_layer = timed && (l == 1);
             hidden_epilogue(D.layer[l], l, true, wsMask + ((size_t)t * (Ld - 1) + l) * H_COMPUTE);
+            probe_layer = false;
             if (l == 0) {
               // layer 0 has consumed SB.  Fetch step t+1's slices, then (barrier) x_t and the
               // slices of step t are visible to every warp: partial norms of step t, finish the
@@ -978,8 +1036,10 @@ __global__ void h16_absmax_kernel(const float* __restrict__ W, int count, uint32
 // scaled by the power of two that puts max |W| in [2^10, 2^11).
 //   transposed == 0 (forward):  A rows r = output feature n, reduction kk = input feature k.
 //   transposed == 1 (adjoint):  A rows r = input feature k,  reduction kk = output feature n.
+// Block b stores rows_b rows: k-step image = [hi unit | lo unit], unit = [2 k-chunks][rows_b][8 halfs].
 __global__ void h16_pack_kernel(const float* __restrict__ W, int K, int N, int transposed,
-                                uint8_t* dst, int ksteps, const uint32_t* absmax, float* inv_scale) {
+                                uint8_t* dst, int ksteps, int rows0, int rows1,
+                                const uint32_t* absmax, float* inv_scale) {
   const float mx = __uint_as_float(*absmax);
   float sc = 1.f;
   if (mx > 0.f) {
@@ -996,10 +1056,13 @@ __global__ void h16_pack_kernel(const float* __restrict__ W, int K, int N, int t
   __half hi, lo;
   split_h1(W[idx] * sc, hi, lo);
   const int b = r >> 7, rr = r & 127, j = kk >> 4, k16 = kk & 15;
-  uint8_t* p = dst + ((size_t)(b * ksteps + j) * 2) * H_UNIT + (k16 >> 3) * H_A_LBO + (rr >> 3) * H_A_SBO +
+  const int rows = b ? rows1 : rows0;
+  const size_t unit = (size_t)rows * 32;
+  const size_t blk_base = b ? (size_t)ksteps * 2 * rows0 * 32 : 0;
+  uint8_t* p = dst + blk_base + (size_t)j * 2 * unit + (size_t)(k16 >> 3) * rows * 16 + (rr >> 3) * H_A_SBO +
                (rr & 7) * 16 + (k16 & 7) * 2;
   *reinterpret_cast<__half*>(p) = hi;
-  *reinterpret_cast<__half*>(p + H_UNIT) = lo;
+  *reinterpret_cast<__half*>(p + unit) = lo;
 }
 
 // ------------------------------------------------------------------------------------- host side
@@ -1013,13 +1076,15 @@ struct H16State {
   float* d_bias = nullptr;     // forward biases, packed
   float* d_scale = nullptr;    // [Ld + Lc] inverse weight scales
   float* d_wsS = nullptr;      // [num_sms][T][2][32] staging-cost norms saved by the forward sweep
+  uint2* d_gtab = nullptr;     // group tables of the four passes, concatenated
+  uint32_t gtab_off[4] = {0, 0, 0, 0}, ngroups[4] = {0, 0, 0, 0};
   uint32_t* d_absmax = nullptr;
   uint32_t hb_bytes = 0;
   int nslot = 0;
   size_t smem_bytes = 0;
   int num_sms = 0;
   int n = 0, m = 0, fout = 0;
-  int cluster = 4;
+  int cluster = 1;  // B200: multicast did not pay for this stream (12.6 ms vs 13.0 ms on C2)
   int max_clusters[5] = {0, 0, 0, 0, 0};
   int last_cluster = 1;
   long long* d_dbg = nullptr;
@@ -1028,11 +1093,17 @@ struct H16State {
 inline void h16_layer_geom(HLayer& Y, int M_true, int red_true) {
   Y.M_true = M_true;
   Y.nblk = (M_true + 127) / 128;
-  Y.ksteps = rup(red_true, 32) / 16;  // even: a ring group is two k-steps of one block
+  Y.ksteps = rup(red_true, 16) / 16;
+  Y.rows[0] = Y.nblk > 1 ? 128 : std::max(32, rup(M_true, 16));
+  Y.rows[1] = Y.nblk > 1 ? std::max(32, rup(M_true - 128, 16)) : 0;
   Y.next_kpad = rup(M_true, 16);
   Y.bias = nullptr;
   Y.gsrc = nullptr;
   Y.inv_scale = nullptr;
+}
+
+inline size_t h16_layer_bytes(const HLayer& Y) {
+  return (size_t)Y.ksteps * 64 * (Y.rows[0] + Y.rows[1]);
 }
 
 inline size_t h16_build_geometry(H16State& S) {
@@ -1043,13 +1114,13 @@ inline size_t h16_build_geometry(H16State& S) {
     for (int l = 0; l < Ln; ++l) {
       h16_layer_geom(F.layer[l], dims[l + 1], dims[l]);
       F.layer[l].gsrc = reinterpret_cast<const uint8_t*>(off);
-      off += (size_t)F.layer[l].nblk * F.layer[l].ksteps * H_BK_BYTES;
+      off += h16_layer_bytes(F.layer[l]);
     }
     for (int i = 0; i < Ln; ++i) {
       const int lt = Ln - 1 - i;
       h16_layer_geom(Bw.layer[i], dims[lt], dims[lt + 1]);
       Bw.layer[i].gsrc = reinterpret_cast<const uint8_t*>(off);
-      off += (size_t)Bw.layer[i].nblk * Bw.layer[i].ksteps * H_BK_BYTES;
+      off += h16_layer_bytes(Bw.layer[i]);
     }
   };
   one(S.dyn_dims, S.Ld, S.dir[DIR_DYN_F], S.dir[DIR_DYN_B]);
@@ -1072,16 +1143,19 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
   if (S.Ld < 2) { S.why = "dynamics MLP has no hidden layer"; return GMPC_OK; }
   if (hmax > 256) { S.why = "hidden width > 256 (two 128-row MMA blocks)"; return GMPC_OK; }
   if (c.n + c.m > 32 || c.cost_fout > 32) { S.why = "n+m or fout > 32"; return GMPC_OK; }
-  S.hb_bytes = (uint32_t)(rup(hmax, 32) / 8) * H_B_LBO;
+  S.hb_bytes = (uint32_t)(rup(hmax, 16) / 8) * H_B_LBO;
   const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
-  const HSmem L0 = h_smem_layout(0, S.hb_bytes, c.n, c.m, c.cost_fout);
+  S.stream_bytes = h16_build_geometry(S);
+  int ng_total = 0;
+  for (int d = 0; d < 4; ++d)
+    for (int l = 0; l < S.dir[d].L; ++l) ng_total += S.dir[d].layer[l].nblk * ((S.dir[d].layer[l].ksteps + 1) / 2);
+  const HSmem L0 = h_smem_layout(0, S.hb_bytes, c.n, c.m, c.cost_fout, ng_total);
   int nslot = (int)((budget - std::min(budget, (size_t)L0.total)) / H_SLOT_BYTES);
   nslot = std::min(nslot, H_MAX_SLOTS);
   if (const char* env = getenv("GMPC_H16_SLOTS")) nslot = std::min(nslot, std::max(2, atoi(env)));
   if (nslot < 4) { S.why = "shared memory"; return GMPC_OK; }
   S.nslot = nslot;
-  S.smem_bytes = h_smem_layout(nslot, S.hb_bytes, c.n, c.m, c.cost_fout).total;
-  S.stream_bytes = h16_build_geometry(S);
+  S.smem_bytes = h_smem_layout(nslot, S.hb_bytes, c.n, c.m, c.cost_fout, ng_total).total;
   size_t nbias = 0;
   for (int l = 0; l < S.Ld; ++l) nbias += rup(dyn_dims[l + 1], 4);
   for (int l = 0; l < S.Lc; ++l) nbias += rup(cost_dims[l + 1], 4);
@@ -1104,6 +1178,26 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
     S.dir[DIR_COST_F].layer[l].bias = bp; bp += rup(cost_dims[l + 1], 4);
     S.dir[DIR_COST_F].layer[l].inv_scale = S.d_scale + S.Ld + l;
     S.dir[DIR_COST_B].layer[S.Lc - 1 - l].inv_scale = S.d_scale + S.Ld + l;
+  }
+  {  // ring groups of every pass: two k-steps of one block (one when the block's k-step count is odd)
+    std::vector<uint2> tab;
+    for (int d = 0; d < 4; ++d) {
+      S.gtab_off[d] = (uint32_t)tab.size();
+      uint32_t off = 0;
+      for (int l = 0; l < S.dir[d].L; ++l) {
+        const HLayer& Y = S.dir[d].layer[l];
+        for (int b = 0; b < Y.nblk; ++b)
+          for (int j = 0; j < Y.ksteps; j += 2) {
+            const uint32_t bytes = (uint32_t)std::min(2, Y.ksteps - j) * 64 * Y.rows[b];
+            tab.push_back(make_uint2(off, bytes));
+            off += bytes;
+          }
+      }
+      S.ngroups[d] = (uint32_t)tab.size() - S.gtab_off[d];
+    }
+    if (cudaMalloc(&S.d_gtab, tab.size() * sizeof(uint2)) != cudaSuccess) return GMPC_E_CUDA;
+    if (cudaMemcpy(S.d_gtab, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess)
+      return GMPC_E_CUDA;
   }
   if (cudaFuncSetAttribute(plan_h16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)S.smem_bytes) != cudaSuccess ||
@@ -1129,7 +1223,7 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
   }
   cudaGetLastError();
   if (const char* env = getenv("GMPC_TC_CLUSTER")) S.cluster = atoi(env);
-  if (S.cluster != 1 && S.cluster != 2 && S.cluster != 4) S.cluster = 4;
+  if (S.cluster != 1 && S.cluster != 2 && S.cluster != 4) S.cluster = 1;
   while (S.cluster > 1 && S.max_clusters[S.cluster] <= 0) S.cluster >>= 1;
   if (getenv("GMPC_DEBUG")) {
     cudaMalloc(&S.d_dbg, sizeof(long long) * 16 * 1024);
@@ -1149,6 +1243,8 @@ inline void h16_destroy(H16State& S) {
   cudaFree(S.d_absmax);
   cudaFree(S.d_wsS);
   S.d_wsS = nullptr;
+  cudaFree(S.d_gtab);
+  S.d_gtab = nullptr;
   cudaFree(S.d_dbg);
   S.d_stream = nullptr;
   S.d_bias = nullptr;
@@ -1171,9 +1267,9 @@ inline int h16_set_weights(H16State& S, const float* const* dyn_W, const float* 
       const HLayer& r = Bw.layer[Ln - 1 - l];
       h16_absmax_kernel<<<std::min(blocks, 64), 256, 0, st>>>(W[l], K * N, S.d_absmax + sbase + l);
       h16_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 0, const_cast<uint8_t*>(f.gsrc), f.ksteps,
-                                              S.d_absmax + sbase + l, S.d_scale + sbase + l);
+                                              f.rows[0], f.rows[1], S.d_absmax + sbase + l, S.d_scale + sbase + l);
       h16_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 1, const_cast<uint8_t*>(r.gsrc), r.ksteps,
-                                              S.d_absmax + sbase + l, S.d_scale + sbase + l);
+                                              r.rows[0], r.rows[1], S.d_absmax + sbase + l, S.d_scale + sbase + l);
       *launches += 3;
       cudaMemcpyAsync(const_cast<float*>(f.bias), b[l], sizeof(float) * N, cudaMemcpyDeviceToDevice, st);
     }
@@ -1200,6 +1296,7 @@ inline int h16_launch(H16State& S, const PlanParams& P, cudaStream_t st, int64_t
   Q.use_cost = P.use_cost; Q.final_fwd = P.final_fwd;
   Q.nslot = S.nslot;
   Q.hb_bytes = S.hb_bytes;
+  for (int d = 0; d < 4; ++d) { Q.gtab[d] = S.d_gtab + S.gtab_off[d]; Q.ngroups[d] = S.ngroups[d]; }
   if (const char* env = getenv("GMPC_H16_EXP")) Q.exp_ = (uint32_t)atoi(env);
   Q.NQ = P.NQ;
   Q.ntiles = (int)((P.NQ + H_NB - 1) / H_NB);
@@ -1236,7 +1333,7 @@ inline int h16_launch(H16State& S, const PlanParams& P, cudaStream_t st, int64_t
     long long hdbg[16];
     cudaStreamSynchronize(st);
     cudaMemcpy(hdbg, S.d_dbg, sizeof(hdbg), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[gmpc] h16 CTA0 cycles: mma-warp wait_act %lld wait_full %lld issue %lld | compute wait_acc(hidden) %lld epilogue %lld wait_acc(final) %lld boundary %lld total %lld | fwd-top %lld fwd-mid %lld bwd-mid %lld update %lld | issuer2 wait_act %lld wait_full %lld\n",
+    fprintf(stderr, "[gmpc] h16 CTA0 cycles: mma-warp wait_act %lld wait_full %lld issue %lld | compute wait_acc(hidden) %lld epilogue %lld wait_acc(final) %lld boundary %lld total %lld | dynF-L1 acc0->acc1 total %lld count %lld (x %lld %lld) | issuer2 wait_act %lld wait_full %lld\n",
             hdbg[0], hdbg[1], hdbg[2], hdbg[4], hdbg[5], hdbg[6], hdbg[8], hdbg[7], hdbg[11], hdbg[12], hdbg[13], hdbg[14], hdbg[9], hdbg[10]);
   }
   return e == cudaSuccess ? GMPC_OK : GMPC_E_CUDA;

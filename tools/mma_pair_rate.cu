@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) bench(long long* out, const uint8_t* gsrc
   uint8_t* ring = sm;                      // NS x 16 KB
   uint8_t* bop = sm + 160 * 1024;          // B operand, 26 KB
   const int nbk = 26;                      // one 200x200 layer: 2 blocks x 13 k-steps
-  if (warp == 2 && c.stream) {             // producer: refill the ring from L2 like the planner
+  if (warp == 2 && c.stream == 1) {             // producer: refill the ring from L2 like the planner
     uint32_t slot = 0, ph = 0;
     for (int r = 0; r < c.reps; ++r)
       for (int i = 0; i < nbk; i += 2) {
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) bench(long long* out, const uint8_t* gsrc
       int b = 0, j = 0;
 #pragma unroll
       for (int i = 0; i < nbk; i += 2) {
-        if (c.stream) { mbar_wait_a(full_a + slot * 8, ph); if (c.fence) tc_fence_after(); }
+        if (c.stream == 1) { mbar_wait_a(full_a + slot * 8, ph); if (c.fence) tc_fence_after(); }
         const int b0i = b, j0 = j;
         int b1 = b0i, j1 = j0 + 1;
         if (j1 == 13) { j1 = 0; ++b1; }
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128) bench(long long* out, const uint8_t* gsrc
           const uint64_t ah1 = ah + 512;
           umma_f16(tb + b1 * 64, ah1, b0 + (uint64_t)((j1 * b_kstep) >> 4), ihi, 1u);
           if (c.n_lo) umma_f16(tb + b1 * 64 + 32, ah1 + 256, b0 + (uint64_t)((j1 * b_kstep) >> 4), ilo, 1u);
-          if (c.stream) umma_commit_a(empty_a + slot * 8);
+          if (c.stream == 1 || c.stream == 2 || (c.stream == 3 && (i & 6) == 6)) umma_commit_a(empty_a + slot * 8);
         }
         b = b1; j = j1 + 1;
         if (j == 13) { j = 0; ++b; }
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128) bench(long long* out, const uint8_t* gsrc
     for (int r = 0; r < c.reps; ++r) {
       int b = 0, j = 0;
       for (int i = 0; i < nbk; i += 2) {
-        if (c.stream) { mbar_wait(&full[slot], ph); if (c.fence) tc_fence_after(); }
+        if (c.stream == 1) { mbar_wait(&full[slot], ph); if (c.fence) tc_fence_after(); }
         const int b0i = b, j0 = j;
         int b1 = b0i, j1 = j0 + 1;
         if (j1 == 13) { j1 = 0; ++b1; }
@@ -118,8 +118,8 @@ int main() {
   long long* d; uint8_t* g;
   cudaMalloc(&d, 1024 * 8); cudaMalloc(&g, 1 << 20); cudaMemset(g, 0, 1 << 20);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  for (int fence = 0; fence < 2; ++fence)
-    for (int stream = 1; stream < 2; ++stream)
+  for (int fence = 1; fence < 2; ++fence)
+    for (int stream = 0; stream < 4; ++stream)
       for (int b_mn = 1; b_mn < 2; ++b_mn)
         for (int pair = 0; pair < 3; ++pair) {
           Cfg c{b_mn, stream, 200, 9, pair == 2 ? 96 : 64, pair == 0 ? 0 : (pair == 2 ? 0 : 32), 1, fence};
@@ -129,7 +129,7 @@ int main() {
           if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
           long long h[128]; cudaMemcpy(h, d, grid * 8, cudaMemcpyDeviceToHost);
           long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-          printf("fence-per-stage=%d stream=%d B=%s %s: %6.1f cycles per block-k-step (%.0f per 200x200 layer)\n", single, stream,
+          printf("f=%d mode=%d (0 none, 1 stream+commit, 2 commit only, 3 commit every 4th stage) B=%s %s: %6.1f cycles per block-k-step (%.0f per 200x200 layer)\n", single, stream,
                  b_mn ? "MN-major" : "K-major ", pair == 0 ? "N=64 only   " : pair == 1 ? "N=64 + N=32 " : "N=96 only   ",
                  (double)mx / (200.0 * 26), (double)mx / 200.0);
         }
