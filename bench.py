@@ -120,15 +120,19 @@ def time_cpu_port(cfg, params, x0, U0, goal, lr, target_s=15.0, reps=1):
     dt = time.perf_counter() - t0
     sample = int(min(x0.shape[0], max(probe, probe * target_s / max(dt, 1e-3))))
     sample = max(probe, (sample // 64) * 64)
-    best = None
-    for _ in range(reps):
+    # the sample is at most the whole workload; when that takes less than the target, repeat it
+    # so that the figure still comes from about target_s of CPU work (mean over the repeats)
+    tot, n = 0.0, 0
+    while n < reps or (tot < 0.6 * target_s and n < 20):
         t0 = time.perf_counter()
         oracle.plan(f(x0, sample), f(U0, sample), f(goal, sample), op, "adam", cfg["iters"], lr)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
+        tot += time.perf_counter() - t0
+        n += 1
+    best = tot / n
     return dict(value=sample / best, unit=UNIT, cores=cores, kind="port",
-                sample=f"{sample} of {x0.shape[0]} states of workload (fp32 torch-CPU oracle port, "
-                       f"{best:.2f} s; JAX reference not installable offline)"), best, sample
+                sample=f"{sample} of {x0.shape[0]} states of workload, {n} pass(es) of {best:.2f} s each "
+                       f"(fp32 torch-CPU oracle port, all {cores} host threads; JAX reference not "
+                       f"installable offline)"), best, sample
 
 
 def run_reference(args, cfg, rank):

@@ -38,6 +38,7 @@ _SIGS = {
     "gmpc_set_path": (C.c_int, [C.c_void_p, C.c_int]),
     "gmpc_last_path": (C.c_int, [C.c_void_p]),
     "gmpc_launch_count": (C.c_int64, [C.c_void_p]),
+    "gmpc_range_overflow": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "gmpc_set_weights": (C.c_int, [C.c_void_p, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f),
                                    C.POINTER(_f), _f, C.c_void_p]),
     "gmpc_rollout": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.c_void_p]),
@@ -138,6 +139,12 @@ class Handle:
     @property
     def last_path(self):
         return {PATH_FFMA: "ffma", PATH_TC: "tc", PATH_TC16: "tc16"}[self.lib.gmpc_last_path(self._h)]
+
+    def range_overflow(self):
+        """CTAs of the fp16-split kernel that clamped an operand since the last call (synchronises)."""
+        cnt = C.c_int32(0)
+        _check(self.lib.gmpc_range_overflow(self._h, C.byref(cnt), _stream(self.device)))
+        return int(cnt.value)
 
     @property
     def launch_count(self):

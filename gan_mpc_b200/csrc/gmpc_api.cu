@@ -452,6 +452,20 @@ extern "C" int gmpc_plan(gmpc_handle* h, int64_t B, int32_t K, const float* x0, 
   return GMPC_OK;
 }
 
+extern "C" int gmpc_range_overflow(gmpc_handle* h, int32_t* count, void* stream) {
+  if (!h || !count) return fail(GMPC_E_ARG, "gmpc_range_overflow: null argument");
+  *count = 0;
+  if (!h->h16.supported || h->h16.d_ovf == nullptr) return GMPC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU_CHECK(cudaSetDevice(h->cfg.device));
+  uint32_t v = 0;
+  CU_CHECK(cudaMemcpyAsync(&v, h->h16.d_ovf, sizeof(v), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaStreamSynchronize(st));
+  if (v != 0) CU_CHECK(cudaMemsetAsync(h->h16.d_ovf, 0, sizeof(v), st));
+  *count = (int32_t)std::min<uint32_t>(v, 0x7fffffffu);
+  return GMPC_OK;
+}
+
 extern "C" int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float* x0_host,
                               const float* U0_host, const float* goal_host, int32_t method,
                               int32_t N, float lr, float b1, float b2, float eps,
@@ -493,6 +507,23 @@ extern "C" int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float*
   if (J_all_host)
     CU_CHECK(cudaMemcpyAsync(J_all_host, d_Ja, f_Ja * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_CHECK(cudaStreamSynchronize(st));
+  if (h->last_path == GMPC_PATH_TC16) {
+    int32_t clamped = 0;
+    rc = gmpc_range_overflow(h, &clamped, stream);
+    if (rc) return rc;
+    if (clamped > 0) {
+      // an operand left the fp16-split kernel's range: the plan is re-done on the fp32 CUDA-core
+      // kernel (still the GPU; there is no CPU path) when the caller left the choice to us
+      if (h->path != GMPC_PATH_AUTO)
+        return fail(GMPC_E_UNSUPPORTED, "gmpc_plan_host: operand magnitude above 65000 on the fp16-split path; "
+                                        "use GMPC_PATH_AUTO, GMPC_PATH_FFMA or GMPC_PATH_TC");
+      h->path = GMPC_PATH_FFMA;
+      rc = gmpc_plan_host(h, B, K, x0_host, U0_host, goal_host, method, N, lr, b1, b2, eps, U_best_host,
+                          X_best_host, J_best_host, idx_best_host, J_all_host, stream);
+      h->path = GMPC_PATH_AUTO;
+      return rc;
+    }
+  }
   return GMPC_OK;
 }
 

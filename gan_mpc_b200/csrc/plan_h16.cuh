@@ -52,9 +52,6 @@ constexpr int H_SLOT_BYTES = H_GROUP_BYTES;
 constexpr int H_MAX_SLOTS = 12;
 constexpr int H_SROW = H_NB + 1;     // padded row of the small fp32 arrays
 constexpr int H_SB_BYTES = 4096;     // small operand: <= 32 features
-#ifndef H_POLL_NS
-#define H_POLL_NS 100
-#endif
 
 struct HLayer {
   const uint8_t* gsrc;     // [block][k-step][hi unit | lo unit]
@@ -77,7 +74,8 @@ struct HParams {
   HDir dir[4];
   int n, m, T, K;
   int fout, mode, method, iters, use_cost, final_fwd, ntiles, nslot;
-  uint32_t hb_bytes, exp_;  // exp_: timing experiments (GMPC_H16_EXP), results are garbage when set
+  uint32_t hb_bytes, exp_;  // exp_: timing experiments (GMPC_H16_EXP with GMPC_DEBUG: 1 = no weight stream,
+                            // 2 = no operand stores); honoured by the TIMED instantiation only, results are garbage
   const uint2* gtab[4];     // per pass: {byte offset in the pass image, bytes} of every ring group
   uint32_t ngroups[4];
   long long NQ;
@@ -86,6 +84,7 @@ struct HParams {
   float *U_out, *X_out, *J_out, *dU_out, *lam_out;
   float *ws_X, *ws_G, *ws_U, *ws_M, *ws_V, *ws_S;
   uint32_t* ws_mask;
+  uint32_t* ovf;   // incremented by a CTA that clamped an fp16 operand (|scaled value| > 65000)
   long long* dbg;
 };
 
@@ -244,7 +243,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     // guarantees the releases up to G - R - NS, and G - R - NS >= G - 2 NS iff NS >= R.
     const int w = (warp == 0) ? 0 : 1;
     const int LP = NS >= 8 ? 4 : (NS >= 6 ? 3 : 2), R = 2 * LP;
-    if (lane < LP && !(P.exp_ & 1)) {
+    if (lane < LP && !(TIMED && (P.exp_ & 1))) {
       uint32_t ngk[4];
       const uint8_t* basek[4];
       const uint2* gtk[4];
@@ -275,9 +274,6 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           continue;
         }
         const uint32_t bar = full_a + slot * 8;
-        if (P.exp_ & 16) {
-          while (!mbar_try_wait_a(empty_a + slot * 8, ph ^ 1)) __nanosleep(200);
-        } else
         mbar_wait_a(empty_a + slot * 8, ph ^ 1);  // all C CTAs released the slot
         const uint2 ge = gtk[kind][gi];         // {offset, bytes}; bytes is a multiple of 64 * C
         const uint32_t part = ge.y / C;
@@ -323,7 +319,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       const uint32_t d_off = which == 0 ? 0u : 2u * H_NB;  // issuer 1 accumulates into columns [64, 96)
       // ring cursor: barrier address, A descriptor low word of the slot start, slots left, parity
       uint32_t fb = full_a, a_lo = a_lo0, left = (uint32_t)NS, ph = 0;
-      const bool nostream = P.exp_ & 1;
+      const bool nostream = TIMED && (P.exp_ & 1);  // timing experiment: no weight stream (garbage results)
       // loop invariants the compiler would otherwise re-derive from special registers / the
       // constant bank inside every chunk (S2UR SR_CgaSize -> UIMAD -> LDCU chains in the SASS)
       uint32_t NSr = (uint32_t)NS, mc = C > 1 ? 1u : 0u, cmask_r = cmask, full_r = full_a, alo0_r = a_lo0;
@@ -407,7 +403,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
             const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + d_off;
             if (TIMED) tt = clock64();
-            if (!(P.exp_ & 32)) mbar_wait_a(act_a, act_ph0);
+            mbar_wait_a(act_a, act_ph0);
             if (TIMED) { const long long dt = clock64() - tt; t_act += dt; if (kind == DIR_DYN_F || kind == DIR_DYN_B) t_actl[l & 3] += dt; }
             act_ph0 ^= 1;
             if (TIMED) tl0 = clock64();
@@ -423,7 +419,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
               issue(0, 4, false, d_base, b_lo0, b_hi, 0u);
               if (probe) { tl1 = clock64(); t_b0a += tl1 - tl0; }
               if (TIMED) tt = clock64();
-              if (!(P.exp_ & 32)) mbar_wait_a(act_a + 8, act_ph1);
+              mbar_wait_a(act_a + 8, act_ph1);
               if (TIMED) { const long long dt = clock64() - tt; t_act += dt; if (kind == DIR_DYN_F || kind == DIR_DYN_B) t_actl[4 + (l & 3)] += dt; }
               act_ph1 ^= 1;
               if (probe) { const long long t1 = clock64(); t_p1 += t1 - tl1; tl1 = t1; }
@@ -497,8 +493,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       if (lane == 0) mbar_arrive(&act_bar[part]);
     };
     // 16 values of feature f (trajectories c0 .. c0+15), already scaled -> operand buffer `dst`
+    float opmax = 0.f;  // largest operand magnitude this thread has written (range check)
     auto store_row16 = [&](uint8_t* dst, int f, const float (&v)[16]) {
       uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int k = 0; k < 16; k += 2) opmax = fmaxf(opmax, fmaxf(fabsf(v[k]), fabsf(v[k + 1])));
 #pragma unroll
       for (int k = 0; k < 8; ++k) split_h2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
       uint8_t* p = dst + (f >> 3) * H_B_LBO + (f & 7) * 16 + (c0 >> 3) * H_B_SBO;
@@ -553,7 +552,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
               }
               v[c] = z;
             }
-            if (!(P.exp_ & 2)) store_row16(dst, f, v);
+            if (!(TIMED && (P.exp_ & 2))) store_row16(dst, f, v);
           }
           publish(b);
           if (timed) t_epi += clock64() - tq;
@@ -621,7 +620,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       const float* pu = stbuf(t) + L.o_pu * H_SROW;
       for (int e = ct; e < m * H_NB; e += H_COMPUTE) {
         const int j = e / H_NB, r = e - j * H_NB;
-        h16_store_op(SB, n + j, r, pu[j * H_SROW + r]);
+        const float uv = pu[j * H_SROW + r];
+        opmax = fmaxf(opmax, fabsf(uv));
+        h16_store_op(SB, n + j, r, uv);
       }
     };
     // staging-cost norms of step t, phase A: every warp sums the features i = wi, wi+8, ... of its
@@ -737,6 +738,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           const int i = e / H_NB, r = e - i * H_NB;
           const float v = wsX[e];
           x_s[i * H_SROW + r] = v;
+          opmax = fmaxf(opmax, fabsf(v));
           h16_store_op(SB, i, r, v);
         }
         Jr = 0.f;
@@ -1002,6 +1004,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         }
       }
     }
+    // fp16 operand range check (the epilogue clamps with satfinite; the host re-plans on the fp32
+    // CUDA-core kernel when this fires, see gmpc_plan_host)
+    if (!(opmax <= 65000.f) && P.ovf != nullptr) atomicAdd(P.ovf, 1u);
     if (TIMED && ct == 0) {
       P.dbg[blockIdx.x * 16 + 4] = t_acc;
       P.dbg[blockIdx.x * 16 + 5] = t_epi;
@@ -1077,6 +1082,7 @@ struct H16State {
   float* d_scale = nullptr;    // [Ld + Lc] inverse weight scales
   float* d_wsS = nullptr;      // [num_sms][T][2][32] staging-cost norms saved by the forward sweep
   uint2* d_gtab = nullptr;     // group tables of the four passes, concatenated
+  uint32_t* d_ovf = nullptr;   // operand range-check counter (see HParams::ovf)
   uint32_t gtab_off[4] = {0, 0, 0, 0}, ngroups[4] = {0, 0, 0, 0};
   uint32_t* d_absmax = nullptr;
   uint32_t hb_bytes = 0;
@@ -1165,6 +1171,8 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
   if (cudaMalloc(&S.d_scale, (S.Ld + S.Lc) * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
   if (cudaMalloc(&S.d_absmax, (S.Ld + S.Lc) * sizeof(uint32_t)) != cudaSuccess) return GMPC_E_CUDA;
   if (cudaMalloc(&S.d_wsS, (size_t)S.num_sms * c.T * 2 * H_NB * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
+  if (cudaMalloc(&S.d_ovf, sizeof(uint32_t)) != cudaSuccess) return GMPC_E_CUDA;
+  if (cudaMemset(S.d_ovf, 0, sizeof(uint32_t)) != cudaSuccess) return GMPC_E_CUDA;
   float* bp = S.d_bias;
   for (int d = 0; d < 4; ++d)
     for (int l = 0; l < S.dir[d].L; ++l)
@@ -1245,6 +1253,8 @@ inline void h16_destroy(H16State& S) {
   S.d_wsS = nullptr;
   cudaFree(S.d_gtab);
   S.d_gtab = nullptr;
+  cudaFree(S.d_ovf);
+  S.d_ovf = nullptr;
   cudaFree(S.d_dbg);
   S.d_stream = nullptr;
   S.d_bias = nullptr;
@@ -1306,6 +1316,7 @@ inline int h16_launch(H16State& S, const PlanParams& P, cudaStream_t st, int64_t
   Q.ws_X = P.ws_X; Q.ws_G = P.ws_G; Q.ws_U = P.ws_U; Q.ws_M = P.ws_M; Q.ws_V = P.ws_V;
   Q.ws_mask = P.ws_mask;
   Q.ws_S = S.d_wsS;
+  Q.ovf = S.d_ovf;
   Q.dbg = S.d_dbg;
   if (Q.ntiles <= 0) return GMPC_OK;
   int C = S.cluster;

@@ -76,18 +76,6 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
-// Polite wait for the many-thread consumers (epilogue warps): back off between probes so that
-// 256 polling threads do not flood the barrier unit that also has to retire the TMA complete_tx
-// and tcgen05.commit arrivals the tensor pipe is waiting behind.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
-  const uint32_t a = smem_u32(bar);
-  if (mbar_try_wait_a(a, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_a(a, parity)) {
-    __nanosleep(ns);
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }

@@ -125,6 +125,14 @@ int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float* x0_host,
                    float* X_best_host, float* J_best_host, int32_t* idx_best_host,
                    float* J_all_host, void* stream);
 
+/* The fp16-split tensor-core kernel (GMPC_PATH_TC16) represents operands as fp16 hi + lo parts; an
+ * operand magnitude above 65000 (states, actions or hidden activations; adjoints are rescaled per
+ * trajectory and cannot overflow) is clamped and counted.  This call synchronises `stream`, returns
+ * the number of CTAs that clamped since the last call in *count and resets the counter.  A non-zero
+ * count means the results of those calls are outside the 1e-4 parity contract: re-run them with
+ * GMPC_PATH_FFMA or GMPC_PATH_TC.  gmpc_plan_host does this by itself when the path is AUTO. */
+int gmpc_range_overflow(gmpc_handle* h, int32_t* count, void* stream);
+
 /* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 int64_t gmpc_launch_count(const gmpc_handle* h);
 

@@ -244,3 +244,51 @@ def test_errors_are_loud(built_lib):
         util.make_handle(cfg, p).plan(torch.from_numpy(x0), dev(U0), dev(goal))   # CPU tensor
     with pytest.raises(TypeError):
         util.make_handle(cfg, p).plan(dev(x0).double(), dev(U0), dev(goal))
+
+
+def test_tc16_range_check_and_auto_fallback(built_lib):
+    """fp16-split operands above 65000 are clamped and COUNTED; the host-buffer call re-plans on the
+    fp32 CUDA-core kernel when the path is AUTO and refuses when tc16 was forced."""
+    from gan_mpc_b200 import _lib
+    cfg = util.MID
+    p, x0, U0, goal = util.case(cfg, 5, B=96, K=1)
+    x0 = x0.copy()
+    x0[3] *= 1e5          # one start state far outside the normalised range
+    goal = goal.copy()
+    goal[3] = x0[3][None, :]
+    h = util.make_handle(cfg, p)
+    op = util.to_oracle(p)
+    oU, oX, oJ, oidx, _ = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), op, "grad", 2, 1e-3)
+    # device call on the forced tc16 path: the counter fires
+    h.set_path("tc16")
+    h.plan(dev(x0), dev(U0), dev(goal), method="grad", iters=2, lr=1e-3)
+    assert h.range_overflow() > 0
+    assert h.range_overflow() == 0          # reading resets it
+    with pytest.raises(_lib.GmpcError):     # forced path: the host call refuses rather than return clamped plans
+        h.plan_host(torch.from_numpy(x0), torch.from_numpy(U0), torch.from_numpy(goal),
+                    method="grad", iters=2, lr=1e-3)
+    # AUTO: transparently re-planned on the fp32 kernel
+    h.set_path("auto")
+    Ub, Xb, Jb, idx, _ = h.plan_host(torch.from_numpy(x0), torch.from_numpy(U0), torch.from_numpy(goal),
+                                     method="grad", iters=2, lr=1e-3)
+    assert h.last_path == "ffma"
+    ok = torch.ones(96, dtype=torch.bool)
+    assert util.rel_rows(Xb[ok], oX[ok]) < TOL and util.rel_rows(Ub[ok], oU[ok]) < TOL
+    # in-range inputs never trip it
+    p2, x2, U2, g2 = util.case(cfg, 6, B=96, K=1)
+    h.plan(dev(x2), dev(U2), dev(g2), method="adam", iters=2, lr=1e-2)
+    assert h.last_path == "tc16" and h.range_overflow() == 0
+
+
+@pytest.mark.parametrize("slots", [4, 5, 7, 8])
+def test_tc16_ring_depth_independent(slots, built_lib, monkeypatch):
+    """The weight ring protocol (parity waits, producer round size) must hold for every ring depth."""
+    monkeypatch.setenv("GMPC_H16_SLOTS", str(slots))
+    cfg = util.MID
+    p, x0, U0, goal = util.case(cfg, 9, B=70, K=1)
+    h = util.make_handle(cfg, p)
+    h.set_path("tc16")
+    op = util.to_oracle(p)
+    oU, oX, oJ, _, _ = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), op, "adam", 3, 1e-2)
+    Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=3, lr=1e-2)
+    assert util.rel_rows(Xb, oX) < TOL and util.rel_rows(Ub, oU) < TOL
