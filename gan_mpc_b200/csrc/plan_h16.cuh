@@ -486,11 +486,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
 
     // "operand part `part` of the next layer is in shared memory": every writer fences its own
     // generic-proxy stores for the async proxy, then one lane per warp arrives (count 8)
+    const uint32_t acc_sa = smem_u32(acc_bar), act_sa = smem_u32(act_bar);
     auto publish = [&](int part) {
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&act_bar[part]);
+      if (lane == 0) mbar_arrive_a(act_sa + part * 8);
     };
     // 16 values of feature f (trajectories c0 .. c0+15), already scaled -> operand buffer `dst`
     float opmax = 0.f;  // largest operand magnitude this thread has written (range check)
@@ -523,8 +524,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       for (int b = 0; b < 2; ++b) {
         if (b < Y.nblk) {
           if (timed) tq = clock64();
-          if (b == 0) { mbar_wait(&acc_bar[0], acc_ph0); acc_ph0 ^= 1; }
-          else        { mbar_wait(&acc_bar[1], acc_ph1); acc_ph1 ^= 1; }
+          if (b == 0) { mbar_wait_a(acc_sa, acc_ph0); acc_ph0 ^= 1; }
+          else        { mbar_wait_a(acc_sa + 8, acc_ph1); acc_ph1 ^= 1; }
           if (timed) {
             const long long t1 = clock64();
             t_acc += t1 - tq;
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + t_lane + c0;
       const float inv = *Y.inv_scale;
       if (timed) tq = clock64();
-      mbar_wait(&acc_bar[0], acc_ph0);
+      mbar_wait_a(acc_sa, acc_ph0);
       acc_ph0 ^= 1;
       if (timed) t_fin += clock64() - tq;
       tc_fence_after();

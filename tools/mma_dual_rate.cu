@@ -55,11 +55,11 @@ __global__ void __launch_bounds__(384) bench(long long* out, int mode, int reps)
     float acc = 0.f;
     uint4* dst = reinterpret_cast<uint4*>(sm + 100 * 1024) + (tid - 128);
     while (!mbar_try_wait(&bar[0], 0)) {
-      if (mode == 4) {
+      if (mode == 4 || mode == 6) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
           uint32_t d[16];
-          tmem_ld16_issue(tb + t_lane + 256 + k * 16, d);
+          tmem_ld16_issue(tb + t_lane + (mode == 4 ? 256 : 0) + k * 16, d);
           tmem_ld_wait();
           acc += __uint_as_float(d[3]);
         }
@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(384) bench(long long* out, int mode, int reps)
 int main() {
   long long* d; cudaMalloc(&d, 4096 * 8);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const char* names[] = {"one issuer, both products", "two issuers (N=64 | N=32)", "one issuer, N=64 only", "two issuers + 8 warps polling an mbarrier", "two issuers + 8 warps in a tcgen05.ld loop", "two issuers + 8 warps in an STS.128 loop"};
-  for (int mode = 0; mode < 6; ++mode) {
+  const char* names[] = {"one issuer, both products", "two issuers (N=64 | N=32)", "one issuer, N=64 only", "two issuers + 8 warps polling an mbarrier", "two issuers + 8 warps in a tcgen05.ld loop", "two issuers + 8 warps in an STS.128 loop", "two issuers + 8 warps tcgen05.ld on the accumulator columns"};
+  for (int mode = 0; mode < 7; ++mode) {
     cudaMemset(d, 0, 4096 * 8);
     bench<<<128, 384, 200 * 1024>>>(d, mode, 200);
     if (cudaDeviceSynchronize() != cudaSuccess) { printf("error\n"); return 1; }
