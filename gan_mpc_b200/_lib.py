@@ -59,6 +59,9 @@ _SIGS = {
     "gmpc_clip_adam_step": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, _f, C.c_int32, C.c_float,
                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p]),
+    "gmpc_critic_train_scan": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, _f,
+                                         C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                         _f, _f, C.c_void_p]),
     "gmpc_l2_loss": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.c_void_p]),
     "gmpc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "gmpc_tc_probe": (C.c_int, [C.c_int] * 4 + [C.c_uint32] * 11 + [C.c_void_p] * 3),
@@ -287,6 +290,22 @@ class Handle:
             _ptr(grad_flat, device=dev, name="grad_flat"), _ptr(mom, device=dev, name="mom"),
             _ptr(vel, device=dev, name="vel"), int(step), lr, max_norm, grad_scale, b1, b2, eps,
             _stream(dev)))
+
+    def critic_train_scan(self, xseq, label, perm, params_flat, mom, vel, step0, lr, max_norm=100.0,
+                          b1=0.9, b2=0.999, eps=1e-8):
+        """The whole minibatch scan of one critic update in one call (single GPU): perm is int32
+        [steps, Bc]; params/mom/vel are updated in place; returns the minibatch losses [steps]."""
+        dev = self.device
+        steps, Bc = perm.shape
+        losses = torch.empty(steps, device=dev, dtype=torch.float32)
+        scratch = torch.empty(self.critic_param_count, device=dev, dtype=torch.float32)
+        _check(self.lib.gmpc_critic_train_scan(
+            self._h, steps, Bc, xseq.shape[1], _ptr(xseq, device=dev, name="xseq"),
+            _ptr(label, device=dev, name="label"), _ptr(perm, dtype=torch.int32, device=dev, name="perm"),
+            _ptr(params_flat, device=dev, name="params_flat"), _ptr(mom, device=dev, name="mom"),
+            _ptr(vel, device=dev, name="vel"), int(step0), lr, max_norm, b1, b2, eps, _ptr(losses),
+            _ptr(scratch), _stream(dev)))
+        return losses
 
     def l2_loss(self, X, desired):
         B = X.shape[0]

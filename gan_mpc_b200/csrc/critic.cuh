@@ -54,11 +54,12 @@ __global__ void critic_kernel(const CriticDims D, const float* __restrict__ xseq
   const float* Wh = prm + D.oWh;
   const float* bh = prm + D.obh;
 
-  if (do_bwd) {
-    for (long long i = tid; i < D.P; i += blockDim.x) part[i] = 0.f;
-  }
+  // every parameter receives a contribution from every sample, so the CTA's first sample stores
+  // and later ones accumulate: no zero-fill pass and no read of the partial buffer for it
+  bool first = true;
+  auto acc_part = [&](long long idx, float v) { part[idx] = first ? v : part[idx] + v; };
 
-  for (long long s = blockIdx.x; s < Bc; s += gridDim.x) {
+  for (long long s = blockIdx.x; s < Bc; s += gridDim.x, first = false) {
     const long long src = perm ? (long long)perm[s] : s;
     __syncthreads();
     for (int i = tid; i < T1 * n; i += blockDim.x) xs[i] = xseq[src * T1 * n + i];
@@ -113,16 +114,16 @@ __global__ void critic_kernel(const CriticDims D, const float* __restrict__ xseq
       }
     }
     __syncthreads();
-    if (!do_bwd) continue;
+    if (!do_bwd) continue;  // (first is irrelevant without a backward pass)
     // ---------------------------------------------------------------- head backward
     const float ds = scal[0];
     {
       const float* a = hact + (D.L - 1) * W;
       if (tid < D.dlast) {
-        part[D.oWo + tid] += a[tid] * ds;
+        acc_part(D.oWo + tid, a[tid] * ds);
         hda[tid] = prm[D.oWo + tid] * ds;
       }
-      if (tid == 0) part[D.obo] += ds;
+      if (tid == 0) acc_part(D.obo, ds);
     }
     __syncthreads();
     for (int l = D.L - 2; l >= 0; --l) {
@@ -131,9 +132,9 @@ __global__ void critic_kernel(const CriticDims D, const float* __restrict__ xseq
         const float a = hact[(l + 1) * W + tid];
         const float dz = (a > 0.f) ? hda[tid] : 0.f;
         hdz[tid] = dz;
-        part[D.oDb[l] + tid] += dz;
+        acc_part(D.oDb[l] + tid, dz);
         for (int i = 0; i < din; ++i)
-          part[D.oDk[l] + (size_t)i * D.H + tid] += hact[l * W + i] * dz;
+          acc_part(D.oDk[l] + (size_t)i * D.H + tid, hact[l * W + i] * dz);
       }
       __syncthreads();
       for (int i = warp; i < din; i += nwarps) {
@@ -177,11 +178,11 @@ __global__ void critic_kernel(const CriticDims D, const float* __restrict__ xseq
     if (tid < G) {
       float bsum = 0.f;
       for (int t = 0; t < T1; ++t) bsum += gates[t * G + tid];
-      part[D.obh + tid] += bsum;
+      acc_part(D.obh + tid, bsum);
       for (int i = 0; i < n; ++i) {
         float acc = 0.f;
         for (int t = 0; t < T1; ++t) acc = fmaf(xs[t * n + i], gates[t * G + tid], acc);
-        part[D.oWi + (size_t)i * G + tid] += acc;
+        acc_part(D.oWi + (size_t)i * G + tid, acc);
       }
       for (int i = 0; i < F; i += 4) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -193,10 +194,10 @@ __global__ void critic_kernel(const CriticDims D, const float* __restrict__ xseq
           if (i + 2 < F) a2 = fmaf(h[2], dz, a2);
           if (i + 3 < F) a3 = fmaf(h[3], dz, a3);
         }
-        part[D.oWh + (size_t)i * G + tid] += a0;
-        if (i + 1 < F) part[D.oWh + (size_t)(i + 1) * G + tid] += a1;
-        if (i + 2 < F) part[D.oWh + (size_t)(i + 2) * G + tid] += a2;
-        if (i + 3 < F) part[D.oWh + (size_t)(i + 3) * G + tid] += a3;
+        acc_part(D.oWh + (size_t)i * G + tid, a0);
+        if (i + 1 < F) acc_part(D.oWh + (size_t)(i + 1) * G + tid, a1);
+        if (i + 2 < F) acc_part(D.oWh + (size_t)(i + 2) * G + tid, a2);
+        if (i + 3 < F) acc_part(D.oWh + (size_t)(i + 3) * G + tid, a3);
       }
     }
   }
@@ -220,10 +221,69 @@ __global__ void critic_reduce_kernel(const float* partial, int nparts, long long
   }
 }
 
+// The three tail steps of one minibatch step in ONE launch (single-GPU scan, gmpc_critic_train_scan):
+// deterministic reduction of the per-CTA partial gradients, global-norm clip, Adam.  Every block
+// reduces its 256 parameters and its share of the squared norm, then the blocks meet at a grid-wide
+// ticket barrier (the grid is ceil(P/256) blocks, far fewer than the SM count, so all of them are
+// resident), sum the block norms in the same fixed order, and update their own 256 parameters.
+// `expected` = number of tickets after this launch (the counter only ever grows).
+// bc1 / bc2 = 1 - b^step are computed on the host in double precision.
+__global__ void critic_reduce_clip_adam_kernel(const float* partial, int nparts, long long P,
+                                               float* grad, const float* losses, long long Bc,
+                                               float inv_count, float* loss, float* params, float* mom,
+                                               float* vel, float lr, float max_norm, float b1, float b2,
+                                               float eps, float bc1, float bc2, float* blocksq,
+                                               unsigned long long* ticket, unsigned long long expected) {
+  __shared__ float red[8];
+  __shared__ float gn_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long p = (long long)blockIdx.x * blockDim.x + tid;
+  float g = 0.f, mo = 0.f, ve = 0.f, pv = 0.f;
+  if (p < P) {
+    for (int c = 0; c < nparts; ++c) g += partial[(size_t)c * P + p];
+    grad[p] = g;
+    mo = mom[p]; ve = vel[p]; pv = params[p];   // fetched before the barrier, used after it
+  }
+  float ss = warp_sum(g * g);
+  if (lane == 0) red[warp] = ss;
+  if (loss != nullptr && blockIdx.x == 0 && warp == 0) {
+    float acc = 0.f;
+    for (long long s = lane; s < Bc; s += 32) acc += losses[s];
+    acc = warp_sum(acc);
+    if (lane == 0) loss[0] = acc * inv_count;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    blocksq[blockIdx.x] = tot;
+    __threadfence();
+    atomicAdd(ticket, 1ULL);
+    while (*reinterpret_cast<volatile unsigned long long*>(ticket) < expected) {}
+    __threadfence();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float tot = 0.f;
+    for (unsigned b = lane; b < gridDim.x; b += 32) tot += __ldcg(blocksq + b);
+    tot = warp_sum(tot);
+    if (lane == 0) gn_s = sqrtf(tot);
+  }
+  __syncthreads();
+  if (p >= P) return;
+  const float gn = gn_s;
+  if (!(gn < max_norm)) g = g / gn * max_norm;
+  mo = b1 * mo + (1.f - b1) * g;
+  ve = b2 * ve + (1.f - b2) * g * g;
+  mom[p] = mo;
+  vel[p] = ve;
+  params[p] = pv - lr * (mo / bc1) / (sqrtf(ve / bc2) + eps);
+}
+
 // optax.chain(clip_by_global_norm(max_norm), adam(lr)) + apply_updates on a flat vector.
 // Single CTA: the vector is tiny and the global norm needs a grid-wide reduction otherwise.
 __global__ void clip_adam_kernel(long long P, float* params, const float* grad, float* mom,
-                                 float* vel, int step, float lr, float max_norm, float gscale,
+                                 float* vel, float bc1, float bc2, float lr, float max_norm, float gscale,
                                  float b1, float b2, float eps) {
   __shared__ float red[32];
   __shared__ float gn_s;
@@ -244,8 +304,6 @@ __global__ void clip_adam_kernel(long long P, float* params, const float* grad, 
   __syncthreads();
   const float gn = gn_s;
   const bool clip = !(gn < max_norm);
-  const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
-  const float bc2 = (float)(1.0 - pow((double)b2, (double)step));
   for (long long i = tid; i < P; i += blockDim.x) {
     float g = grad[i] * gscale;
     if (clip) g = g / gn * max_norm;

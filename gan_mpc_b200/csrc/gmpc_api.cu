@@ -70,6 +70,8 @@ struct gmpc_handle {
   CriticDims cd;
   float* d_partial = nullptr;
   float* d_losses = nullptr;
+  float* d_fuse = nullptr;   // 8-byte ticket counter, then per-block squared norms of the fused tail kernel
+  unsigned long long fuse_tickets = 0;  // tickets handed out so far (the device counter only grows)
   size_t losses_cap = 0;
   int critic_grid = 0;
   // tensor-core path state (3xTF32 kernel and the fp16-split kernel)
@@ -249,7 +251,7 @@ extern "C" int gmpc_destroy(gmpc_handle* h) {
   cudaFree(h->d_wpack); cudaFree(h->d_mpcw);
   cudaFree(h->ws_X); cudaFree(h->ws_G); cudaFree(h->ws_U); cudaFree(h->ws_M); cudaFree(h->ws_V);
   cudaFree(h->ws_mask); cudaFree(h->d_scratch); cudaFree(h->d_stage);
-  cudaFree(h->d_partial); cudaFree(h->d_losses);
+  cudaFree(h->d_partial); cudaFree(h->d_losses); cudaFree(h->d_fuse);
   delete h;
   return GMPC_OK;
 }
@@ -606,9 +608,58 @@ extern "C" int gmpc_clip_adam_step(gmpc_handle* h, int64_t P, float* params_flat
     return fail(GMPC_E_ARG, "gmpc_clip_adam_step: bad argument");
   if (P == 0) return GMPC_OK;
   CU_CHECK(cudaSetDevice(h->cfg.device));
-  clip_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(P, params_flat, grad_flat, mom, vel, step,
+  const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
+  const float bc2 = (float)(1.0 - pow((double)b2, (double)step));
+  clip_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(P, params_flat, grad_flat, mom, vel, bc1, bc2,
                                                          lr, max_norm, grad_scale, b1, b2, eps);
   ++h->launches;
+  CU_CHECK(cudaGetLastError());
+  return GMPC_OK;
+}
+
+extern "C" int gmpc_critic_train_scan(gmpc_handle* h, int32_t steps, int64_t Bc, int32_t T1,
+                                      const float* data_xseq, const float* data_label,
+                                      const int32_t* perm, float* params_flat, float* mom, float* vel,
+                                      int32_t step0, float lr, float max_norm, float b1, float b2,
+                                      float eps, float* losses, float* grad_scratch, void* stream) {
+  if (!h || steps < 0 || Bc < 1 || step0 < 0 || !perm || !params_flat || !mom || !vel || !losses ||
+      !grad_scratch || !data_xseq || !data_label)
+    return fail(GMPC_E_ARG, "gmpc_critic_train_scan: bad argument");
+  if (h->cfg.critic_features <= 0) return fail(GMPC_E_STATE, "gmpc_critic_train_scan: handle was created without a critic");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU_CHECK(cudaSetDevice(h->cfg.device));
+  CriticDims d = h->cd;
+  d.T1 = T1;
+  const size_t smem = critic_smem(d, T1);
+  if (smem > 227 * 1024) return fail(GMPC_E_UNSUPPORTED, "gmpc_critic_train_scan: sequence too long for one SM's shared memory");
+  if ((size_t)Bc > h->losses_cap) {
+    if (h->d_losses) cudaFree(h->d_losses);
+    h->d_losses = nullptr; h->losses_cap = 0;
+    CU_CHECK(cudaMalloc(&h->d_losses, sizeof(float) * (size_t)Bc * 2));
+    h->losses_cap = (size_t)Bc;
+  }
+  const int rb = (int)((d.P + 255) / 256);
+  if (rb > h->num_sms) return fail(GMPC_E_UNSUPPORTED, "gmpc_critic_train_scan: critic too large for the fused tail kernel");
+  if (!h->d_fuse) {
+    CU_CHECK(cudaMalloc(&h->d_fuse, sizeof(float) * (size_t)(rb + 2)));
+    CU_CHECK(cudaMemsetAsync(h->d_fuse, 0, sizeof(float) * (size_t)(rb + 2), st));
+    h->fuse_tickets = 0;
+  }
+  const int threads = std::max(64, ((std::max(4 * d.F, d.H) + 31) / 32) * 32);
+  const int grid = (int)std::min<int64_t>(Bc, h->critic_grid);
+  const float inv_count = 1.f / (float)Bc;
+  for (int32_t s = 0; s < steps; ++s) {
+    critic_kernel<<<grid, threads, smem, st>>>(d, data_xseq, data_label, perm + (size_t)s * Bc, params_flat,
+                                               inv_count, Bc, h->d_losses, nullptr, h->d_partial, 1);
+    const int step = step0 + s + 1;
+    const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
+    const float bc2 = (float)(1.0 - pow((double)b2, (double)step));
+    critic_reduce_clip_adam_kernel<<<rb, 256, 0, st>>>(
+        h->d_partial, grid, d.P, grad_scratch, h->d_losses, Bc, inv_count, losses + s, params_flat, mom, vel,
+        lr, max_norm, b1, b2, eps, bc1, bc2, h->d_fuse + 2, reinterpret_cast<unsigned long long*>(h->d_fuse),
+        h->fuse_tickets += (unsigned long long)rb);
+    h->launches += 2;
+  }
   CU_CHECK(cudaGetLastError());
   return GMPC_OK;
 }

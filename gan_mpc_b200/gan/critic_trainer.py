@@ -54,6 +54,15 @@ def train_critic_parameters(train_args, opt_state, params, perm, dataset):
     Bc = perm.shape[1]
     lo, hi = parallel.shard_range(Bc, rank, world)
     perm = perm.to(torch.int32)
+    if world == 1 and perm.shape[0] > 0:
+        # one C-ABI call enqueues the whole scan (the reference's lax.scan is one executable too)
+        mu, nu = opt.moments(opt_state, "critic_params", flat)
+        losses = h.critic_train_scan(X, Y, perm.contiguous(), flat, mu, nu, step0=opt_state["count"],
+                                     lr=opt.lr, max_norm=opt.max_norm, b1=opt.b1, b2=opt.b2, eps=opt.eps)
+        opt_state["count"] += perm.shape[0]
+        params = dict(params)
+        params["critic_params"] = policy.critic_model.model.unflatten(flat, n)
+        return params, opt_state, losses.mean()
     losses = []
     for s in range(perm.shape[0]):
         loss, g = h.critic_loss_grad(X, Y, flat, inv_count=1.0 / Bc, perm=perm[s, lo:hi].contiguous())

@@ -164,6 +164,18 @@ int gmpc_clip_adam_step(gmpc_handle* h, int64_t P, float* params_flat, const flo
                         float* mom, float* vel, int32_t step, float lr, float max_norm,
                         float grad_scale, float b1, float b2, float eps, void* stream);
 
+/* The whole minibatch scan of train_critic_parameters (gan/critic_trainer.py:48-65, a lax.scan in the
+ * reference) enqueued by one call: for s < steps { gather perm[s, :], BCE loss + flat gradient
+ * (batch mean), clip_by_global_norm(max_norm) + Adam step number step0 + s + 1 } on one GPU.
+ * perm is int32 [steps, Bc] on the device (sampled with replacement by the caller, :88-90);
+ * losses[steps] receives the minibatch losses; grad_scratch[P] is caller-owned scratch.
+ * Multi-GPU data-parallel training keeps the per-step calls with the all-reduce in between. */
+int gmpc_critic_train_scan(gmpc_handle* h, int32_t steps, int64_t Bc, int32_t T1,
+                           const float* data_xseq, const float* data_label, const int32_t* perm,
+                           float* params_flat, float* mom, float* vel, int32_t step0, float lr,
+                           float max_norm, float b1, float b2, float eps, float* losses,
+                           float* grad_scratch, void* stream);
+
 /* L2MPC.loss (norm/l2_policy.py:12-18): X[B,T+1,n], desired[B,T+1,n] -> loss[B]. */
 int gmpc_l2_loss(gmpc_handle* h, int64_t B, const float* X, const float* desired, float* loss,
                  void* stream);

@@ -93,6 +93,14 @@ def test_train_critic_scan(built_lib):
         0, torch.from_numpy(perm).long(), util.tt(xs), util.tt(lab), 1e-3, n, F, L, H)
     assert float((dflat.double().cpu() - of).abs().max()) < 2e-5
     assert abs(float(torch.stack(losses).mean()) - float(oloss)) < 1e-5
+    # the single-call scan (gmpc_critic_train_scan) enqueues exactly the same kernels
+    sflat = dev(flat)
+    sm, sv = torch.zeros_like(sflat), torch.zeros_like(sflat)
+    slosses = h.critic_train_scan(dx, dl, dperm, sflat, sm, sv, step0=0, lr=1e-3)
+    # (same reduction order; the fused tail kernel may contract FMAs differently: last-bit tolerance)
+    for a, b in ((sflat, dflat), (sm, dm), (sv, dv), (slosses, torch.stack(losses).reshape(-1))):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-9)
+    assert float((sflat.double().cpu() - of).abs().max()) < 2e-5
 
 
 def test_golden_critic(built_lib):
