@@ -61,7 +61,7 @@ struct HLayer {
   int nblk;                // 128-row blocks
   int ksteps;              // reduction length / 16 (may be odd: the last group of a block is then one k-step)
   int next_kpad;           // round_up(M_true, 16): features the epilogue defines in the next operand
-  int rows[2];             // stored A rows of block 0 / 1 (multiple of 16, >= 32, <= 128): the MMA reads
+  int rows[4];             // stored A rows of block b (multiple of 16, >= 32, <= 128): the MMA reads
                            // 128 rows, the rows past rows[b] alias later bytes and land in unused lanes
 };
 struct HDir {
@@ -74,6 +74,7 @@ struct HParams {
   HDir dir[4];
   int n, m, T, K;
   int fout, mode, method, iters, use_cost, final_fwd, ntiles, nslot;
+  int wide, pad1_;  // wide: hidden width in (256, 512] -> 3-4 row blocks, serial layer schedule (see kernel)
   uint32_t hb_bytes, exp_;  // exp_: timing experiments (GMPC_H16_EXP with GMPC_DEBUG: 1 = no weight stream,
                             // 2 = no operand stores); honoured by the TIMED instantiation only, results are garbage
   const uint2* gtab[4];     // per pass: {byte offset in the pass image, bytes} of every ring group
@@ -138,11 +139,12 @@ struct HSmem {
   // offsets inside one staging buffer (two buffers ping-pong, filled one step ahead by cp.async)
   int o_pu, o_pg, o_px, o_pm, o_pv, o_su, o_sd;
 };
-__host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int n, int m, int fout, int ngroups_total) {
+__host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int n, int m, int fout, int ngroups_total,
+                                               int wide) {
   HSmem s;
   s.ring = 0;
   s.hb0 = (uint32_t)nslot * H_SLOT_BYTES;
-  s.hb1 = s.hb0 + hb_bytes;
+  s.hb1 = wide ? s.hb0 : s.hb0 + hb_bytes;  // wide: one buffer, rewritten in place between layers
   s.sb = s.hb1 + hb_bytes;
   s.small = s.sb + H_SB_BYTES;
   int r = 0;
@@ -175,7 +177,7 @@ template <bool TIMED>
 __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_constant__ HParams P) {
   extern __shared__ __align__(128) uint8_t hsm[];
   const HSmem L = h_smem_layout(P.nslot, P.hb_bytes, P.n, P.m, P.fout,
-                                (int)(P.ngroups[0] + P.ngroups[1] + P.ngroups[2] + P.ngroups[3]));
+                                (int)(P.ngroups[0] + P.ngroups[1] + P.ngroups[2] + P.ngroups[3]), P.wide);
   uint8_t* ring = hsm + L.ring;
   uint8_t* HB0 = hsm + L.hb0;
   uint8_t* HB1 = hsm + L.hb1;
@@ -397,11 +399,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
               }
               continue;
             }
-            const bool two_parts = (l > 0) && (prev_nblk > 1);
+            const bool two_parts = !P.wide && (l > 0) && (prev_nblk > 1);
             prev_nblk = nblk;
             const uint64_t b_desc0 = umma_smem_desc((l == 0) ? sb_a : hb_a[(l - 1) & 1], H_B_LBO, H_B_SBO);
             const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
-            const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + d_off;
+            const uint32_t d_base = tmem_base + (P.wide ? 0u : (lc & 1) * H_TMEM_BUF) + d_off;
             if (TIMED) tt = clock64();
             mbar_wait_a(act_a, act_ph0);
             if (TIMED) { const long long dt = clock64() - tt; t_act += dt; if (kind == DIR_DYN_F || kind == DIR_DYN_B) t_actl[l & 3] += dt; }
@@ -412,6 +414,16 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
               a_blk = (uint32_t)(which * rows * 32) >> 4 | ((uint32_t)(rows * 16) >> 4) << 16;
               a_k2 = (uint32_t)(rows * 64) >> 4;
             };
+            if (P.wide) {
+              // serial schedule: the operand is complete, all blocks go out back to back into the
+              // single accumulator buffer, one commit for the layer
+              for (int b = 0; b < nblk; ++b) {
+                set_block(Y.rows[b]);
+                issue(0, ngrp, odd, d_base + b * H_TMEM_BLK, b_lo0, b_hi, 0u);
+              }
+              umma_commit_a(acc_a);
+              continue;
+            }
             set_block(Y.rows[0]);
             // block 0: groups [0, 4) (k-steps 0..7) need operand part 0 only; the rest need part 1
             const bool probe = TIMED && kind == DIR_DYN_F && l == 2;
@@ -479,8 +491,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     float* wsM = P.ws_M + (size_t)blockIdx.x * T * m * H_NB;
     float* wsV = P.ws_V + (size_t)blockIdx.x * T * m * H_NB;
     float* wsS = P.ws_S + (size_t)blockIdx.x * T * 2 * H_NB;  // saved staging-cost norms
-    uint32_t* wsMask = P.ws_mask + (size_t)blockIdx.x * ((size_t)T * (Ld - 1) + (Lc - 1)) * H_COMPUTE;
-    uint32_t* costMask = wsMask + (size_t)T * (Ld - 1) * H_COMPUTE;
+    const int MSTR = (P.wide ? 2 : 1) * H_COMPUTE;  // mask words per (step, layer): 32 bits cover 2 blocks x 16 columns
+    uint32_t* wsMask = P.ws_mask + (size_t)blockIdx.x * ((size_t)T * (Ld - 1) + (Lc - 1)) * MSTR;
+    uint32_t* costMask = wsMask + (size_t)T * (Ld - 1) * MSTR;
     const bool adam = (P.mode == MODE_PLAN && P.method == 1);
     const bool need_goal = cost_mode || P.mode == MODE_L2GRAD;
 
@@ -510,7 +523,50 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     // hidden layer li of a pass: TMEM -> (+bias, relu, mask) or (mask gate) -> hi/lo -> HB[li & 1]
     const int f0 = q * 32 + lane;  // this thread's feature in row block 0 (block 1: +128)
     bool probe_layer = false;
+    // wide layers (3-4 row blocks): serial schedule.  All MMAs of the layer are complete before the
+    // single operand buffer is rewritten in place; one publish when every block has been written.
+    auto hidden_epilogue_wide = [&](const HLayer& Y, bool fwd, uint32_t* maskp) {
+      const uint32_t d_base = tmem_base + t_lane + c0;
+      const float inv = *Y.inv_scale;
+      if (timed) tq = clock64();
+      mbar_wait_a(acc_sa, acc_ph0);
+      acc_ph0 ^= 1;
+      if (timed) { const long long t1 = clock64(); t_acc += t1 - tq; tq = t1; }
+      tc_fence_after();
+      for (int b = 0; b < Y.nblk; ++b) {
+        const int f = b * 128 + f0;
+        uint32_t* mp = maskp + (b >> 1) * H_COMPUTE + ct;
+        uint32_t mw = (fwd && !(b & 1)) ? 0u : *mp;
+        const float bias = (fwd && f < Y.M_true) ? Y.bias[f] : 0.f;
+        uint32_t d1[16], d2[16], d3[16];
+        tmem_ld16_issue(d_base + b * H_TMEM_BLK, d1);
+        tmem_ld16_issue(d_base + b * H_TMEM_BLK + H_NB, d2);
+        tmem_ld16_issue(d_base + b * H_TMEM_BLK + 2 * H_NB, d3);
+        tmem_ld_wait();
+        if (f < Y.next_kpad) {
+          const bool live = f < Y.M_true;
+          float v[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float z = live ? fmaf(__uint_as_float(d1[c]) + (__uint_as_float(d2[c]) + __uint_as_float(d3[c])), inv, bias) : 0.f;
+            if (fwd) {
+              if (z > 0.f) mw |= 1u << ((b & 1) * 16 + c);
+              z = fmaxf(z, 0.f);
+            } else {
+              z = ((mw >> ((b & 1) * 16 + c)) & 1u) ? z : 0.f;
+            }
+            v[c] = z;
+          }
+          store_row16(HB0, f, v);
+        }
+        if (fwd) *mp = mw;
+      }
+      publish(0);
+      if (timed) t_epi += clock64() - tq;
+      ++lc;
+    };
     auto hidden_epilogue = [&](const HLayer& Y, int li, bool fwd, uint32_t* maskp) {
+      if (P.wide) { hidden_epilogue_wide(Y, fwd, maskp); return; }
       uint8_t* dst = (li & 1) ? HB1 : HB0;
       const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + t_lane + c0;
       uint32_t mw = fwd ? 0u : maskp[ct];
@@ -565,7 +621,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     // last layer of a pass (<= 32 output features): every warp keeps the barrier phase, the two
     // f-warps load their 16 columns of the accumulator: out[c] = (d1 + d2) * inv_scale
     auto final_load = [&](const HLayer& Y, float (&out)[16]) {
-      const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + t_lane + c0;
+      const uint32_t d_base = tmem_base + (P.wide ? 0u : (lc & 1) * H_TMEM_BUF) + t_lane + c0;
       const float inv = *Y.inv_scale;
       if (timed) tq = clock64();
       mbar_wait_a(acc_sa, acc_ph0);
@@ -751,7 +807,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           const HDir& D = P.dir[DIR_DYN_F];
           for (int l = 0; l < D.L - 1; ++l) {
             probe_layer = timed && (l == 1);
-            hidden_epilogue(D.layer[l], l, true, wsMask + ((size_t)t * (Ld - 1) + l) * H_COMPUTE);
+            hidden_epilogue(D.layer[l], l, true, wsMask + ((size_t)t * (Ld - 1) + l) * MSTR);
             probe_layer = false;
             if (l == 0) {
               // layer 0 has consumed SB.  Fetch step t+1's slices, then (barrier) x_t and the
@@ -805,7 +861,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         if (P.use_cost) {
           const HDir& D = P.dir[DIR_COST_F];
           for (int l = 0; l < D.L - 1; ++l)
-            hidden_epilogue(D.layer[l], l, true, costMask + (size_t)l * H_COMPUTE);
+            hidden_epilogue(D.layer[l], l, true, costMask + (size_t)l * MSTR);
           float o[16];
           const HLayer& Yf = D.layer[D.L - 1];
           const float bias = (fwarp && lane < P.fout) ? Yf.bias[lane] : 0.f;
@@ -847,7 +903,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           publish(0);  // seed operand of the cost MLP's backward pass
           const HDir& D = P.dir[DIR_COST_B];
           for (int lb = 0; lb < D.L - 1; ++lb)
-            hidden_epilogue(D.layer[lb], lb, false, costMask + (size_t)(D.L - 2 - lb) * H_COMPUTE);
+            hidden_epilogue(D.layer[lb], lb, false, costMask + (size_t)(D.L - 2 - lb) * MSTR);
           float o[16];
           final_load(D.layer[D.L - 1], o);
           if (fwarp && lane < n) {
@@ -913,7 +969,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           const float* B = stbuf(t);
           for (int lb = 0; lb < D.L - 1; ++lb) {
             hidden_epilogue(D.layer[lb], lb, false,
-                            wsMask + ((size_t)t * (Ld - 1) + (D.L - 2 - lb)) * H_COMPUTE);
+                            wsMask + ((size_t)t * (Ld - 1) + (D.L - 2 - lb)) * MSTR);
             if (lb == 0) {
               if (t > 0) prefetch(t - 1, true); else prefetch_none();
               prefetch_wait1();  // slices of step t landed
@@ -1044,7 +1100,7 @@ __global__ void h16_absmax_kernel(const float* __restrict__ W, int count, uint32
 //   transposed == 1 (adjoint):  A rows r = input feature k,  reduction kk = output feature n.
 // Block b stores rows_b rows: k-step image = [hi unit | lo unit], unit = [2 k-chunks][rows_b][8 halfs].
 __global__ void h16_pack_kernel(const float* __restrict__ W, int K, int N, int transposed,
-                                uint8_t* dst, int ksteps, int rows0, int rows1,
+                                uint8_t* dst, int ksteps, int rows0, int rows1, int rows2, int rows3,
                                 const uint32_t* absmax, float* inv_scale) {
   const float mx = __uint_as_float(*absmax);
   float sc = 1.f;
@@ -1062,9 +1118,11 @@ __global__ void h16_pack_kernel(const float* __restrict__ W, int K, int N, int t
   __half hi, lo;
   split_h1(W[idx] * sc, hi, lo);
   const int b = r >> 7, rr = r & 127, j = kk >> 4, k16 = kk & 15;
-  const int rows = b ? rows1 : rows0;
+  const int rowsv[4] = {rows0, rows1, rows2, rows3};
+  const int rows = rowsv[b];
   const size_t unit = (size_t)rows * 32;
-  const size_t blk_base = b ? (size_t)ksteps * 2 * rows0 * 32 : 0;
+  size_t blk_base = 0;
+  for (int bb = 0; bb < b; ++bb) blk_base += (size_t)ksteps * 2 * rowsv[bb] * 32;
   uint8_t* p = dst + blk_base + (size_t)j * 2 * unit + (size_t)(k16 >> 3) * rows * 16 + (rr >> 3) * H_A_SBO +
                (rr & 7) * 16 + (k16 & 7) * 2;
   *reinterpret_cast<__half*>(p) = hi;
@@ -1088,6 +1146,7 @@ struct H16State {
   uint32_t* d_absmax = nullptr;
   uint32_t hb_bytes = 0;
   int nslot = 0;
+  int wide = 0;                // hidden width in (256, 512]: serial layer schedule
   size_t smem_bytes = 0;
   int num_sms = 0;
   int n = 0, m = 0, fout = 0;
@@ -1101,8 +1160,8 @@ inline void h16_layer_geom(HLayer& Y, int M_true, int red_true) {
   Y.M_true = M_true;
   Y.nblk = (M_true + 127) / 128;
   Y.ksteps = rup(red_true, 16) / 16;
-  Y.rows[0] = Y.nblk > 1 ? 128 : std::max(32, rup(M_true, 16));
-  Y.rows[1] = Y.nblk > 1 ? std::max(32, rup(M_true - 128, 16)) : 0;
+  for (int b = 0; b < 4; ++b)
+    Y.rows[b] = b < Y.nblk - 1 ? 128 : (b == Y.nblk - 1 ? std::max(32, rup(M_true - 128 * b, 16)) : 0);
   Y.next_kpad = rup(M_true, 16);
   Y.bias = nullptr;
   Y.gsrc = nullptr;
@@ -1110,7 +1169,7 @@ inline void h16_layer_geom(HLayer& Y, int M_true, int red_true) {
 }
 
 inline size_t h16_layer_bytes(const HLayer& Y) {
-  return (size_t)Y.ksteps * 64 * (Y.rows[0] + Y.rows[1]);
+  return (size_t)Y.ksteps * 64 * (Y.rows[0] + Y.rows[1] + Y.rows[2] + Y.rows[3]);
 }
 
 inline size_t h16_build_geometry(H16State& S) {
@@ -1148,7 +1207,8 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
   for (int i = 1; i < S.Lc; ++i) hmax = std::max(hmax, cost_dims[i]);
   S.supported = false;
   if (S.Ld < 2) { S.why = "dynamics MLP has no hidden layer"; return GMPC_OK; }
-  if (hmax > 256) { S.why = "hidden width > 256 (two 128-row MMA blocks)"; return GMPC_OK; }
+  if (hmax > 512) { S.why = "hidden width > 512 (four 128-row MMA blocks)"; return GMPC_OK; }
+  S.wide = hmax > 256 ? 1 : 0;
   if (c.n + c.m > 32 || c.cost_fout > 32) { S.why = "n+m or fout > 32"; return GMPC_OK; }
   S.hb_bytes = (uint32_t)(rup(hmax, 16) / 8) * H_B_LBO;
   const size_t budget = (size_t)prop.sharedMemPerBlockOptin;
@@ -1156,13 +1216,13 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
   int ng_total = 0;
   for (int d = 0; d < 4; ++d)
     for (int l = 0; l < S.dir[d].L; ++l) ng_total += S.dir[d].layer[l].nblk * ((S.dir[d].layer[l].ksteps + 1) / 2);
-  const HSmem L0 = h_smem_layout(0, S.hb_bytes, c.n, c.m, c.cost_fout, ng_total);
+  const HSmem L0 = h_smem_layout(0, S.hb_bytes, c.n, c.m, c.cost_fout, ng_total, S.wide);
   int nslot = (int)((budget - std::min(budget, (size_t)L0.total)) / H_SLOT_BYTES);
   nslot = std::min(nslot, H_MAX_SLOTS);
   if (const char* env = getenv("GMPC_H16_SLOTS")) nslot = std::min(nslot, std::max(2, atoi(env)));
   if (nslot < 4) { S.why = "shared memory"; return GMPC_OK; }
   S.nslot = nslot;
-  S.smem_bytes = h_smem_layout(nslot, S.hb_bytes, c.n, c.m, c.cost_fout, ng_total).total;
+  S.smem_bytes = h_smem_layout(nslot, S.hb_bytes, c.n, c.m, c.cost_fout, ng_total, S.wide).total;
   size_t nbias = 0;
   for (int l = 0; l < S.Ld; ++l) nbias += rup(dyn_dims[l + 1], 4);
   for (int l = 0; l < S.Lc; ++l) nbias += rup(cost_dims[l + 1], 4);
@@ -1278,9 +1338,11 @@ inline int h16_set_weights(H16State& S, const float* const* dyn_W, const float* 
       const HLayer& r = Bw.layer[Ln - 1 - l];
       h16_absmax_kernel<<<std::min(blocks, 64), 256, 0, st>>>(W[l], K * N, S.d_absmax + sbase + l);
       h16_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 0, const_cast<uint8_t*>(f.gsrc), f.ksteps,
-                                              f.rows[0], f.rows[1], S.d_absmax + sbase + l, S.d_scale + sbase + l);
+                                              f.rows[0], f.rows[1], f.rows[2], f.rows[3], S.d_absmax + sbase + l,
+                                              S.d_scale + sbase + l);
       h16_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 1, const_cast<uint8_t*>(r.gsrc), r.ksteps,
-                                              r.rows[0], r.rows[1], S.d_absmax + sbase + l, S.d_scale + sbase + l);
+                                              r.rows[0], r.rows[1], r.rows[2], r.rows[3], S.d_absmax + sbase + l,
+                                              S.d_scale + sbase + l);
       *launches += 3;
       cudaMemcpyAsync(const_cast<float*>(f.bias), b[l], sizeof(float) * N, cudaMemcpyDeviceToDevice, st);
     }
@@ -1306,6 +1368,7 @@ inline int h16_launch(H16State& S, const PlanParams& P, cudaStream_t st, int64_t
   Q.fout = P.fout; Q.mode = P.mode; Q.method = P.method; Q.iters = P.iters;
   Q.use_cost = P.use_cost; Q.final_fwd = P.final_fwd;
   Q.nslot = S.nslot;
+  Q.wide = S.wide;
   Q.hb_bytes = S.hb_bytes;
   for (int d = 0; d < 4; ++d) { Q.gtab[d] = S.d_gtab + S.gtab_off[d]; Q.ngroups[d] = S.ngroups[d]; }
   if (const char* env = getenv("GMPC_H16_EXP")) Q.exp_ = (uint32_t)atoi(env);
