@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(synthetic.CONFIGS))
-    ap.add_argument("--path", default="auto", choices=["auto", "ffma", "tc", "tc16"])
+    ap.add_argument("--path", default="auto", choices=["auto", "ffma", "tc", "tc16", "tc16s"])
     ap.add_argument("--lr", type=float, default=1e-2)
     ap.add_argument("--batch", type=int, default=0, help="override states per GPU")
     ap.add_argument("--ref-seconds", type=float, default=15.0)

@@ -14,9 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgmpc.so")
 
 METHOD_GRAD, METHOD_ADAM = 0, 1
-PATH_AUTO, PATH_FFMA, PATH_TC, PATH_TC16 = 0, 1, 2, 3
+PATH_AUTO, PATH_FFMA, PATH_TC, PATH_TC16, PATH_TC16S = 0, 1, 2, 3, 4
 METHODS = {"grad": METHOD_GRAD, "adam": METHOD_ADAM}
-PATHS = {"auto": PATH_AUTO, "ffma": PATH_FFMA, "tc": PATH_TC, "tc16": PATH_TC16}
+PATHS = {"auto": PATH_AUTO, "ffma": PATH_FFMA, "tc": PATH_TC, "tc16": PATH_TC16, "tc16s": PATH_TC16S}
 
 
 class GmpcError(RuntimeError):
@@ -141,7 +141,7 @@ class Handle:
 
     @property
     def last_path(self):
-        return {PATH_FFMA: "ffma", PATH_TC: "tc", PATH_TC16: "tc16"}[self.lib.gmpc_last_path(self._h)]
+        return {PATH_FFMA: "ffma", PATH_TC: "tc", PATH_TC16: "tc16", PATH_TC16S: "tc16s"}[self.lib.gmpc_last_path(self._h)]
 
     def range_overflow(self):
         """CTAs of the fp16-split kernel that clamped an operand since the last call (synchronises)."""

@@ -50,6 +50,8 @@ struct gmpc_handle {
   int num_sms = 0;
   int path = GMPC_PATH_AUTO;
   int last_path = GMPC_PATH_FFMA;
+  bool auto_retry = false;   // gmpc_plan_host was entered with path AUTO (range-check retries allowed)
+  bool in_retry = false;
   int64_t launches = 0;
   bool have_weights = false;
   int maxt = 1;
@@ -261,10 +263,10 @@ extern "C" int64_t gmpc_critic_param_count(const gmpc_handle* h) {
 }
 
 extern "C" int gmpc_set_path(gmpc_handle* h, int path) {
-  if (!h || path < GMPC_PATH_AUTO || path > GMPC_PATH_TC16) return fail(GMPC_E_ARG, "gmpc_set_path: bad argument");
+  if (!h || path < GMPC_PATH_AUTO || path > GMPC_PATH_TC16S) return fail(GMPC_E_ARG, "gmpc_set_path: bad argument");
   if (path == GMPC_PATH_TC && !h->tc.supported)
     return fail(GMPC_E_UNSUPPORTED, "gmpc_set_path: tensor-core path unsupported for this shape: " + h->tc.why);
-  if (path == GMPC_PATH_TC16 && !h->h16.supported)
+  if ((path == GMPC_PATH_TC16 || path == GMPC_PATH_TC16S) && !h->h16.supported)
     return fail(GMPC_E_UNSUPPORTED, "gmpc_set_path: tensor-core path unsupported for this shape: " + h->h16.why);
   h->path = path;
   return GMPC_OK;
@@ -331,9 +333,9 @@ static int launch_ffma(gmpc_handle* h, PlanParams& P, cudaStream_t st) {
   const int grid = std::min(P.ntiles, h->num_sms);
   if (grid <= 0) return GMPC_OK;
   const int path = pick_path(h, P.NQ);
-  if (path == GMPC_PATH_TC || path == GMPC_PATH_TC16) {
+  if (path == GMPC_PATH_TC || path == GMPC_PATH_TC16 || path == GMPC_PATH_TC16S) {
     int rc = path == GMPC_PATH_TC ? tc_launch(h->tc, P, st, &h->launches)
-                                  : h16_launch(h->h16, P, st, &h->launches);
+                                  : h16_launch(h->h16, P, path == GMPC_PATH_TC16S, st, &h->launches);
     if (rc) return fail(rc, "tensor-core planner launch failed");
     h->last_path = path;
     return GMPC_OK;
@@ -475,6 +477,7 @@ extern "C" int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float*
                               int32_t* idx_best_host, float* J_all_host, void* stream) {
   int rc = check_ready(h, "gmpc_plan_host", B);
   if (rc) return rc;
+  if (!h->in_retry) h->auto_retry = (h->path == GMPC_PATH_AUTO);  // decided by the outermost call
   if (B == 0) return GMPC_OK;
   if (K < 1) return fail(GMPC_E_ARG, "gmpc_plan_host: K must be >= 1");
   if (!x0_host || !U0_host || !goal_host || !U_best_host || !X_best_host || !J_best_host ||
@@ -509,19 +512,23 @@ extern "C" int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float*
   if (J_all_host)
     CU_CHECK(cudaMemcpyAsync(J_all_host, d_Ja, f_Ja * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_CHECK(cudaStreamSynchronize(st));
-  if (h->last_path == GMPC_PATH_TC16) {
+  if (h->last_path == GMPC_PATH_TC16 || h->last_path == GMPC_PATH_TC16S) {
     int32_t clamped = 0;
     rc = gmpc_range_overflow(h, &clamped, stream);
     if (rc) return rc;
     if (clamped > 0) {
-      // an operand left the fp16-split kernel's range: the plan is re-done on the fp32 CUDA-core
-      // kernel (still the GPU; there is no CPU path) when the caller left the choice to us
-      if (h->path != GMPC_PATH_AUTO)
+      // an operand left the fp16-split kernel's range: when the caller left the choice to us the plan
+      // is re-done with forward rescaling and, should even that clamp, on the fp32 CUDA-core kernel
+      // (still the GPU; there is no CPU path)
+      if (!h->auto_retry)
         return fail(GMPC_E_UNSUPPORTED, "gmpc_plan_host: operand magnitude above 65000 on the fp16-split path; "
-                                        "use GMPC_PATH_AUTO, GMPC_PATH_FFMA or GMPC_PATH_TC");
-      h->path = GMPC_PATH_FFMA;
+                                        "use GMPC_PATH_AUTO, GMPC_PATH_TC16S, GMPC_PATH_FFMA or GMPC_PATH_TC");
+      const int retry = h->last_path == GMPC_PATH_TC16 ? GMPC_PATH_TC16S : GMPC_PATH_FFMA;
+      h->path = retry;
+      h->in_retry = true;
       rc = gmpc_plan_host(h, B, K, x0_host, U0_host, goal_host, method, N, lr, b1, b2, eps, U_best_host,
                           X_best_host, J_best_host, idx_best_host, J_all_host, stream);
+      h->in_retry = false;
       h->path = GMPC_PATH_AUTO;
       return rc;
     }

@@ -82,4 +82,9 @@ __device__ __forceinline__ float pow2_scale_to_8(float v) {
   return __uint_as_float((uint32_t)(k + 127) << 23);
 }
 
+// 1 / s for s an exact power of two (normal range): one integer subtract instead of a division.
+__device__ __forceinline__ float pow2_recip(float s) {
+  return __uint_as_float(0x7F000000u - __float_as_uint(s));
+}
+
 }  // namespace gmpc

@@ -163,7 +163,8 @@ __host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int
   s.st_rows = o;
   s.r_st = r; r += 3 * o;   // three staging buffers (t % 3)
   s.r_part = r; r += 32;  // per-warp partial sums of the two staging-cost norms, two generations
-  s.r_sc = r; r += 2;     // 1/scale of the adjoint operand in flight, scale for the next one
+  s.r_sc = r; r += 5;     // 1/scale of the adjoint operand in flight, scale for the next one,
+                          // two generations (step parity) of the forward operand scale
   s.rows = r;
   s.gtab = s.small + (uint32_t)r * H_SROW * 4;
   s.gtab = (s.gtab + 15u) & ~15u;
@@ -173,11 +174,14 @@ __host__ __device__ inline HSmem h_smem_layout(int nslot, uint32_t hb_bytes, int
   return s;
 }
 
-template <bool TIMED>
+// FSCALE: per-trajectory power-of-two scaling of the FORWARD operands as well (states of any
+// magnitude); without it the forward pass assumes |state|, |action|, |activation| < 65000 and
+// counts clamps (HParams::ovf).  The adjoint sweep is always rescaled.
+template <bool TIMED, bool WIDE, bool FSCALE>
 __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_constant__ HParams P) {
   extern __shared__ __align__(128) uint8_t hsm[];
   const HSmem L = h_smem_layout(P.nslot, P.hb_bytes, P.n, P.m, P.fout,
-                                (int)(P.ngroups[0] + P.ngroups[1] + P.ngroups[2] + P.ngroups[3]), P.wide);
+                                (int)(P.ngroups[0] + P.ngroups[1] + P.ngroups[2] + P.ngroups[3]), WIDE);
   uint8_t* ring = hsm + L.ring;
   uint8_t* HB0 = hsm + L.hb0;
   uint8_t* HB1 = hsm + L.hb1;
@@ -191,6 +195,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
   float* part_s = small + L.r_part * H_SROW;  // [8] partial |x-goal|^2, then [8] partial |u|^2
   float* isc_s = small + L.r_sc * H_SROW;     // 1 / scale of the adjoint operand in flight
   float* snx_s = isc_s + H_SROW;              // scale for the next adjoint operand
+  // [2][32] forward operand scale of step t in row (t & 1), 16-byte aligned for vector loads
+  float* fsc_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(snx_s + H_SROW) + 15) & ~(uintptr_t)15);
+  constexpr int FSR = H_NB;                   // row stride of fsc_s
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(hsm + L.bars);
   uint64_t* empty_bar = full_bar + H_MAX_SLOTS;
   uint64_t* acc_bar = empty_bar + H_MAX_SLOTS;  // [2]: accumulator block b complete
@@ -399,11 +406,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
               }
               continue;
             }
-            const bool two_parts = !P.wide && (l > 0) && (prev_nblk > 1);
+            const bool two_parts = !WIDE && (l > 0) && (prev_nblk > 1);
             prev_nblk = nblk;
             const uint64_t b_desc0 = umma_smem_desc((l == 0) ? sb_a : hb_a[(l - 1) & 1], H_B_LBO, H_B_SBO);
             const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
-            const uint32_t d_base = tmem_base + (P.wide ? 0u : (lc & 1) * H_TMEM_BUF) + d_off;
+            const uint32_t d_base = tmem_base + (WIDE ? 0u : (lc & 1) * H_TMEM_BUF) + d_off;
             if (TIMED) tt = clock64();
             mbar_wait_a(act_a, act_ph0);
             if (TIMED) { const long long dt = clock64() - tt; t_act += dt; if (kind == DIR_DYN_F || kind == DIR_DYN_B) t_actl[l & 3] += dt; }
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
               a_blk = (uint32_t)(which * rows * 32) >> 4 | ((uint32_t)(rows * 16) >> 4) << 16;
               a_k2 = (uint32_t)(rows * 64) >> 4;
             };
-            if (P.wide) {
+            if (WIDE) {
               // serial schedule: the operand is complete, all blocks go out back to back into the
               // single accumulator buffer, one commit for the layer
               for (int b = 0; b < nblk; ++b) {
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     float* wsM = P.ws_M + (size_t)blockIdx.x * T * m * H_NB;
     float* wsV = P.ws_V + (size_t)blockIdx.x * T * m * H_NB;
     float* wsS = P.ws_S + (size_t)blockIdx.x * T * 2 * H_NB;  // saved staging-cost norms
-    const int MSTR = (P.wide ? 2 : 1) * H_COMPUTE;  // mask words per (step, layer): 32 bits cover 2 blocks x 16 columns
+    const int MSTR = (WIDE ? 2 : 1) * H_COMPUTE;  // mask words per (step, layer): 32 bits cover 2 blocks x 16 columns
     uint32_t* wsMask = P.ws_mask + (size_t)blockIdx.x * ((size_t)T * (Ld - 1) + (Lc - 1)) * MSTR;
     uint32_t* costMask = wsMask + (size_t)T * (Ld - 1) * MSTR;
     const bool adam = (P.mode == MODE_PLAN && P.method == 1);
@@ -525,7 +532,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     bool probe_layer = false;
     // wide layers (3-4 row blocks): serial schedule.  All MMAs of the layer are complete before the
     // single operand buffer is rewritten in place; one publish when every block has been written.
-    auto hidden_epilogue_wide = [&](const HLayer& Y, bool fwd, uint32_t* maskp) {
+    auto hidden_epilogue_wide = [&](const HLayer& Y, bool fwd, uint32_t* maskp, const float* fsc) {
       const uint32_t d_base = tmem_base + t_lane + c0;
       const float inv = *Y.inv_scale;
       if (timed) tq = clock64();
@@ -533,6 +540,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       acc_ph0 ^= 1;
       if (timed) { const long long t1 = clock64(); t_acc += t1 - tq; tq = t1; }
       tc_fence_after();
+      float sc[16];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 q4 = (FSCALE && fwd) ? *reinterpret_cast<const float4*>(fsc + c0 + 4 * c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+        sc[4 * c4] = q4.x; sc[4 * c4 + 1] = q4.y; sc[4 * c4 + 2] = q4.z; sc[4 * c4 + 3] = q4.w;
+      }
       for (int b = 0; b < Y.nblk; ++b) {
         const int f = b * 128 + f0;
         uint32_t* mp = maskp + (b >> 1) * H_COMPUTE + ct;
@@ -548,7 +561,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           float v[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            float z = live ? fmaf(__uint_as_float(d1[c]) + (__uint_as_float(d2[c]) + __uint_as_float(d3[c])), inv, bias) : 0.f;
+            float z = live ? fmaf(__uint_as_float(d1[c]) + (__uint_as_float(d2[c]) + __uint_as_float(d3[c])), inv, bias * sc[c]) : 0.f;
             if (fwd) {
               if (z > 0.f) mw |= 1u << ((b & 1) * 16 + c);
               z = fmaxf(z, 0.f);
@@ -565,8 +578,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       if (timed) t_epi += clock64() - tq;
       ++lc;
     };
-    auto hidden_epilogue = [&](const HLayer& Y, int li, bool fwd, uint32_t* maskp) {
-      if (P.wide) { hidden_epilogue_wide(Y, fwd, maskp); return; }
+    // `fsc` (forward only): the 32 per-trajectory scales of the operand in flight.  The forward pass
+    // runs in scaled units a' = a * s (ReLU is positively homogeneous), so the bias enters as b * s.
+    auto hidden_epilogue = [&](const HLayer& Y, int li, bool fwd, uint32_t* maskp, const float* fsc) {
+      if (WIDE) { hidden_epilogue_wide(Y, fwd, maskp, fsc); return; }
       uint8_t* dst = (li & 1) ? HB1 : HB0;
       const uint32_t d_base = tmem_base + (lc & 1) * H_TMEM_BUF + t_lane + c0;
       uint32_t mw = fwd ? 0u : maskp[ct];
@@ -593,6 +608,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           tmem_ld16_issue(d_base + b * H_TMEM_BLK, d1);
           tmem_ld16_issue(d_base + b * H_TMEM_BLK + H_NB, d2);
           tmem_ld16_issue(d_base + b * H_TMEM_BLK + 2 * H_NB, d3);
+          float sc[16];  // fetched while the TMEM loads are in flight, not live across the wait above
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 q4 = (FSCALE && fwd) ? *reinterpret_cast<const float4*>(fsc + c0 + 4 * c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+            sc[4 * c4] = q4.x; sc[4 * c4 + 1] = q4.y; sc[4 * c4 + 2] = q4.z; sc[4 * c4 + 3] = q4.w;
+          }
           tmem_ld_wait();
           const int f = b * 128 + f0;
           if (f < Y.next_kpad) {
@@ -600,7 +621,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             float v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-              float z = live ? fmaf(__uint_as_float(d1[c]) + (__uint_as_float(d2[c]) + __uint_as_float(d3[c])), inv, bias[b]) : 0.f;
+              float z = live ? fmaf(__uint_as_float(d1[c]) + (__uint_as_float(d2[c]) + __uint_as_float(d3[c])), inv, bias[b] * sc[c]) : 0.f;
               if (fwd) {
                 if (z > 0.f) mw |= 1u << (b * 16 + c);
                 z = fmaxf(z, 0.f);
@@ -621,7 +642,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     // last layer of a pass (<= 32 output features): every warp keeps the barrier phase, the two
     // f-warps load their 16 columns of the accumulator: out[c] = (d1 + d2) * inv_scale
     auto final_load = [&](const HLayer& Y, float (&out)[16]) {
-      const uint32_t d_base = tmem_base + (P.wide ? 0u : (lc & 1) * H_TMEM_BUF) + t_lane + c0;
+      const uint32_t d_base = tmem_base + (WIDE ? 0u : (lc & 1) * H_TMEM_BUF) + t_lane + c0;
       const float inv = *Y.inv_scale;
       if (timed) tq = clock64();
       mbar_wait_a(acc_sa, acc_ph0);
@@ -675,9 +696,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     // u rows (features n .. n+m-1) of the forward operand q = [x ; u], from the staged U[t]
     auto sb_u_rows = [&](int t) {
       const float* pu = stbuf(t) + L.o_pu * H_SROW;
+      const float* fs = fsc_s + (t & 1) * FSR;
       for (int e = ct; e < m * H_NB; e += H_COMPUTE) {
         const int j = e / H_NB, r = e - j * H_NB;
-        const float uv = pu[j * H_SROW + r];
+        const float uv = FSCALE ? pu[j * H_SROW + r] * fs[r] : pu[j * H_SROW + r];
         opmax = fmaxf(opmax, fabsf(uv));
         h16_store_op(SB, n + j, r, uv);
       }
@@ -791,12 +813,21 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         named_bar_sync(1, H_COMPUTE);  // the previous sweep's last update is complete
         prefetch(0, false);
         if (T > 1) prefetch(1, false); else prefetch_none();
+        if (ct < H_NB) {  // operand scale of step 0 from x0 (>= 1 so small states never scale the actions up)
+          float mx = 1.f;
+          for (int i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(wsX[i * H_NB + ct]));
+          const float s0 = FSCALE ? pow2_scale_to_8(mx) : 1.f;
+          fsc_s[ct] = s0;
+          fsc_s[FSR + ct] = s0;  // step 1 uses the scale of x_0 as well (scales lag one step)
+        }
+        named_bar_sync(1, H_COMPUTE);
         for (int e = ct; e < n * H_NB; e += H_COMPUTE) {
           const int i = e / H_NB, r = e - i * H_NB;
           const float v = wsX[e];
           x_s[i * H_SROW + r] = v;
-          opmax = fmaxf(opmax, fabsf(v));
-          h16_store_op(SB, i, r, v);
+          const float vs = FSCALE ? v * fsc_s[r] : v;
+          opmax = fmaxf(opmax, fabsf(vs));
+          h16_store_op(SB, i, r, vs);
         }
         Jr = 0.f;
         prefetch_wait1();  // slices of step 0 landed (step 1 may still be in flight)
@@ -807,7 +838,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           const HDir& D = P.dir[DIR_DYN_F];
           for (int l = 0; l < D.L - 1; ++l) {
             probe_layer = timed && (l == 1);
-            hidden_epilogue(D.layer[l], l, true, wsMask + ((size_t)t * (Ld - 1) + l) * MSTR);
+            hidden_epilogue(D.layer[l], l, true, wsMask + ((size_t)t * (Ld - 1) + l) * MSTR, fsc_s + (t & 1) * FSR);
             probe_layer = false;
             if (l == 0) {
               // layer 0 has consumed SB.  Fetch step t+1's slices, then (barrier) x_t and the
@@ -835,19 +866,44 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           final_load(Yf, o);
           const bool more = (t + 1 < T) || P.use_cost;
           if (fwarp && lane < n) {
+            // scales of the operand in flight (step t) and of the next one, as vector loads
+            const float4* fcur = reinterpret_cast<const float4*>(fsc_s + (t & 1) * FSR + c0);
+            const float4* fnxt = reinterpret_cast<const float4*>(fsc_s + ((t + 1) & 1) * FSR + c0);
             float v[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = (o[c] + bias) + xo[c];
-            if (more) store_row16(SB, lane, v);
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 a = FSCALE ? fcur[c4] : one4, b = FSCALE ? fnxt[c4] : one4;
+              const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int c = 0; c < 16; ++c) xo[c] = v[c];
+              for (int k = 0; k < 4; ++k) {
+                const int c = 4 * c4 + k;
+                // the layer ran in scaled units; 1/s is exact (power of two)
+                xo[c] = fmaf(o[c], pow2_recip(av[k]), bias) + xo[c];
+                v[c] = xo[c] * bv[k];
+              }
+            }
+            if (more) store_row16(SB, lane, v);
           }
           if (more) publish(0);
-          if (fwarp && lane < n) {  // off the critical path: keep x_{t+1} for the costs and the adjoint
+          if (fwarp) {  // off the critical path: keep x_{t+1} for the costs and the adjoint
+            float xabs[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              x_s[lane * H_SROW + c0 + c] = xo[c];
-              wsX[(size_t)(t + 1) * n * H_NB + lane * H_NB + c0 + c] = xo[c];
+            for (int c = 0; c < 16; ++c) xabs[c] = lane < n ? fabsf(xo[c]) : 0.f;
+            if (lane < n) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                x_s[lane * H_SROW + c0 + c] = xo[c];
+                wsX[(size_t)(t + 1) * n * H_NB + lane * H_NB + c0 + c] = xo[c];
+              }
+            }
+            // scale of step t+2 from x_{t+1} (one step of lag), written over the row of step t:
+            // its last readers were this warp's loads above and the epilogues of step t
+            if (FSCALE) {
+              const float mx = colmax16(xabs);
+              __syncwarp();
+              if (!(lane & 1)) fsc_s[(t & 1) * FSR + c0 + ((lane >> 1) & 15)] = pow2_scale_to_8(fmaxf(mx, 1.f));
+              __syncwarp();
             }
           }
         }
@@ -861,14 +917,15 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         if (P.use_cost) {
           const HDir& D = P.dir[DIR_COST_F];
           for (int l = 0; l < D.L - 1; ++l)
-            hidden_epilogue(D.layer[l], l, true, costMask + (size_t)l * MSTR);
+            hidden_epilogue(D.layer[l], l, true, costMask + (size_t)l * MSTR, fsc_s + (T & 1) * FSR);
           float o[16];
           const HLayer& Yf = D.layer[D.L - 1];
           const float bias = (fwarp && lane < P.fout) ? Yf.bias[lane] : 0.f;
           final_load(Yf, o);
           if (fwarp && lane < P.fout) {
+            const float* fcur = fsc_s + (T & 1) * FSR;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) y_s[lane * H_SROW + c0 + c] = o[c] + bias;
+            for (int c = 0; c < 16; ++c) y_s[lane * H_SROW + c0 + c] = fmaf(o[c], FSCALE ? pow2_recip(fcur[c0 + c]) : 1.f, bias);
           }
           named_bar_sync(1, H_COMPUTE);
           if (ct < H_NB) {
@@ -903,7 +960,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           publish(0);  // seed operand of the cost MLP's backward pass
           const HDir& D = P.dir[DIR_COST_B];
           for (int lb = 0; lb < D.L - 1; ++lb)
-            hidden_epilogue(D.layer[lb], lb, false, costMask + (size_t)(D.L - 2 - lb) * MSTR);
+            hidden_epilogue(D.layer[lb], lb, false, costMask + (size_t)(D.L - 2 - lb) * MSTR, nullptr);
           float o[16];
           final_load(D.layer[D.L - 1], o);
           if (fwarp && lane < n) {
@@ -969,7 +1026,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           const float* B = stbuf(t);
           for (int lb = 0; lb < D.L - 1; ++lb) {
             hidden_epilogue(D.layer[lb], lb, false,
-                            wsMask + ((size_t)t * (Ld - 1) + (D.L - 2 - lb)) * MSTR);
+                            wsMask + ((size_t)t * (Ld - 1) + (D.L - 2 - lb)) * MSTR, nullptr);
             if (lb == 0) {
               if (t > 0) prefetch(t - 1, true); else prefetch_none();
               prefetch_wait1();  // slices of step t landed
@@ -1030,7 +1087,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             __syncwarp();
             if (t > 0 && !(lane & 1)) {
               const int col = c0 + ((lane >> 1) & 15);
-              isc_s[col] = 1.f / snx_s[col];
+              isc_s[col] = pow2_recip(snx_s[col]);
               snx_s[col] = pow2_scale_to_8(mx);
             }
             __syncwarp();
@@ -1130,6 +1187,14 @@ __global__ void h16_pack_kernel(const float* __restrict__ W, int K, int N, int t
 }
 
 // ------------------------------------------------------------------------------------- host side
+using H16Kernel = void (*)(const HParams);
+// wide layers always run with forward scaling (wide random dynamics over long horizons diverge)
+inline H16Kernel h16_kernel_ptr(bool timed, bool wide, bool fscale) {
+  if (wide) return timed ? plan_h16_kernel<true, true, true> : plan_h16_kernel<false, true, true>;
+  if (fscale) return timed ? plan_h16_kernel<true, false, true> : plan_h16_kernel<false, false, true>;
+  return timed ? plan_h16_kernel<true, false, false> : plan_h16_kernel<false, false, false>;
+}
+
 struct H16State {
   bool supported = false;
   std::string why = "not initialised";
@@ -1268,11 +1333,11 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
     if (cudaMemcpy(S.d_gtab, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess)
       return GMPC_E_CUDA;
   }
-  if (cudaFuncSetAttribute(plan_h16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)S.smem_bytes) != cudaSuccess ||
-      cudaFuncSetAttribute(plan_h16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)S.smem_bytes) != cudaSuccess)
-    return GMPC_E_CUDA;
+  for (int t = 0; t < 2; ++t)
+    for (int f = 0; f < 2; ++f)
+      if (cudaFuncSetAttribute(h16_kernel_ptr(t, S.wide, f), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)S.smem_bytes) != cudaSuccess)
+        return GMPC_E_CUDA;
   for (int C = 2; C <= 4; C *= 2) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1287,7 +1352,7 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, plan_h16_kernel<false>, &cfg) != cudaSuccess) nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, h16_kernel_ptr(false, S.wide, false), &cfg) != cudaSuccess) nc = 0;
     S.max_clusters[C] = nc;
   }
   cudaGetLastError();
@@ -1360,7 +1425,7 @@ inline bool h16_worthwhile(const H16State& S, int64_t NQ) {
   return NQ >= 64 && S.Ld > 1 && hmin >= 64;
 }
 
-inline int h16_launch(H16State& S, const PlanParams& P, cudaStream_t st, int64_t* launches) {
+inline int h16_launch(H16State& S, const PlanParams& P, bool fscale, cudaStream_t st, int64_t* launches) {
   HParams Q;
   memset(&Q, 0, sizeof(Q));
   for (int d = 0; d < 4; ++d) Q.dir[d] = S.dir[d];
@@ -1400,8 +1465,7 @@ inline int h16_launch(H16State& S, const PlanParams& P, cudaStream_t st, int64_t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = S.d_dbg != nullptr ? cudaLaunchKernelEx(&cfg, plan_h16_kernel<true>, Q)
-                                     : cudaLaunchKernelEx(&cfg, plan_h16_kernel<false>, Q);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, h16_kernel_ptr(S.d_dbg != nullptr, S.wide, fscale), Q);
   ++*launches;
   S.last_cluster = C;
   if (S.d_dbg != nullptr && e == cudaSuccess) {

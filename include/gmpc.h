@@ -42,6 +42,8 @@ extern "C" {
 #define GMPC_PATH_FFMA 1 /* fp32 CUDA-core path (exact fp32 FMA arithmetic) */
 #define GMPC_PATH_TC 2   /* tcgen05 3xTF32 tensor-core path (error if shape unsupported) */
 #define GMPC_PATH_TC16 3 /* tcgen05 fp16-split (hi/lo, 3 products, fp32 accumulate) path, pipelined */
+#define GMPC_PATH_TC16S 4 /* same, with per-trajectory power-of-two scaling of the forward operands too
+                            (states of any magnitude; ~6 % slower).  Hidden widths above 256 always use it. */
 
 typedef struct gmpc_config {
   int32_t n;             /* state size x_size                       (dynamics/nn.py:13 x_out) */
@@ -130,7 +132,8 @@ int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float* x0_host,
  * trajectory and cannot overflow) is clamped and counted.  This call synchronises `stream`, returns
  * the number of CTAs that clamped since the last call in *count and resets the counter.  A non-zero
  * count means the results of those calls are outside the 1e-4 parity contract: re-run them with
- * GMPC_PATH_FFMA or GMPC_PATH_TC.  gmpc_plan_host does this by itself when the path is AUTO. */
+ * GMPC_PATH_TC16S (forward operands rescaled per trajectory), GMPC_PATH_FFMA or GMPC_PATH_TC.
+ * gmpc_plan_host does this by itself when the path is AUTO (TC16 -> TC16S -> FFMA). */
 int gmpc_range_overflow(gmpc_handle* h, int32_t* count, void* stream);
 
 /* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */

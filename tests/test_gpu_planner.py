@@ -14,7 +14,7 @@ from tests import util
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-PATHS = ["ffma", "tc", "tc16"]
+PATHS = ["ffma", "tc", "tc16", "tc16s"]
 
 
 def select_path(h, path):
@@ -252,10 +252,10 @@ def test_tc16_range_check_and_auto_fallback(built_lib):
     from gan_mpc_b200 import _lib
     cfg = util.MID
     p, x0, U0, goal = util.case(cfg, 5, B=96, K=1)
-    x0 = x0.copy()
-    x0[3] *= 1e5          # one start state far outside the normalised range
-    goal = goal.copy()
-    goal[3] = x0[3][None, :]
+    # states are rescaled per trajectory inside the kernel (any magnitude is fine); what can still
+    # leave the fp16 range is an action far larger than its own state
+    U0 = U0.copy()
+    U0[3] *= 1e6
     h = util.make_handle(cfg, p)
     op = util.to_oracle(p)
     oU, oX, oJ, oidx, _ = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), op, "grad", 2, 1e-3)
@@ -267,7 +267,7 @@ def test_tc16_range_check_and_auto_fallback(built_lib):
     with pytest.raises(_lib.GmpcError):     # forced path: the host call refuses rather than return clamped plans
         h.plan_host(torch.from_numpy(x0), torch.from_numpy(U0), torch.from_numpy(goal),
                     method="grad", iters=2, lr=1e-3)
-    # AUTO: transparently re-planned on the fp32 kernel
+    # AUTO: transparently re-planned (rescaled variant first, fp32 kernel if that clamps too)
     h.set_path("auto")
     Ub, Xb, Jb, idx, _ = h.plan_host(torch.from_numpy(x0), torch.from_numpy(U0), torch.from_numpy(goal),
                                      method="grad", iters=2, lr=1e-3)
@@ -292,3 +292,41 @@ def test_tc16_ring_depth_independent(slots, built_lib, monkeypatch):
     oU, oX, oJ, _, _ = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), op, "adam", 3, 1e-2)
     Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=3, lr=1e-2)
     assert util.rel_rows(Xb, oX) < TOL and util.rel_rows(Ub, oU) < TOL
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1e3, 1e5])
+def test_tc16s_state_scale_invariance(scale, built_lib):
+    """The tc16s variant of the fp16-split kernel rescales every trajectory's operands by exact powers of two (forward
+    and adjoint), so states far from O(1) keep the 1e-4 parity with the fp64 oracle."""
+    cfg = util.MID
+    p, x0, U0, goal = util.case(cfg, 31, B=64, K=1)
+    x0 = (x0 * scale).astype(np.float32)
+    goal = (goal * scale).astype(np.float32)
+    h = util.make_handle(cfg, p)
+    h.set_path("tc16s")
+    op = util.to_oracle(p)
+    margin = [None]
+    oX, oJ, odU, olam = oracle.objective_grad(util.tt(x0), util.tt(U0[:, 0]), util.tt(goal), op, margin)
+    J, dU, X, lam = h.objective_grad(dev(x0), dev(U0[:, 0]), dev(goal), want_lam=True)
+    assert h.range_overflow() == 0
+    assert util.rel_rows(X, oX) < TOL
+    assert util.rel_rows(J[:, None], oJ[:, None]) < TOL
+    away = margin[0] > 1e-5 * max(1.0, scale)
+    assert int(away.sum()) >= 32
+    assert util.rel_rows(dU[away.cuda()], odU[away]) < TOL
+
+
+def test_auto_retries_with_forward_scaling(built_lib):
+    """Large states clamp on the plain fp16-split kernel; the host call (path AUTO) re-plans with
+    the per-trajectory rescaled variant and stays on the tensor cores."""
+    cfg = util.MID
+    p, x0, U0, goal = util.case(cfg, 33, B=96, K=1)
+    x0 = (x0 * 3e5).astype(np.float32)
+    goal = (goal * 3e5).astype(np.float32)
+    h = util.make_handle(cfg, p)
+    op = util.to_oracle(p)
+    oU, oX, oJ, oidx, _ = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), op, "grad", 2, 1e-3)
+    Ub, Xb, Jb, idx, _ = h.plan_host(torch.from_numpy(x0), torch.from_numpy(U0), torch.from_numpy(goal),
+                                     method="grad", iters=2, lr=1e-3)
+    assert h.last_path == "tc16s"
+    assert util.rel_rows(Xb, oX) < TOL and util.rel_rows(Jb[:, None], oJ[:, None]) < TOL
