@@ -267,10 +267,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         }
       }
       const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), ring_a = smem_u32(ring);
-      const uint32_t G0 = (uint32_t)(LP * w + lane);
+      const uint32_t G0 = (uint32_t)(2 * lane + w);  // consecutive groups alternate between the two producer warps
       uint32_t slot = G0 % (uint32_t)NS, ph = (G0 / (uint32_t)NS) & 1u;
       uint32_t gi = G0;  // group index relative to the start of pass p (may run past its end)
       int ti = 0, p = 0, kind = h_pass_kind(P, 0);
+      const long long t_start = clock64();
       while (true) {
         while (kind != DIR_END && gi >= ngk[kind]) {
           gi -= ngk[kind];
@@ -283,7 +284,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
           continue;
         }
         const uint32_t bar = full_a + slot * 8;
-        mbar_wait_a(empty_a + slot * 8, ph ^ 1);  // all C CTAs released the slot
+        // poll instead of blocking: a lane whose slot is free issues its copy at once, it is not held
+        // back by the slower slots of the other lanes of its warp
+        if (!mbar_try_wait_a(empty_a + slot * 8, ph ^ 1)) {  // all C CTAs released the slot?
+          if (clock64() - t_start > 60000000000LL) __trap();
+          continue;
+        }
         const uint2 ge = gtk[kind][gi];         // {offset, bytes}; bytes is a multiple of 64 * C
         const uint32_t part = ge.y / C;
         const uint32_t dst = ring_a + slot * H_GROUP_BYTES + crank * part;
