@@ -29,6 +29,12 @@ class Config(C.Structure):
         "critic_features", "critic_layers", "critic_hidden", "device")]
 
 
+class IlqrOptions(C.Structure):
+    """gmpc_ilqr_options: the trajax options the reference sets (policy/eval.py:10-20)."""
+    _fields_ = [("maxiter", C.c_int32), ("grad_norm_threshold", C.c_float),
+                ("alpha_0", C.c_float), ("alpha_min", C.c_float)]
+
+
 _f = C.c_void_p  # device/host float*
 _SIGS = {
     "gmpc_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
@@ -51,6 +57,10 @@ _SIGS = {
     "gmpc_plan_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_int32,
                                  C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, _f, _f,
                                  _f, _f, _f, C.c_void_p]),
+    "gmpc_ilqr": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.POINTER(IlqrOptions), _f, _f, _f,
+                            _f, _f, _f, _f, _f, C.c_void_p]),
+    "gmpc_ilqr_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                  C.c_void_p]),
     "gmpc_critic_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_void_p]),
     "gmpc_critic_loss_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_float,
                                         _f, _f, C.c_void_p]),
@@ -245,6 +255,43 @@ class Handle:
             _ptr(idx, dtype=torch.int32, device=cpu), _ptr(J_all, device=cpu),
             _stream(self.device)))
         return out
+
+    def ilqr(self, x0, U0, goal, maxiter=100, grad_norm_threshold=1e-4, alpha_0=1.0,
+             alpha_min=0.00005, want_lqr=False, **unsupported):
+        """trajax iLQR (the reference's ilqr_solve, policy/optimizers.py:10-21), batched:
+        x0 [B,n], U0 [B,T,m], goal [B,T+1,n] ->
+        (X, U, obj, gradient, adjoints, (A, B) or None, iteration).  Keyword names are those of
+        TRAJAX_iLQR_KWARGS (policy/eval.py:10-20); the thresholds the reference leaves at 0.0 and
+        make_psd=False must keep those values."""
+        for k, v in unsupported.items():
+            if k not in ("relative_grad_norm_threshold", "obj_step_threshold",
+                         "inputs_step_threshold", "make_psd", "psd_delta"):
+                raise TypeError(f"ilqr: unknown option {k!r}")
+            if v not in (0.0, False):
+                raise NotImplementedError(f"ilqr: {k}={v!r} (the reference uses 0.0 / False)")
+        dev = self.device
+        B = x0.shape[0]
+        f = dict(device=dev, dtype=torch.float32)
+        X = torch.empty(B, self.T + 1, self.n, **f)
+        U = torch.empty(B, self.T, self.m, **f)
+        obj = torch.empty(B, **f)
+        grad = torch.empty(B, self.T, self.m, **f)
+        lam = torch.empty(B, self.T + 1, self.n, **f)
+        it = torch.empty(B, device=dev, dtype=torch.int32)
+        A = torch.empty(B, self.T, self.n, self.n, **f) if want_lqr else None
+        Bm = torch.empty(B, self.T, self.n, self.m, **f) if want_lqr else None
+        opt = IlqrOptions(int(maxiter), float(grad_norm_threshold), float(alpha_0), float(alpha_min))
+        _check(self.lib.gmpc_ilqr(
+            self._h, B, _ptr(x0, device=dev, name="x0"), _ptr(U0, device=dev, name="U0"),
+            _ptr(goal, device=dev, name="goal"), C.byref(opt), _ptr(X), _ptr(U), _ptr(obj),
+            _ptr(grad), _ptr(lam), _ptr(it, dtype=torch.int32), _ptr(A), _ptr(Bm), _stream(dev)))
+        return X, U, obj, grad, lam, ((A, Bm) if want_lqr else None), it
+
+    def ilqr_stats(self):
+        """(tile-level outer iterations, rollouts) of the ilqr calls since the last query."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        _check(self.lib.gmpc_ilqr_stats(self._h, C.byref(a), C.byref(b), _stream(self.device)))
+        return int(a.value), int(b.value)
 
     # ---------------------------------------------------------------- critic / losses
     def critic_forward(self, xseq, params_flat):

@@ -14,6 +14,7 @@
 #include "critic.cuh"
 #include "diag.cuh"
 #include "plan_ffma.cuh"
+#include "ilqr.cuh"
 #include "plan_tc.cuh"
 #include "plan_h16.cuh"
 
@@ -79,6 +80,10 @@ struct gmpc_handle {
   // tensor-core path state (3xTF32 kernel and the fp16-split kernel)
   TcState tc;
   H16State h16;
+  // iLQR kernel scratch (allocated on first use)
+  float* d_ilqr_ws = nullptr;
+  size_t ilqr_ws_bytes = 0;
+  long long* d_ilqr_stats = nullptr;
 };
 
 extern "C" const char* gmpc_last_error(void) { return g_err.c_str(); }
@@ -254,6 +259,7 @@ extern "C" int gmpc_destroy(gmpc_handle* h) {
   cudaFree(h->ws_X); cudaFree(h->ws_G); cudaFree(h->ws_U); cudaFree(h->ws_M); cudaFree(h->ws_V);
   cudaFree(h->ws_mask); cudaFree(h->d_scratch); cudaFree(h->d_stage);
   cudaFree(h->d_partial); cudaFree(h->d_losses); cudaFree(h->d_fuse);
+  cudaFree(h->d_ilqr_ws); cudaFree(h->d_ilqr_stats);
   delete h;
   return GMPC_OK;
 }
@@ -453,6 +459,90 @@ extern "C" int gmpc_plan(gmpc_handle* h, int64_t B, int32_t K, const float* x0, 
     if (J_all) CU_CHECK(cudaMemcpyAsync(J_all, J_best, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
   }
   CU_CHECK(cudaGetLastError());
+  return GMPC_OK;
+}
+
+// ilqr_solve (policy/optimizers.py:10-21): the whole trajax iLQR loop as one kernel (csrc/ilqr.cuh).
+extern "C" int gmpc_ilqr(gmpc_handle* h, int64_t B, const float* x0, const float* U0,
+                         const float* goal, const gmpc_ilqr_options* opt, float* X, float* U,
+                         float* obj, float* gradient, float* adjoints, int32_t* iteration,
+                         float* lqr_A, float* lqr_B, void* stream) {
+  int rc = check_ready(h, "gmpc_ilqr", B);
+  if (rc) return rc;
+  if (B == 0) return GMPC_OK;
+  if (!x0 || !U0 || !goal || !opt || !X || !U || !obj) return fail(GMPC_E_ARG, "gmpc_ilqr: null argument");
+  if (opt->maxiter < 0) return fail(GMPC_E_ARG, "gmpc_ilqr: maxiter must be >= 0");
+  const gmpc_config& c = h->cfg;
+  if (c.m > IL_MAXM) return fail(GMPC_E_UNSUPPORTED, "gmpc_ilqr: action size above 16");
+  cudaStream_t st = (cudaStream_t)stream;
+  const IlqrSmem SL = ilqr_smem_layout(c.n, c.m, c.cost_fout, h->hpad);
+  cudaDeviceProp prop;
+  CU_CHECK(cudaGetDeviceProperties(&prop, c.device));
+  if (SL.bytes > (size_t)prop.sharedMemPerBlockOptin)
+    return fail(GMPC_E_UNSUPPORTED, "gmpc_ilqr: the Riccati matrices of a 32-trajectory tile do not fit shared memory (state size too large)");
+  const IlqrWs WL = ilqr_ws_layout(c.n, c.m, c.T, c.cost_fout);
+  const size_t need = (size_t)h->num_sms * WL.total * sizeof(float);
+  if (need > h->ilqr_ws_bytes) {
+    CU_CHECK(cudaStreamSynchronize(st));
+    rc = grow((void**)&h->d_ilqr_ws, &h->ilqr_ws_bytes, need);
+    if (rc) return rc;
+  }
+  if (!h->d_ilqr_stats) {
+    CU_CHECK(cudaMalloc(&h->d_ilqr_stats, 2 * sizeof(long long)));
+    CU_CHECK(cudaMemset(h->d_ilqr_stats, 0, 2 * sizeof(long long)));
+    CU_CHECK(cudaFuncSetAttribute(ilqr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)prop.sharedMemPerBlockOptin));
+    CU_CHECK(cudaFuncSetAttribute(ilqr_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)prop.sharedMemPerBlockOptin));
+  }
+  IlqrParams Q;
+  memset(&Q, 0, sizeof(Q));
+  PlanParams& P = Q.pp;
+  make_dirs(h->dyn, P.dir[DIR_DYN_F], P.dir[DIR_DYN_B]);
+  make_dirs(h->cost, P.dir[DIR_COST_F], P.dir[DIR_COST_B]);
+  P.n = c.n; P.m = c.m; P.T = c.T; P.K = 1;
+  P.hpad = h->hpad;
+  P.fout = c.cost_fout;
+  P.use_cost = 1;
+  P.mpcw = h->d_mpcw;
+  P.ws_mask = h->ws_mask;
+  P.NQ = B;
+  P.ntiles = (int)((B + RT - 1) / RT);
+  P.x0 = x0; P.U_in = U0; P.goal = goal;
+  P.X_out = X; P.U_out = U; P.J_out = obj; P.dU_out = gradient; P.lam_out = adjoints;
+  Q.maxiter = opt->maxiter;
+  Q.gthr = opt->grad_norm_threshold;
+  Q.alpha0 = opt->alpha_0;
+  Q.alpha_min = opt->alpha_min;
+  Q.it_out = iteration;
+  Q.A_out = lqr_A;
+  Q.B_out = lqr_B;
+  Q.ws = h->d_ilqr_ws;
+  Q.ws_stride = (long long)WL.total;
+  Q.stats = h->d_ilqr_stats;
+  const int grid = std::min(P.ntiles, h->num_sms);
+  if (h->maxt == 1)
+    ilqr_kernel<1><<<grid, NTHREADS, SL.bytes, st>>>(Q);
+  else
+    ilqr_kernel<2><<<grid, NTHREADS, SL.bytes, st>>>(Q);
+  ++h->launches;
+  CU_CHECK(cudaGetLastError());
+  return GMPC_OK;
+}
+
+extern "C" int gmpc_ilqr_stats(gmpc_handle* h, int64_t* outer_iterations, int64_t* rollouts, void* stream) {
+  if (!h || !outer_iterations || !rollouts) return fail(GMPC_E_ARG, "gmpc_ilqr_stats: null argument");
+  *outer_iterations = 0;
+  *rollouts = 0;
+  if (!h->d_ilqr_stats) return GMPC_OK;
+  CU_CHECK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  long long v[2] = {0, 0};
+  CU_CHECK(cudaMemcpyAsync(v, h->d_ilqr_stats, sizeof(v), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaMemsetAsync(h->d_ilqr_stats, 0, sizeof(v), st));
+  CU_CHECK(cudaStreamSynchronize(st));
+  *outer_iterations = v[0];
+  *rollouts = v[1];
   return GMPC_OK;
 }
 

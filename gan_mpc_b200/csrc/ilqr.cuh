@@ -1,0 +1,632 @@
+// ilqr.cuh -- the reference's own planner step, trajax iLQR (policy/optimizers.py:10-21 with the
+// options of policy/eval.py:10-20), as ONE persistent kernel on the fp32 CUDA cores.
+//
+// A CTA owns a tile of RT = 32 trajectories and runs the whole iLQR loop for it in lock step with
+// vmap semantics (a lane whose own loop condition is false is frozen while the tile continues):
+//
+//   rollout -> [ linearize + adjoint scan -> continuation test -> Riccati sweep (tvlqr)
+//                -> backtracking line search of feedback rollouts ]*
+//
+// * linearize: the dynamics Jacobians A_t = I + dMLP/dx, B_t = dMLP/du are n adjoint passes with
+//   unit seeds through the ReLU masks of one forward pass (what jax.jacobian's n VJPs do); with the
+//   trajectories as the 32 columns of the tile every pass is a full [features x 32] FFMA tile and
+//   reuses the layer machinery of plan_ffma.cuh (weights streamed from L2 through the cp.async ring).
+//   The cost Hessians are closed forms: pseudo-Huber (cost/cost_model.py:20-28) and the Gauss-Newton
+//   term 2 w2 Jf^T Jf of the terminal cost MLP (cost/nn.py:23-29; exact, the MLP is piecewise linear).
+// * Riccati sweep and adjoint scan: thread (lane r = trajectory, w = tid / 32) owns every 8th entry
+//   of each small matrix of trajectory r; all matrices live in shared memory as [entry][32], so
+//   every access is conflict free and no shuffles are needed.  This region aliases the MLP buffers.
+// * G_ = G + max(0, 1e-8 - lambda_min(G)) I (trajax lqr_step): a Cholesky factorisation that succeeds
+//   proves lambda_min > 0 and the shift is 0 (to within 1e-8); only when it fails is lambda_min computed
+//   (cyclic Jacobi) and the shifted matrix factorised.
+//
+// trajax is an un-vendored dependency (requirements.txt:51); the algorithm is restated from the
+// published method, the checker is oracle/ilqr.py.
+#pragma once
+#include "plan_ffma.cuh"
+
+namespace gmpc {
+
+constexpr int IL_MAXM = 16;      // action size limit of the per-lane Cholesky / Jacobi code
+constexpr float IL_DELTA = 1e-8f;
+
+struct IlqrParams {
+  PlanParams pp;        // layer descriptors, sizes, x0 / U_in / goal, X_out / U_out / J_out / dU_out / lam_out
+  int maxiter;
+  float gthr, alpha0, alpha_min;
+  int* it_out;          // [B] iterations run per trajectory
+  float* A_out;         // [B,T,n,n] nullable: dynamics Jacobians at the returned trajectory (lqr[5])
+  float* B_out;         // [B,T,n,m] nullable (lqr[6])
+  float* ws;            // per-CTA slabs, see IlqrWs
+  long long ws_stride;  // floats per CTA
+  long long* stats;     // nullable: [0] outer iterations (tile level), [1] line-search rollouts
+};
+
+// per-CTA global scratch, every array is [..][RT]
+struct IlqrWs {
+  size_t X, Xn, G, lam, U, Un, k, grad, A, B, K, Jf, QT, qT, total;
+};
+__host__ __device__ inline IlqrWs ilqr_ws_layout(int n, int m, int T, int fout) {
+  IlqrWs s;
+  size_t o = 0;
+  const size_t sx = (size_t)(T + 1) * n * RT, su = (size_t)T * m * RT;
+  s.X = o; o += sx;
+  s.Xn = o; o += sx;
+  s.G = o; o += sx;
+  s.lam = o; o += sx;
+  s.U = o; o += su;
+  s.Un = o; o += su;
+  s.k = o; o += su;
+  s.grad = o; o += su;
+  s.A = o; o += (size_t)T * n * n * RT;
+  s.B = o; o += (size_t)T * n * m * RT;
+  s.K = o; o += (size_t)T * m * n * RT;
+  s.Jf = o; o += (size_t)fout * n * RT;
+  s.QT = o; o += (size_t)n * n * RT;
+  s.qT = o; o += (size_t)n * RT;
+  s.total = o;
+  return s;
+}
+
+struct IlqrSmem {
+  int un_floats;     // union of the MLP buffers and the Riccati region
+  int small_floats;  // persistent small arrays
+  size_t bytes;
+};
+__host__ __device__ inline IlqrSmem ilqr_smem_layout(int n, int m, int fout, int hpad) {
+  IlqrSmem s;
+  const int n4 = (n + 3) & ~3, nm4 = (n + m + 3) & ~3, f4 = (fout + 3) & ~3;
+  const int s4 = n4 > f4 ? n4 : f4;
+  const int mlp = 2 * hpad * RT + NSTAGE * STAGE_FLOATS;
+  const int ric = (2 * n * n + 3 * m * n + 2 * m * m + 3 * n + 3 * m + 2) * RT;
+  s.un_floats = mlp > ric ? mlp : ric;
+  s.small_floats = (2 * nm4 + s4 + f4 + 11 + 4) * RT + 32;
+  s.bytes = sizeof(float) * ((size_t)s.un_floats + s.small_floats);
+  return s;
+}
+
+// smallest eigenvalue of the symmetric m x m matrix of lane r (cyclic Jacobi, rare path)
+__device__ __noinline__ float il_min_eig(const float* G_s, int m, int r) {
+  float a[IL_MAXM * IL_MAXM];
+  for (int i = 0; i < m * m; ++i) a[i] = G_s[i * RT + r];
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    float off = 0.f;
+    for (int p = 0; p < m - 1; ++p)
+      for (int q = p + 1; q < m; ++q) {
+        const float apq = a[p * m + q];
+        off += apq * apq;
+        if (fabsf(apq) < 1e-37f) continue;
+        const float theta = (a[q * m + q] - a[p * m + p]) / (2.f * apq);
+        const float t = copysignf(1.f, theta) / (fabsf(theta) + sqrtf(theta * theta + 1.f));
+        const float c = rsqrtf(t * t + 1.f), s = t * c;
+        for (int k = 0; k < m; ++k) {
+          const float akp = a[k * m + p], akq = a[k * m + q];
+          a[k * m + p] = c * akp - s * akq;
+          a[k * m + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < m; ++k) {
+          const float apk = a[p * m + k], aqk = a[q * m + k];
+          a[p * m + k] = c * apk - s * aqk;
+          a[q * m + k] = s * apk + c * aqk;
+        }
+      }
+    if (off < 1e-30f) break;
+  }
+  float mn = a[0];
+  for (int i = 1; i < m; ++i) mn = fminf(mn, a[i * m + i]);
+  return mn;
+}
+
+// Cholesky factor of (G + shift I) of lane r into L_s (lower triangle); false if a pivot is not > 0
+__device__ __forceinline__ bool il_cholesky(const float* G_s, float* L_s, int m, int r, float shift) {
+  bool ok = true;
+  for (int a = 0; a < m; ++a)
+    for (int b = 0; b <= a; ++b) {
+      float s = G_s[(a * m + b) * RT + r] + (a == b ? shift : 0.f);
+      for (int c = 0; c < b; ++c) s = fmaf(-L_s[(a * m + c) * RT + r], L_s[(b * m + c) * RT + r], s);
+      if (a == b) {
+        if (!(s > 0.f)) ok = false;
+        L_s[(a * m + a) * RT + r] = sqrtf(s);
+      } else {
+        L_s[(a * m + b) * RT + r] = s / L_s[(b * m + b) * RT + r];
+      }
+    }
+  return ok;
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant__ IlqrParams Q) {
+  const PlanParams& P = Q.pp;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, r = tid & 31, w = tid >> 5;
+  const int n = P.n, m = P.m, T = P.T, fout = P.fout;
+  const int n4 = (n + 3) & ~3, nm4 = (n + m + 3) & ~3, f4 = (fout + 3) & ~3;
+  const int s4 = n4 > f4 ? n4 : f4;
+  const IlqrSmem SL = ilqr_smem_layout(n, m, fout, P.hpad);
+  // MLP view of the union region
+  float* bufA = smem;
+  float* bufB = bufA + P.hpad * RT;
+  float* ring = bufB + P.hpad * RT;
+  // Riccati view of the same region
+  float* P_s = smem;                  // [n*n]  value-function Hessian
+  float* T_s = P_s + n * n * RT;      // [n*n]  A^T P
+  float* BtP_s = T_s + n * n * RT;    // [m*n]  B^T P, later H + G K
+  float* H_s = BtP_s + m * n * RT;    // [m*n]  B^T P A
+  float* K_s = H_s + m * n * RT;      // [m*n]  feedback gain
+  float* G_s = K_s + m * n * RT;      // [m*m]
+  float* L_s = G_s + m * m * RT;      // [m*m]  Cholesky factor of G_
+  float* p_s = L_s + m * m * RT;      // [n]
+  float* pn_s = p_s + n * RT;         // [n]
+  float* d_s = pn_s + n * RT;         // [n]    x_t - goal_t
+  float* u_s = d_s + n * RT;          // [m]
+  float* h_s = u_s + m * RT;          // [m]
+  float* k_s = h_s + m * RT;          // [m]
+  float* sd_s = k_s + m * RT;         // [1]    sqrt(|d|^2 + a^2)
+  float* su_s = sd_s + RT;            // [1]    sqrt(|u|^2 + a^2)
+  // persistent small arrays
+  float* q_s = smem + SL.un_floats;   // [nm4]  rows 0..n-1 = x, n..n+m-1 = u
+  float* seed_s = q_s + nm4 * RT;     // [s4]   unit seeds of the Jacobian passes
+  float* dq_s = seed_s + s4 * RT;     // [nm4]
+  float* y_s = dq_s + nm4 * RT;       // [f4]
+  float* obj_s = y_s + f4 * RT;
+  float* objn_s = obj_s + RT;
+  float* alpha_s = objn_s + RT;
+  float* gpart_s = alpha_s + RT;      // [8]
+  int* act_s = reinterpret_cast<int*>(gpart_s + 8 * RT);
+  int* srch_s = act_s + RT;
+  int* acc_s = srch_s + RT;
+  int* it_s = acc_s + RT;
+  for (int i = tid; i < SL.small_floats; i += NTHREADS) q_s[i] = 0.f;
+
+  const float w0 = 1.f / (1.f + expf(-P.mpcw[0]));
+  const float w1 = 1.f / (1.f + expf(-P.mpcw[1]));
+  const float w2 = 1.f / (1.f + expf(-P.mpcw[2]));
+  const float a2 = ALPHA * ALPHA;
+
+  const IlqrWs WL = ilqr_ws_layout(n, m, T, fout);
+  float* wsb = Q.ws + (size_t)blockIdx.x * Q.ws_stride;
+  float *wsX = wsb + WL.X, *wsXn = wsb + WL.Xn, *wsG = wsb + WL.G, *wsLam = wsb + WL.lam;
+  float *wsU = wsb + WL.U, *wsUn = wsb + WL.Un, *wsk = wsb + WL.k, *wsGrad = wsb + WL.grad;
+  float *wsA = wsb + WL.A, *wsB = wsb + WL.B, *wsK = wsb + WL.K, *wsJf = wsb + WL.Jf;
+  float *wsQT = wsb + WL.QT, *wsqT = wsb + WL.qT;
+  const int Ld = P.dir[DIR_DYN_F].L, Lc = P.dir[DIR_COST_F].L;
+  const size_t mask_layer = (size_t)MAXT * NTHREADS;
+  uint32_t* dynMask = P.ws_mask + (size_t)blockIdx.x * ((size_t)(Ld - 1) + (Lc - 1)) * mask_layer;
+  uint32_t* costMask = dynMask + (size_t)(Ld - 1) * mask_layer;
+  long long n_outer = 0, n_roll = 0;
+
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+    const long long q0 = (long long)tile * RT;
+    __syncthreads();
+    // ------------------------------------------------------------------ stage the tile
+    for (int e = tid; e < RT * n; e += NTHREADS) {
+      const int rr = e / n, i = e - rr * n;
+      const long long q = q0 + rr;
+      wsX[i * RT + rr] = (q < P.NQ) ? P.x0[q * n + i] : 0.f;
+    }
+    {
+      const int per = (T + 1) * n;
+      for (int e = tid; e < RT * per; e += NTHREADS) {
+        const int rr = e / per, rest = e - rr * per;
+        const long long q = q0 + rr;
+        wsG[rest * RT + rr] = (q < P.NQ) ? P.goal[q * per + rest] : 0.f;
+      }
+    }
+    {
+      const int per = T * m;
+      for (int e = tid; e < RT * per; e += NTHREADS) {
+        const int rr = e / per, rest = e - rr * per;
+        const long long q = q0 + rr;
+        wsU[rest * RT + rr] = (q < P.NQ) ? P.U_in[q * per + rest] : 0.f;
+      }
+    }
+    if (tid < RT) {
+      act_s[r] = (q0 + r < P.NQ) ? 1 : 0;
+      srch_s[r] = 0;
+      acc_s[r] = 0;
+      it_s[r] = 0;
+      alpha_s[r] = Q.alpha0;
+      obj_s[r] = 0.f;
+    }
+    bool init = true;
+    float alpha = Q.alpha0;
+    WeightPipe wp;
+
+#pragma unroll 1
+    while (true) {
+      // ================================================================ rollout (plain or feedback)
+      // trajax rollout (first pass) / ddp_rollout: u = U[t] + alpha k[t] + K[t] (x_new[t] - X[t])
+      float* Xd = init ? wsX : wsXn;
+      float* Ud = init ? wsU : wsUn;
+      wp.p = 0; wp.li = 0; wp.ci = 0; wp.issued = 0; wp.consumed = 0;
+      wp.sched = SCHED_ROLL;
+      wp.kind = DIR_DYN_F;
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < NSTAGE - 1; ++s) pipe_issue(P, wp, ring, tid);
+      for (int i = tid; i < n * RT; i += NTHREADS) {
+        const float v = wsX[i];
+        q_s[i] = v;
+        if (!init) Xd[i] = v;
+      }
+      float Jr = 0.f;
+      ++n_roll;
+      __syncthreads();
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        for (int e = tid; e < m * RT; e += NTHREADS) {
+          const int a = e >> 5;
+          float u = wsU[(t * m + a) * RT + r];
+          if (!init) {
+            float s = alpha * wsk[(t * m + a) * RT + r];
+            const float* Kr = wsK + (size_t)((t * m + a) * n) * RT + r;
+            const float* Xr = wsX + (size_t)(t * n) * RT + r;
+            for (int j = 0; j < n; ++j) s = fmaf(Kr[j * RT], q_s[j * RT + r] - Xr[j * RT], s);
+            u += s;
+            Ud[(t * m + a) * RT + r] = u;
+          }
+          q_s[(n + a) * RT + r] = u;
+        }
+        __syncthreads();
+        if (tid < RT) {  // cost/cost_model.py:20-28 staging cost at (x_t, u_t, goal_t)
+          float uu = 0.f, dd = 0.f;
+          for (int j = 0; j < m; ++j) {
+            const float u = q_s[(n + j) * RT + r];
+            uu = fmaf(u, u, uu);
+          }
+          for (int i = 0; i < n; ++i) {
+            const float d = q_s[i * RT + r] - wsG[(t * n + i) * RT + r];
+            dd = fmaf(d, d, dd);
+          }
+          Jr += w0 * (sqrtf(uu + a2) - ALPHA) + w1 * (sqrtf(dd + a2) - ALPHA);
+        }
+        mlp_forward<MAXT>(P, P.dir[DIR_DYN_F], q_s, q_s, EPI_RESID, Xd + (size_t)(t + 1) * n * RT, dynMask,
+                          bufA, bufB, ring, wp, tid);
+        __syncthreads();
+      }
+      mlp_forward<MAXT>(P, P.dir[DIR_COST_F], q_s, y_s, 0, nullptr, costMask, bufA, bufB, ring, wp, tid);
+      cp_async_wait<0>();
+      __syncthreads();
+      if (tid < RT) {
+        float yy = 0.f;
+        for (int o = 0; o < fout; ++o) {
+          const float y = y_s[o * RT + r];
+          yy = fmaf(y, y, yy);
+        }
+        Jr += w2 * yy;  // cost/cost_model.py:30-31
+        // ---------------------------------------------------------------- line_search_ddp decision
+        if (init) {
+          obj_s[r] = Jr;
+        } else if (srch_s[r]) {
+          const float o = obj_s[r];
+          const float oc = (o != o) ? INFINITY : o;  // NaN objective -> inf
+          const float on = (Jr != Jr) ? oc : Jr;     // NaN trial -> rejected
+          const bool better = on < oc;               // strict decrease only
+          acc_s[r] = better ? 1 : 0;
+          if (better) obj_s[r] = on;
+          const float ar = 0.5f * alpha;
+          alpha_s[r] = ar;
+          srch_s[r] = (!better && ar > Q.alpha_min) ? 1 : 0;
+        } else {
+          acc_s[r] = 0;
+        }
+      }
+      __syncthreads();
+      if (!init) {
+        for (int e = tid; e < (T + 1) * n * RT; e += NTHREADS)
+          if (acc_s[r]) wsX[e] = wsXn[e];
+        for (int e = tid; e < T * m * RT; e += NTHREADS)
+          if (acc_s[r]) wsU[e] = wsUn[e];
+        const int more = __syncthreads_or(tid < RT && srch_s[r]);
+        if (more) {
+          alpha *= 0.5f;
+          continue;
+        }
+      }
+
+      // ================================================================ linearize (get_lqr_params)
+      wp.p = 0; wp.li = 0; wp.ci = 0; wp.issued = 0; wp.consumed = 0;
+      wp.sched = SCHED_LIN;
+      wp.kind = DIR_DYN_F;
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < NSTAGE - 1; ++s) pipe_issue(P, wp, ring, tid);
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        for (int e = tid; e < (n + m) * RT; e += NTHREADS) {
+          const int row = e >> 5;
+          q_s[e] = row < n ? wsX[(t * n + row) * RT + r] : wsU[(t * m + row - n) * RT + r];
+        }
+        __syncthreads();
+        mlp_forward<MAXT>(P, P.dir[DIR_DYN_F], q_s, dq_s, 0, nullptr, dynMask, bufA, bufB, ring, wp, tid);
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+          __syncthreads();
+          for (int e = tid; e < s4 * RT; e += NTHREADS) seed_s[e] = ((e >> 5) == i) ? 1.f : 0.f;
+          mlp_backward<MAXT>(P, P.dir[DIR_DYN_B], seed_s, dq_s, dynMask, bufA, bufB, ring, wp, tid);
+          __syncthreads();
+          for (int e = tid; e < (n + m) * RT; e += NTHREADS) {
+            const int j = e >> 5;
+            const float v = dq_s[e];
+            if (j < n) wsA[(size_t)((t * n + i) * n + j) * RT + r] = v + (i == j ? 1.f : 0.f);
+            else wsB[(size_t)((t * n + i) * m + (j - n)) * RT + r] = v;
+          }
+        }
+        __syncthreads();
+      }
+      for (int e = tid; e < n * RT; e += NTHREADS) q_s[e] = wsX[(size_t)T * n * RT + e];
+      __syncthreads();
+      mlp_forward<MAXT>(P, P.dir[DIR_COST_F], q_s, y_s, 0, nullptr, costMask, bufA, bufB, ring, wp, tid);
+#pragma unroll 1
+      for (int o = 0; o < fout; ++o) {
+        __syncthreads();
+        for (int e = tid; e < s4 * RT; e += NTHREADS) seed_s[e] = ((e >> 5) == o) ? 1.f : 0.f;
+        mlp_backward<MAXT>(P, P.dir[DIR_COST_B], seed_s, dq_s, costMask, bufA, bufB, ring, wp, tid);
+        __syncthreads();
+        for (int e = tid; e < n * RT; e += NTHREADS) wsJf[(size_t)o * n * RT + e] = dq_s[e];
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+      // terminal quadratisation: Q_T = 2 w2 Jf^T Jf, q_T = 2 w2 Jf^T y
+      for (int e = tid; e < n * n * RT; e += NTHREADS) {
+        const int ij = e >> 5, i = ij / n, j = ij - i * n;
+        float s = 0.f;
+        for (int o = 0; o < fout; ++o) s = fmaf(wsJf[(o * n + i) * RT + r], wsJf[(o * n + j) * RT + r], s);
+        wsQT[e] = 2.f * w2 * s;
+      }
+      for (int e = tid; e < n * RT; e += NTHREADS) {
+        const int i = e >> 5;
+        float s = 0.f;
+        for (int o = 0; o < fout; ++o) s = fmaf(wsJf[(o * n + i) * RT + r], y_s[o * RT + r], s);
+        s *= 2.f * w2;
+        wsqT[e] = s;
+        p_s[e] = s;
+        wsLam[(size_t)T * n * RT + e] = s;
+      }
+      // ================================================================ adjoint scan (gradient, adjoints)
+      float g2 = 0.f;
+      __syncthreads();
+#pragma unroll 1
+      for (int t = T - 1; t >= 0; --t) {
+        if (tid < RT) {
+          float uu = 0.f, dd = 0.f;
+          for (int j = 0; j < m; ++j) {
+            const float u = wsU[(t * m + j) * RT + r];
+            uu = fmaf(u, u, uu);
+          }
+          for (int i = 0; i < n; ++i) {
+            const float d = wsX[(t * n + i) * RT + r] - wsG[(t * n + i) * RT + r];
+            dd = fmaf(d, d, dd);
+          }
+          sd_s[r] = sqrtf(dd + a2);
+          su_s[r] = sqrtf(uu + a2);
+        }
+        __syncthreads();
+        for (int e = tid; e < (n + m) * RT; e += NTHREADS) {
+          const int row = e >> 5;
+          if (row < n) {
+            const int i = row;
+            float s = w1 * (wsX[(t * n + i) * RT + r] - wsG[(t * n + i) * RT + r]) / sd_s[r];
+            const float* Ar = wsA + (size_t)(t * n * n + i) * RT + r;
+            for (int k = 0; k < n; ++k) s = fmaf(Ar[(size_t)k * n * RT], p_s[k * RT + r], s);
+            pn_s[i * RT + r] = s;
+            wsLam[(size_t)(t * n + i) * RT + r] = s;
+          } else {
+            const int a = row - n;
+            float s = w0 * wsU[(t * m + a) * RT + r] / su_s[r];
+            const float* Br = wsB + (size_t)(t * n * m + a) * RT + r;
+            for (int k = 0; k < n; ++k) s = fmaf(Br[(size_t)k * m * RT], p_s[k * RT + r], s);
+            wsGrad[(t * m + a) * RT + r] = s;
+            g2 = fmaf(s, s, g2);
+          }
+        }
+        __syncthreads();
+        for (int e = tid; e < n * RT; e += NTHREADS) p_s[e] = pn_s[e];
+        __syncthreads();
+      }
+      gpart_s[w * RT + r] = g2;
+      __syncthreads();
+      if (tid < RT) {  // trajax ilqr continuation_criterion, per lane
+        float gn2 = 0.f;
+        for (int k = 0; k < NTHREADS / 32; ++k) gn2 += gpart_s[k * RT + r];
+        const float gn = sqrtf(gn2);
+        if (!init && act_s[r]) it_s[r] += 1;
+        act_s[r] = (act_s[r] && it_s[r] < Q.maxiter && gn > Q.gthr && alpha_s[r] > Q.alpha_min) ? 1 : 0;
+      }
+      const int any = __syncthreads_or(tid < RT && act_s[r]);
+      if (!any) break;
+      ++n_outer;
+
+      // ================================================================ tvlqr backward sweep
+      for (int e = tid; e < n * n * RT; e += NTHREADS) P_s[e] = wsQT[e];
+      for (int e = tid; e < n * RT; e += NTHREADS) p_s[e] = wsqT[e];
+      __syncthreads();
+#pragma unroll 1
+      for (int t = T - 1; t >= 0; --t) {
+        const float* Ag = wsA + (size_t)t * n * n * RT + r;  // A[k][j] at Ag[(k*n+j)*RT]
+        const float* Bg = wsB + (size_t)t * n * m * RT + r;  // B[k][a] at Bg[(k*m+a)*RT]
+        // 0: per-lane norms, d, u
+        for (int e = tid; e < (n + m) * RT; e += NTHREADS) {
+          const int row = e >> 5;
+          if (row < n) d_s[e] = wsX[(t * n + row) * RT + r] - wsG[(t * n + row) * RT + r];
+          else u_s[(row - n) * RT + r] = wsU[(t * m + row - n) * RT + r];
+        }
+        __syncthreads();
+        if (tid < RT) {
+          float uu = 0.f, dd = 0.f;
+          for (int j = 0; j < m; ++j) uu = fmaf(u_s[j * RT + r], u_s[j * RT + r], uu);
+          for (int i = 0; i < n; ++i) dd = fmaf(d_s[i * RT + r], d_s[i * RT + r], dd);
+          sd_s[r] = sqrtf(dd + a2);
+          su_s[r] = sqrtf(uu + a2);
+        }
+        // 1: AtP = A^T P, BtP = B^T P
+        for (int e = tid; e < (n * n + m * n) * RT; e += NTHREADS) {
+          const int ee = e >> 5;
+          float s = 0.f;
+          if (ee < n * n) {
+            const int i = ee / n, j = ee - i * n;
+            for (int k = 0; k < n; ++k) s = fmaf(Ag[(size_t)(k * n + i) * RT], P_s[(k * n + j) * RT + r], s);
+            T_s[ee * RT + r] = s;
+          } else {
+            const int e2 = ee - n * n, a = e2 / n, j = e2 - a * n;
+            for (int k = 0; k < n; ++k) s = fmaf(Bg[(size_t)(k * m + a) * RT], P_s[(k * n + j) * RT + r], s);
+            BtP_s[e2 * RT + r] = s;
+          }
+        }
+        __syncthreads();
+        // 2: AtPA -> P_s, H = BtPA, G = R + BtP B, h = r + B^T p
+        for (int e = tid; e < (n * n + m * n + m * m + m) * RT; e += NTHREADS) {
+          const int ee = e >> 5;
+          float s = 0.f;
+          if (ee < n * n) {
+            const int i = ee / n, j = ee - i * n;
+            for (int k = 0; k < n; ++k) s = fmaf(T_s[(i * n + k) * RT + r], Ag[(size_t)(k * n + j) * RT], s);
+            P_s[ee * RT + r] = s;
+          } else if (ee < n * n + m * n) {
+            const int e2 = ee - n * n, a = e2 / n, j = e2 - a * n;
+            for (int k = 0; k < n; ++k) s = fmaf(BtP_s[(a * n + k) * RT + r], Ag[(size_t)(k * n + j) * RT], s);
+            H_s[e2 * RT + r] = s;
+          } else if (ee < n * n + m * n + m * m) {
+            const int e2 = ee - n * n - m * n, a = e2 / m, b = e2 - a * m;
+            const float su = su_s[r];
+            s = w0 * ((a == b ? 1.f : 0.f) / su - u_s[a * RT + r] * u_s[b * RT + r] / (su * su * su));
+            for (int k = 0; k < n; ++k) s = fmaf(BtP_s[(a * n + k) * RT + r], Bg[(size_t)(k * m + b) * RT], s);
+            G_s[e2 * RT + r] = s;
+          } else {
+            const int a = ee - n * n - m * n - m * m;
+            s = w0 * u_s[a * RT + r] / su_s[r];
+            for (int k = 0; k < n; ++k) s = fmaf(Bg[(size_t)(k * m + a) * RT], p_s[k * RT + r], s);
+            h_s[a * RT + r] = s;
+          }
+        }
+        __syncthreads();
+        // 3: symmetrise AtPA and G
+        for (int e = tid; e < (n * n + m * m) * RT; e += NTHREADS) {
+          const int ee = e >> 5;
+          if (ee < n * n) {
+            const int i = ee / n, j = ee - i * n;
+            if (i < j) {
+              const float v = 0.5f * (P_s[(i * n + j) * RT + r] + P_s[(j * n + i) * RT + r]);
+              P_s[(i * n + j) * RT + r] = v;
+              P_s[(j * n + i) * RT + r] = v;
+            }
+          } else {
+            const int e2 = ee - n * n, a = e2 / m, b = e2 - a * m;
+            if (a < b) {
+              const float v = 0.5f * (G_s[(a * m + b) * RT + r] + G_s[(b * m + a) * RT + r]);
+              G_s[(a * m + b) * RT + r] = v;
+              G_s[(b * m + a) * RT + r] = v;
+            }
+          }
+        }
+        __syncthreads();
+        // 4: G_ = G + max(0, delta - lambda_min) I, Cholesky factor
+        if (tid < RT) {
+          if (!il_cholesky(G_s, L_s, m, r, 0.f)) {
+            const float s0 = il_min_eig(G_s, m, r);
+            il_cholesky(G_s, L_s, m, r, fmaxf(0.f, IL_DELTA - s0));
+          }
+        }
+        __syncthreads();
+        // 5: K = -G_^-1 H (n columns), k = -G_^-1 h
+        for (int e = tid; e < (n + 1) * RT; e += NTHREADS) {
+          const int c = e >> 5;
+          float* x = c < n ? K_s + c * RT + r : k_s + r;           // x[a] at x[a * xs]
+          const int xs = c < n ? n * RT : RT;
+          const float* b = c < n ? H_s + c * RT + r : h_s + r;
+          for (int a = 0; a < m; ++a) {
+            float s = b[a * xs];
+            for (int bb = 0; bb < a; ++bb) s = fmaf(-L_s[(a * m + bb) * RT + r], x[bb * xs], s);
+            x[a * xs] = s / L_s[(a * m + a) * RT + r];
+          }
+          for (int a = m - 1; a >= 0; --a) {
+            float s = x[a * xs];
+            for (int bb = a + 1; bb < m; ++bb) s = fmaf(-L_s[(bb * m + a) * RT + r], x[bb * xs], s);
+            x[a * xs] = s / L_s[(a * m + a) * RT + r];
+          }
+          for (int a = 0; a < m; ++a) x[a * xs] = -x[a * xs];
+        }
+        __syncthreads();
+        // 6: H_GK = H + G K  (unshifted G, as trajax)  -> BtP_s
+        for (int e = tid; e < m * n * RT; e += NTHREADS) {
+          const int ee = e >> 5, a = ee / n, j = ee - a * n;
+          float s = H_s[ee * RT + r];
+          for (int b = 0; b < m; ++b) s = fmaf(G_s[(a * m + b) * RT + r], K_s[(b * n + j) * RT + r], s);
+          BtP_s[ee * RT + r] = s;
+        }
+        __syncthreads();
+        // 7: P = Q + AtPA + H_GK^T K + K^T H ; p = q + A^T p + H_GK^T k + K^T h ; gains out
+        for (int e = tid; e < (n * n + n) * RT; e += NTHREADS) {
+          const int ee = e >> 5;
+          const float sd = sd_s[r];
+          if (ee < n * n) {
+            const int i = ee / n, j = ee - i * n;
+            float s = P_s[ee * RT + r] +
+                      w1 * ((i == j ? 1.f : 0.f) / sd - d_s[i * RT + r] * d_s[j * RT + r] / (sd * sd * sd));
+            for (int a = 0; a < m; ++a) {
+              s = fmaf(BtP_s[(a * n + i) * RT + r], K_s[(a * n + j) * RT + r], s);
+              s = fmaf(K_s[(a * n + i) * RT + r], H_s[(a * n + j) * RT + r], s);
+            }
+            T_s[ee * RT + r] = s;
+          } else {
+            const int i = ee - n * n;
+            float s = w1 * d_s[i * RT + r] / sd;
+            for (int k = 0; k < n; ++k) s = fmaf(Ag[(size_t)(k * n + i) * RT], p_s[k * RT + r], s);
+            for (int a = 0; a < m; ++a) {
+              s = fmaf(BtP_s[(a * n + i) * RT + r], k_s[a * RT + r], s);
+              s = fmaf(K_s[(a * n + i) * RT + r], h_s[a * RT + r], s);
+            }
+            pn_s[i * RT + r] = s;
+          }
+        }
+        for (int e = tid; e < m * n * RT; e += NTHREADS) wsK[(size_t)t * m * n * RT + e] = K_s[e];
+        for (int e = tid; e < m * RT; e += NTHREADS) wsk[(size_t)t * m * RT + e] = k_s[e];
+        __syncthreads();
+        // 8: P <- sym(.), p <- pn
+        for (int e = tid; e < n * n * RT; e += NTHREADS) {
+          const int ee = e >> 5, i = ee / n, j = ee - i * n;
+          P_s[ee * RT + r] = 0.5f * (T_s[(i * n + j) * RT + r] + T_s[(j * n + i) * RT + r]);
+        }
+        for (int e = tid; e < n * RT; e += NTHREADS) p_s[e] = pn_s[e];
+        __syncthreads();
+      }
+      // line search setup: every lane still iterating searches from alpha_0
+      if (tid < RT) srch_s[r] = (act_s[r] && Q.alpha0 > Q.alpha_min) ? 1 : 0;
+      alpha = Q.alpha0;
+      init = false;
+      __syncthreads();
+      if (!__syncthreads_or(tid < RT && srch_s[r])) {
+        // alpha_0 <= alpha_min: no trial can run, every lane stops at the next test
+        if (tid < RT && act_s[r]) { it_s[r] += 1; act_s[r] = 0; }
+        break;
+      }
+    }
+
+    __syncthreads();
+    // ------------------------------------------------------------------ write the tile out
+    if (tid < RT && q0 + r < P.NQ) {
+      if (P.J_out != nullptr) P.J_out[q0 + r] = obj_s[r];
+      if (Q.it_out != nullptr) Q.it_out[q0 + r] = it_s[r];
+    }
+    const struct { float* dst; const float* src; int per; } outs[6] = {
+        {P.U_out, wsU, T * m},          {P.X_out, wsX, (T + 1) * n}, {P.dU_out, wsGrad, T * m},
+        {P.lam_out, wsLam, (T + 1) * n}, {Q.A_out, wsA, T * n * n},   {Q.B_out, wsB, T * n * m}};
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) {
+      if (outs[k].dst == nullptr) continue;
+      const int per = outs[k].per;
+      for (int e = tid; e < RT * per; e += NTHREADS) {
+        const int rr = e / per, rest = e - rr * per;
+        const long long q = q0 + rr;
+        if (q < P.NQ) outs[k].dst[q * per + rest] = outs[k].src[(size_t)rest * RT + rr];
+      }
+    }
+  }
+  if (Q.stats != nullptr && tid == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(Q.stats), (unsigned long long)n_outer);
+    atomicAdd(reinterpret_cast<unsigned long long*>(Q.stats + 1), (unsigned long long)n_roll);
+  }
+}
+
+}  // namespace gmpc

@@ -24,7 +24,13 @@ struct WeightPipe {
   int p, li, ci;  // prefetch cursor: pass, layer in pass, chunk in layer
   int kind;       // DIR_* of pass p
   int issued, consumed;
+  int sched;      // SCHED_*: which pass schedule the prefetch cursor follows
 };
+
+// Pass schedules: the planner's (pass_kind), and the two phases of the iLQR kernel (ilqr.cuh):
+// SCHED_LIN  = per step one forward pass + n adjoint passes (the Jacobian rows), then the cost MLP
+//              forward + fout adjoint passes;  SCHED_ROLL = T forward passes + the cost MLP.
+enum { SCHED_PLAN = 0, SCHED_LIN = 1, SCHED_ROLL = 2 };
 
 __device__ __forceinline__ int pass_kind(const PlanParams& P, int p) {
   const int period = 2 * P.T + (P.use_cost ? 2 : 0);
@@ -45,6 +51,17 @@ __device__ __forceinline__ int pass_kind(const PlanParams& P, int p) {
   return DIR_END;
 }
 
+__device__ __forceinline__ int sched_kind(const PlanParams& P, int sched, int p) {
+  if (sched == SCHED_PLAN) return pass_kind(P, p);
+  if (sched == SCHED_LIN) {
+    const int per = P.n + 1, nd = P.T * per;
+    if (p < nd) return (p % per == 0) ? DIR_DYN_F : DIR_DYN_B;
+    if (p == nd) return DIR_COST_F;
+    return (p - nd <= P.fout) ? DIR_COST_B : DIR_END;
+  }
+  return p < P.T ? DIR_DYN_F : (p == P.T ? DIR_COST_F : DIR_END);
+}
+
 // Issue the cp.async copies of the next weight chunk in schedule order (all threads, uniform).
 __device__ __forceinline__ void pipe_issue(const PlanParams& P, WeightPipe& w, float* ring,
                                            int tid) {
@@ -62,7 +79,7 @@ __device__ __forceinline__ void pipe_issue(const PlanParams& P, WeightPipe& w, f
       if (++w.li == D.L) {
         w.li = 0;
         ++w.p;
-        w.kind = pass_kind(P, w.p);
+        w.kind = sched_kind(P, w.sched, w.p);
       }
     }
   }
@@ -344,6 +361,7 @@ plan_ffma_kernel(const __grid_constant__ PlanParams P) {
     }
     WeightPipe wp;
     wp.p = 0; wp.li = 0; wp.ci = 0; wp.issued = 0; wp.consumed = 0;
+    wp.sched = SCHED_PLAN;
     wp.kind = pass_kind(P, 0);
     __syncthreads();
 #pragma unroll

@@ -6,7 +6,8 @@ from gan_mpc_b200 import _lib
 from gan_mpc_b200.dynamics.nn import dense_stack_lists
 from gan_mpc_b200.policy import optimizers as opt
 
-# kept for signature compatibility (policy/eval.py:10-20); the first-order planner ignores them
+# policy/eval.py:10-20 -- honoured by planner method "ilqr" (gmpc_ilqr); the first-order planner
+# (methods "adam" / "grad", the north-star default) ignores them
 TRAJAX_iLQR_KWARGS = {
     "maxiter": 100, "grad_norm_threshold": 1e-4, "relative_grad_norm_threshold": 0.0,
     "obj_step_threshold": 0.0, "inputs_step_threshold": 0.0, "make_psd": False, "psd_delta": 0.0,
@@ -95,6 +96,17 @@ class EvalMPC:
         h = self._handle(x0b.shape[1], Ub.shape[3])
         self._stage(h, params)
         pk = self.planner_kwargs
+        if pk["method"] == "ilqr":
+            # the reference's own step: trajax iLQR with TRAJAX_iLQR_KWARGS (policy/optimizers.py:19-21)
+            if Ub.shape[1] != 1:
+                raise ValueError("method 'ilqr' plans one action sequence per state (no candidates)")
+            out = h.ilqr(x0b, Ub[:, 0].contiguous(), gb, want_lqr=pk.get("return_lqr", False),
+                         **self.trajax_ilqr_kwargs)
+            self.last_plan_info = {"idx": None, "J_all": None, "path": "ilqr"}
+            if not batched:
+                out = tuple(None if o is None else (tuple(a[0] for a in o) if isinstance(o, tuple) else o[0])
+                            for o in out)
+            return out
         Ubest, X, J, idx, J_all = h.plan(x0b, Ub, gb, method=pk["method"], iters=pk["iters"],
                                          lr=pk["learning_rate"], b1=pk["b1"], b2=pk["b2"],
                                          eps=pk["eps"])

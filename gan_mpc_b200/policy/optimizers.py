@@ -7,8 +7,9 @@ MujocoBasedModel(cost MLP) -- extracts the weights and runs libgmpc.  Anything e
 (there is no CPU fallback).  Every function accepts the reference's unbatched shapes and the
 same shapes with leading batch axes (the reference vmaps; the kernels batch natively).
 
-The planner itself is the north-star first-order planner on the reference's exact objective;
-the reference's own step is trajax iLQR (ranked "next")."""
+Two planners sit behind ilqr_solve: the north-star first-order planner on the reference's exact
+objective (planner method "adam" / "grad", the default) and the reference's own step, trajax iLQR
+(planner method "ilqr": gmpc_ilqr), which honours trajax_ilqr_kwargs."""
 
 import torch
 
@@ -39,13 +40,21 @@ def bind(fn, params, args=()):
 
 def ilqr_solve(cost, dynamics, x0, U, params, cost_args, dynamics_args, trajax_ilqr_kwargs=None):
     """policy/optimizers.py:10-21.  Returns the trajax 7-tuple
-    (X, U, obj, gradient, adjoints, lqr, iteration); `lqr` is None (no LQR sub-problem exists in
-    the first-order planner) and `iteration` is the number of planning iterations run."""
+    (X, U, obj, gradient, adjoints, lqr, iteration).  With the policy's planner method "ilqr" this
+    is trajax iLQR under `trajax_ilqr_kwargs` (lqr = (A, B) Jacobians when planner_kwargs has
+    return_lqr, else None); with the first-order planner `lqr` is None and `iteration` is the number
+    of planning iterations run."""
     pol = _owner(cost, "cost")
     if _owner(dynamics, "dynamics") is not pol:
         raise ValueError("cost and dynamics must belong to the same policy")
     if len(dynamics_args) != 0:
         raise ValueError("MLP dynamics take no extra arguments (policy/eval.py:121)")
+    if trajax_ilqr_kwargs is not None and pol.planner_kwargs["method"] == "ilqr":
+        saved, pol.trajax_ilqr_kwargs = pol.trajax_ilqr_kwargs, trajax_ilqr_kwargs
+        try:
+            return pol._plan(x0, U, params, cost_args[0])
+        finally:
+            pol.trajax_ilqr_kwargs = saved
     return pol._plan(x0, U, params, cost_args[0])
 
 

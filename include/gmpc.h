@@ -127,6 +127,35 @@ int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float* x0_host,
                    float* X_best_host, float* J_best_host, int32_t* idx_best_host,
                    float* J_all_host, void* stream);
 
+/* trajax iLQR options as the reference passes them (policy/eval.py:10-20, TRAJAX_iLQR_KWARGS).
+ * The thresholds the reference leaves at 0.0 and make_psd = False are not configurable. */
+typedef struct gmpc_ilqr_options {
+  int32_t maxiter;             /* 100 */
+  float grad_norm_threshold;   /* 1e-4 */
+  float alpha_0;               /* 1.0 */
+  float alpha_min;             /* 0.00005 */
+} gmpc_ilqr_options;
+
+/* The reference's OWN planner step: ilqr_solve (policy/optimizers.py:10-21) = trajax.optimizers.ilqr
+ * on cost = EvalMPC.cost (policy/eval.py:64-69) and dynamics = EvalMPC.dynamics (:71-73), batched
+ * with vmap semantics (every trajectory gets what its unbatched call would return).  One fused
+ * kernel per call: rollout, linearisation (dynamics Jacobians by n adjoint passes through the ReLU
+ * masks, closed-form cost Hessians), Riccati sweep with the 1e-8 eigenvalue floor, backtracking
+ * line search of feedback rollouts, trajax's continuation test.  fp32 CUDA cores.
+ * x0[B,n], U0[B,T,m], goal[B,T+1,n] ->
+ * X[B,T+1,n], U[B,T,m], obj[B], gradient[B,T,m] (nullable), adjoints[B,T+1,n] (nullable),
+ * iteration[B] (int32, nullable), lqr_A[B,T,n,n] and lqr_B[B,T,n,m] (nullable: the dynamics
+ * Jacobians at the returned trajectory, elements 5 and 6 of trajax's `lqr` tuple) -- the 7-tuple
+ * unpacked at policy/optimizers.py:55.  Limits: m <= 16 and n small enough for the Riccati
+ * matrices of 32 trajectories to fit one SM's shared memory (n <= 24 at m = 6). */
+int gmpc_ilqr(gmpc_handle* h, int64_t B, const float* x0, const float* U0, const float* goal,
+              const gmpc_ilqr_options* opt, float* X, float* U, float* obj, float* gradient,
+              float* adjoints, int32_t* iteration, float* lqr_A, float* lqr_B, void* stream);
+
+/* Work counters of the gmpc_ilqr calls since the last query (synchronises `stream`): tile-level
+ * outer iterations and rollouts (1 + line-search trials) summed over the 32-trajectory tiles. */
+int gmpc_ilqr_stats(gmpc_handle* h, int64_t* outer_iterations, int64_t* rollouts, void* stream);
+
 /* The fp16-split tensor-core kernel (GMPC_PATH_TC16) represents operands as fp16 hi + lo parts; an
  * operand magnitude above 65000 (states, actions or hidden activations; adjoints are rescaled per
  * trajectory and cannot overflow) is clamped and counted.  This call synchronises `stream`, returns

@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from gan_mpc_b200 import synthetic  # noqa: E402
 from oracle import critic as ocritic  # noqa: E402
+from oracle import ilqr as oilqr  # noqa: E402
 from oracle import planner as oracle  # noqa: E402
 from tests import util  # noqa: E402
 
@@ -54,8 +55,26 @@ def critic_case():
                         xseq=xs, label=lab, logit=logit.numpy(), loss=loss.numpy(), grad=g.numpy())
 
 
+def ilqr_case(only_missing=False):
+    """trajax iLQR restatement (oracle/ilqr.py) on the C1 dims: 6 trajectories, 8 iterations."""
+    path = os.path.join(HERE, "ilqr_small.npz")
+    if only_missing and os.path.exists(path):
+        return
+    seed, B, maxiter = 31, 6, 8
+    p, x0, U0, goal = util.case(util.SMALL, seed, B=B)
+    X, U, obj, g, lam, _, it = oilqr.ilqr(util.tt(x0), util.tt(U0[:, 0]), util.tt(goal),
+                                          util.to_oracle(p), maxiter=maxiter)
+    np.savez_compressed(path, seed=seed, B=B, maxiter=maxiter, X=X.numpy(), U=U.numpy(),
+                        obj=obj.numpy(), gradient=g.numpy(), adjoints=lam.numpy(),
+                        iteration=it.numpy())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    if "--ilqr-only" in sys.argv:
+        ilqr_case()
+        sys.exit(0)
+    ilqr_case()
     planner_case("small", util.SMALL, seed=11, B=5, K=3, iters=6, lr=1e-2)
     planner_case("mid", util.MID, seed=12, B=4, K=2, iters=4, lr=1e-2)
     critic_case()

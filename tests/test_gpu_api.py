@@ -170,3 +170,31 @@ def test_js_policy_losses_and_critic_training(built_lib):
                                batch_size=32, key=0, id=1)
     assert len(out) == 5 and len(out[2]) == 2 and len(out[3]) == 2 and out[4] >= 0.0
     assert out[2][1] < out[2][0]                                            # the critic learns
+
+
+def test_policy_with_trajax_ilqr_method(built_lib):
+    """planner method "ilqr" = the reference's own step (trajax iLQR under TRAJAX_iLQR_KWARGS,
+    policy/eval.py:10-20): same entry points, 7-tuple with per-state iteration counts."""
+    from oracle import ilqr as oilqr
+    config = cfg("l2_hyperparameters.yaml")
+    x_size, u_size, B = 3, 1, 40
+    policy, eval_policy, _ = norm_runner.get_policy(config, x_size, u_size)
+    params = norm_runner.get_params(policy, config, x_size, u_size)
+    policy.planner_kwargs["method"] = "ilqr"
+    hx = torch.randn(B, 2, x_size, generator=torch.Generator().manual_seed(4)).cuda()
+    goal, init_u = policy.get_goal_states_init_actions(hx, params)
+    kw = dict(policy.trajax_ilqr_kwargs, maxiter=2)
+    X, U, obj, grad, lam, lqr, it = opt.ilqr_solve(policy.cost, policy.dynamics, hx[:, -1], init_u, params,
+                                                   (goal,), (), kw)
+    assert lqr is None and it.dtype == torch.int32 and int(it.max()) <= 2
+    o = oilqr.ilqr(hx[:, -1].cpu().double(), init_u.cpu().double(), goal.cpu().double(), oracle_params(params),
+                   **kw)
+    util.assert_rows_close("ilqr U", U, o[1], TOL, outlier_frac=0.1, cap=2.0)
+    util.assert_rows_close("ilqr obj", obj[:, None], o[2][:, None], TOL, outlier_frac=0.1, cap=1.0)
+    assert int((it.cpu() == o[6]).sum()) >= B - 2
+    # unbatched call through the policy (full 100-iteration default options): shapes of the reference
+    Xs, Us, objs, gs, lams, _, its = policy.get_optimal_values(params, hx[0])
+    T = config.mpc.horizon
+    assert Xs.shape == (T + 1, x_size) and Us.shape == (T, u_size) and objs.shape == () and its.shape == ()
+    J0 = opt.objective(opt.bind(policy.cost, params, (goal[0],)), opt.bind(policy.dynamics, params), init_u[0], hx[0, -1])
+    assert float(objs) <= float(J0) * (1 + 1e-6)

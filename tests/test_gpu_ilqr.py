@@ -1,0 +1,131 @@
+"""GPU parity of gmpc_ilqr (the reference's own planner step, trajax iLQR: policy/optimizers.py:10-21)
+against oracle/ilqr.py on identical seeded inputs, through the C ABI.
+
+iLQR is a discrete algorithm (accept/reject of line-search trials, stopping tests), and on the
+random-init ReLU dynamics its trajectory through U-space is not continuous in the arithmetic, in
+ANY fp32 implementation.  So parity is layered:
+  * one iteration from the same start (maxiter 0 and 1): 1e-4 relative, row-wise, on X, U, obj,
+    gradient, adjoints and the Jacobians; iteration counts exact;
+  * a few iterations: the same bar with counted outliers (rows whose accept decision flipped);
+  * a full run: invariants that hold for any correct implementation (descent, obj = J(U) and
+    gradient = dJ/dU recomputed by the fp64 oracle at the RETURNED U, iteration bounds) and
+    agreement with the oracle in distribution."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ilqr as oilqr
+from oracle import planner as oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _setup(cfg, seed, B):
+    p, x0, U0, goal = util.case(cfg, seed, B=B)
+    h = util.make_handle(cfg, p)
+    return h, util.to_oracle(p), x0, U0[:, 0].copy(), goal
+
+
+@pytest.mark.parametrize("cfg,B", [(util.SMALL, 1), (util.SMALL, 37), (util.MID, 40), (util.ODD, 33),
+                                   (util.WIDE, 8)])
+def test_ilqr_maxiter0_is_rollout_and_linearisation(cfg, B, built_lib):
+    """No iteration: X = rollout, obj = J, gradient/adjoints from the explicit Jacobians (trajax
+    `adjoint`), lqr A/B = dynamics Jacobians."""
+    h, op, x0, U0, goal = _setup(cfg, 41, B)
+    X, U, obj, g, lam, (A, Bm), it = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=0, want_lqr=True)
+    margin = [None]
+    oX, oJ, odU, olam = oracle.objective_grad(util.tt(x0), util.tt(U0), util.tt(goal), op, margin)
+    assert torch.equal(U.cpu(), torch.from_numpy(U0))
+    assert int(it.abs().max()) == 0
+    assert util.rel_rows(X, oX) < TOL and util.rel_rows(obj[:, None], oJ[:, None]) < TOL
+    away = margin[0] > 1e-6
+    print(f"rows within 1e-6 of a ReLU kink: {int((~away).sum())} of {B}")
+    assert int(away.sum()) >= (B + 1) // 2
+    aw = away.cuda()
+    assert util.rel_rows(g[aw], odU[away]) < TOL
+    assert util.rel_rows(lam[aw], olam[away]) < TOL
+    *_, oA, oB = oilqr.lqr_params(oX, util.tt(U0), util.tt(goal), op)
+    assert util.rel_rows(A[aw], oA[away]) < TOL
+    assert util.rel_rows(Bm[aw], oB[away]) < TOL
+
+
+@pytest.mark.parametrize("cfg,B,maxiter", [(util.SMALL, 37, 1), (util.MID, 40, 1), (util.ODD, 33, 1),
+                                           (util.SMALL, 64, 3), (util.MID, 33, 3)])
+def test_ilqr_iterations_match_oracle(cfg, B, maxiter, built_lib):
+    h, op, x0, U0, goal = _setup(cfg, 43, B)
+    X, U, obj, g, lam, _, it = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=maxiter)
+    oX, oU, oobj, og, olam, _, oit = oilqr.ilqr(util.tt(x0), util.tt(U0), util.tt(goal), op, maxiter=maxiter)
+    same_it = (it.cpu() == oit)
+    print(f"iteration counts equal: {int(same_it.sum())} of {B}")
+    assert int(same_it.sum()) >= B - max(1, B // 16)
+    frac = 0.1 if maxiter == 1 else 0.2
+    util.assert_rows_close("U", U, oU, tol=TOL, outlier_frac=frac, cap=2.0)
+    util.assert_rows_close("X", X, oX, tol=TOL, outlier_frac=frac, cap=2.0)
+    util.assert_rows_close("obj", obj[:, None], oobj[:, None], tol=TOL, outlier_frac=frac, cap=1.0)
+
+
+def test_ilqr_golden(built_lib):
+    z = np.load(os.path.join(GOLDEN, "ilqr_small.npz"))
+    cfg = util.SMALL
+    p, x0, U0, goal = util.case(cfg, int(z["seed"]), B=int(z["B"]))
+    h = util.make_handle(cfg, p)
+    X, U, obj, g, lam, _, it = h.ilqr(dev(x0), dev(U0[:, 0]), dev(goal), maxiter=int(z["maxiter"]))
+    e = util.rel_each(obj[:, None], torch.from_numpy(z["obj"])[:, None])
+    print("golden obj rel err", e.tolist(), "iterations", it.tolist(), z["iteration"].tolist())
+    assert float(e.median()) < TOL and float(e.max()) < 5e-2
+
+
+@pytest.mark.parametrize("cfg,B,maxiter", [(util.SMALL, 70, 100), (util.MID, 48, 40)])
+def test_ilqr_full_run_invariants(cfg, B, maxiter, built_lib):
+    h, op, x0, U0, goal = _setup(cfg, 47, B)
+    X, U, obj, g, lam, _, it = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=maxiter)
+    _, J0 = oracle.objective(util.tt(x0), util.tt(U0), util.tt(goal), op)
+    # descent: accepted steps are strict decreases of the fp32 objective
+    assert bool((obj.double().cpu() <= J0 * (1 + 1e-5)).all())
+    assert 0 <= int(it.min()) and int(it.max()) <= maxiter
+    # the returned tuple is self-consistent at the returned U (fp64 oracle as the judge)
+    margin = [None]
+    oX, oJ, odU, olam = oracle.objective_grad(util.tt(x0), U.double().cpu(), util.tt(goal), op, margin)
+    assert util.rel_rows(X, oX) < TOL
+    assert util.rel_rows(obj[:, None], oJ[:, None]) < TOL
+    away = margin[0] > 1e-6
+    assert int(away.sum()) >= (B + 1) // 2
+    assert util.rel_rows(g[away.cuda()], odU[away]) < 5e-4
+    # agreement with the oracle's own run in distribution (the two trajectories through U-space
+    # separate at the first flipped accept decision; both descend to comparable objectives)
+    _, _, oobj, _, _, _, oit = oilqr.ilqr(util.tt(x0), util.tt(U0), util.tt(goal), op, maxiter=maxiter)
+    ratio = obj.double().cpu() / oobj
+    print(f"obj / oracle obj: median {float(ratio.median()):.4f}, min {float(ratio.min()):.3f}, "
+          f"max {float(ratio.max()):.3f}; iterations kernel median {float(it.float().median())}, "
+          f"oracle median {float(oit.float().median())}; improvement median "
+          f"{float((obj.double().cpu() / J0).median()):.3f}")
+    assert 0.9 < float(ratio.median()) < 1.1
+
+
+def test_ilqr_lane_independence(built_lib):
+    """vmap semantics: a trajectory's result does not depend on its tile mates (bitwise)."""
+    cfg = util.SMALL
+    h, op, x0, U0, goal = _setup(cfg, 53, 40)
+    full = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=10)
+    for b in (0, 35):
+        one = h.ilqr(dev(x0[b:b + 1]), dev(U0[b:b + 1]), dev(goal[b:b + 1]), maxiter=10)
+        for i in (0, 1, 2, 3, 4, 6):
+            assert torch.equal(full[i][b], one[i][0]), i
+
+
+def test_ilqr_rejects_unsupported_options(built_lib):
+    h, op, x0, U0, goal = _setup(util.SMALL, 3, 2)
+    with pytest.raises(NotImplementedError):
+        h.ilqr(dev(x0), dev(U0), dev(goal), make_psd=True)
+    with pytest.raises(TypeError):
+        h.ilqr(dev(x0), dev(U0), dev(goal), bogus=1)
