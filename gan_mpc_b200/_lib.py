@@ -59,6 +59,8 @@ _SIGS = {
                                  _f, _f, _f, C.c_void_p]),
     "gmpc_ilqr": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.POINTER(IlqrOptions), _f, _f, _f,
                             _f, _f, _f, _f, _f, C.c_void_p]),
+    "gmpc_bilevel_l2": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, _f, C.POINTER(IlqrOptions)] + [_f] * 12
+                        + [C.c_void_p]),
     "gmpc_ilqr_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.c_void_p]),
     "gmpc_critic_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_void_p]),
@@ -286,6 +288,37 @@ class Handle:
             _ptr(goal, device=dev, name="goal"), C.byref(opt), _ptr(X), _ptr(U), _ptr(obj),
             _ptr(grad), _ptr(lam), _ptr(it, dtype=torch.int32), _ptr(A), _ptr(Bm), _stream(dev)))
         return X, U, obj, grad, lam, ((A, Bm) if want_lqr else None), it
+
+    def bilevel_l2(self, x0, U0, goal, desired, maxiter=100, grad_norm_threshold=1e-4, alpha_0=1.0,
+                   alpha_min=0.00005, want_hessian=False, V=None, **unsupported):
+        """bilevel_optimization (policy/optimizers.py:34-75) for the L2 loss, batched; see
+        include/gmpc.h.  Returns a dict of X, U, obj, low_level_grad, iteration, loss, B, hessian,
+        H, dxT, grad_mpc_weights."""
+        for k, v in unsupported.items():
+            if k not in ("relative_grad_norm_threshold", "obj_step_threshold",
+                         "inputs_step_threshold", "make_psd", "psd_delta"):
+                raise TypeError(f"bilevel_l2: unknown option {k!r}")
+            if v not in (0.0, False):
+                raise NotImplementedError(f"bilevel_l2: {k}={v!r} (the reference uses 0.0 / False)")
+        dev = self.device
+        B, T, n, m = x0.shape[0], self.T, self.n, self.m
+        f = dict(device=dev, dtype=torch.float32)
+        o = dict(X=torch.empty(B, T + 1, n, **f), U=torch.empty(B, T, m, **f), obj=torch.empty(B, **f),
+                 low_level_grad=torch.empty(B, T, m, **f),
+                 iteration=torch.empty(B, device=dev, dtype=torch.int32), loss=torch.empty(B, **f),
+                 B=torch.empty(B, T, m, **f),
+                 hessian=torch.empty(B, T * m, T * m, **f) if want_hessian else None,
+                 H=torch.empty(B, T, m, **f), dxT=torch.empty(B, n, **f),
+                 grad_mpc_weights=torch.empty(B, 3, **f))
+        opt = IlqrOptions(int(maxiter), float(grad_norm_threshold), float(alpha_0), float(alpha_min))
+        _check(self.lib.gmpc_bilevel_l2(
+            self._h, B, _ptr(x0, device=dev, name="x0"), _ptr(U0, device=dev, name="U0"),
+            _ptr(goal, device=dev, name="goal"), _ptr(desired, device=dev, name="desired"), C.byref(opt),
+            _ptr(o["X"]), _ptr(o["U"]), _ptr(o["obj"]), _ptr(o["low_level_grad"]),
+            _ptr(o["iteration"], dtype=torch.int32), _ptr(o["loss"]), _ptr(o["B"]), _ptr(o["hessian"]),
+            _ptr(o["H"]), _ptr(o["dxT"]), _ptr(o["grad_mpc_weights"]),
+            _ptr(V, device=dev, name="V"), _stream(dev)))
+        return o
 
     def ilqr_stats(self):
         """(tile-level outer iterations, rollouts) of the ilqr calls since the last query."""

@@ -463,10 +463,16 @@ extern "C" int gmpc_plan(gmpc_handle* h, int64_t B, int32_t K, const float* x0, 
 }
 
 // ilqr_solve (policy/optimizers.py:10-21): the whole trajax iLQR loop as one kernel (csrc/ilqr.cuh).
-extern "C" int gmpc_ilqr(gmpc_handle* h, int64_t B, const float* x0, const float* U0,
-                         const float* goal, const gmpc_ilqr_options* opt, float* X, float* U,
-                         float* obj, float* gradient, float* adjoints, int32_t* iteration,
-                         float* lqr_A, float* lqr_B, void* stream) {
+struct BilevelArgs {
+  const float* desired;
+  float *loss, *Bvec, *hess, *H, *dxT, *gw;
+  const float* V;
+};
+
+static int ilqr_launch(gmpc_handle* h, int64_t B, const float* x0, const float* U0,
+                       const float* goal, const gmpc_ilqr_options* opt, float* X, float* U,
+                       float* obj, float* gradient, float* adjoints, int32_t* iteration,
+                       float* lqr_A, float* lqr_B, const BilevelArgs* bl, void* stream) {
   int rc = check_ready(h, "gmpc_ilqr", B);
   if (rc) return rc;
   if (B == 0) return GMPC_OK;
@@ -480,7 +486,7 @@ extern "C" int gmpc_ilqr(gmpc_handle* h, int64_t B, const float* x0, const float
   CU_CHECK(cudaGetDeviceProperties(&prop, c.device));
   if (SL.bytes > (size_t)prop.sharedMemPerBlockOptin)
     return fail(GMPC_E_UNSUPPORTED, "gmpc_ilqr: the Riccati matrices of a 32-trajectory tile do not fit shared memory (state size too large)");
-  const IlqrWs WL = ilqr_ws_layout(c.n, c.m, c.T, c.cost_fout);
+  const IlqrWs WL = ilqr_ws_layout(c.n, c.m, c.T, c.cost_fout, bl != nullptr);
   const size_t need = (size_t)h->num_sms * WL.total * sizeof(float);
   if (need > h->ilqr_ws_bytes) {
     CU_CHECK(cudaStreamSynchronize(st));
@@ -520,6 +526,10 @@ extern "C" int gmpc_ilqr(gmpc_handle* h, int64_t B, const float* x0, const float
   Q.ws = h->d_ilqr_ws;
   Q.ws_stride = (long long)WL.total;
   Q.stats = h->d_ilqr_stats;
+  if (bl) {
+    Q.desired = bl->desired; Q.bl_loss = bl->loss; Q.bl_B = bl->Bvec; Q.bl_hess = bl->hess;
+    Q.bl_H = bl->H; Q.bl_dxT = bl->dxT; Q.bl_gw = bl->gw; Q.bl_V = bl->V;
+  }
   const int grid = std::min(P.ntiles, h->num_sms);
   if (h->maxt == 1)
     ilqr_kernel<1><<<grid, NTHREADS, SL.bytes, st>>>(Q);
@@ -528,6 +538,30 @@ extern "C" int gmpc_ilqr(gmpc_handle* h, int64_t B, const float* x0, const float
   ++h->launches;
   CU_CHECK(cudaGetLastError());
   return GMPC_OK;
+}
+
+extern "C" int gmpc_ilqr(gmpc_handle* h, int64_t B, const float* x0, const float* U0,
+                         const float* goal, const gmpc_ilqr_options* opt, float* X, float* U,
+                         float* obj, float* gradient, float* adjoints, int32_t* iteration,
+                         float* lqr_A, float* lqr_B, void* stream) {
+  return ilqr_launch(h, B, x0, U0, goal, opt, X, U, obj, gradient, adjoints, iteration, lqr_A, lqr_B,
+                     nullptr, stream);
+}
+
+// bilevel_optimization (policy/optimizers.py:34-75) for loss = L2MPC.loss: iLQR + the bilevel tail in
+// the same kernel launch.
+extern "C" int gmpc_bilevel_l2(gmpc_handle* h, int64_t B, const float* x0, const float* U0,
+                               const float* goal, const float* desired, const gmpc_ilqr_options* opt,
+                               float* X, float* U, float* obj, float* low_level_grad,
+                               int32_t* iteration, float* loss, float* loss_grad_U, float* hessian,
+                               float* H, float* dxT, float* grad_mpc_weights, const float* V,
+                               void* stream) {
+  if (!desired || !loss || !H || !dxT || !grad_mpc_weights)
+    return fail(GMPC_E_ARG, "gmpc_bilevel_l2: null argument");
+  if (V && hessian) return fail(GMPC_E_ARG, "gmpc_bilevel_l2: a given direction V skips the Hessian");
+  BilevelArgs bl{desired, loss, loss_grad_U, hessian, H, dxT, grad_mpc_weights, V};
+  return ilqr_launch(h, B, x0, U0, goal, opt, X, U, obj, low_level_grad, nullptr, iteration, nullptr,
+                     nullptr, &bl, stream);
 }
 
 extern "C" int gmpc_ilqr_stats(gmpc_handle* h, int64_t* outer_iterations, int64_t* rollouts, void* stream) {

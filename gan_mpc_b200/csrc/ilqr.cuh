@@ -40,13 +40,23 @@ struct IlqrParams {
   float* ws;            // per-CTA slabs, see IlqrWs
   long long ws_stride;  // floats per CTA
   long long* stats;     // nullable: [0] outer iterations (tile level), [1] line-search rollouts
+  // bilevel tail (policy/optimizers.py:59-73 for loss = L2MPC.loss), run when `desired` is set
+  const float* desired; // [B,T+1,n]
+  float* bl_loss;       // [B]        high-level loss L2MPC.loss(X, desired)
+  float* bl_B;          // [B,T,m]    nullable: loss_grad_wrt_control
+  float* bl_hess;       // [B,Tm,Tm]  nullable: cost_hessian_wrt_control
+  float* bl_H;          // [B,T,m]    solve(hessian, B)
+  float* bl_dxT;        // [B,n]      d x_T / dU . H  (tangent of the terminal state along H)
+  float* bl_gw;         // [B,3]      d (H . grad_U J) / d mpc_weights (raw, pre-sigmoid)
+  const float* bl_V;    // [B,T,m]    nullable: cost_vjp's direction V given by the caller -- used instead
+                        //            of H (no Hessian, no solve; bl_H returns V)
 };
 
 // per-CTA global scratch, every array is [..][RT]
 struct IlqrWs {
-  size_t X, Xn, G, lam, U, Un, k, grad, A, B, K, Jf, QT, qT, total;
+  size_t X, Xn, G, lam, U, Un, k, grad, A, B, K, Jf, QT, qT, S, QS, H, rhs, total;
 };
-__host__ __device__ inline IlqrWs ilqr_ws_layout(int n, int m, int T, int fout) {
+__host__ __device__ inline IlqrWs ilqr_ws_layout(int n, int m, int T, int fout, int bilevel) {
   IlqrWs s;
   size_t o = 0;
   const size_t sx = (size_t)(T + 1) * n * RT, su = (size_t)T * m * RT;
@@ -64,6 +74,14 @@ __host__ __device__ inline IlqrWs ilqr_ws_layout(int n, int m, int T, int fout) 
   s.Jf = o; o += (size_t)fout * n * RT;
   s.QT = o; o += (size_t)n * n * RT;
   s.qT = o; o += (size_t)n * RT;
+  s.S = s.QS = s.H = s.rhs = o;
+  if (bilevel) {  // sensitivities d x_t / dU [n][Tm], Q S, the (Tm)^2 Hessian, the right-hand side
+    const size_t TM = (size_t)T * m;
+    s.S = o; o += (size_t)n * TM * RT;
+    s.QS = o; o += (size_t)n * TM * RT;
+    s.H = o; o += TM * TM * RT;
+    s.rhs = o; o += TM * RT;
+  }
   s.total = o;
   return s;
 }
@@ -183,7 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
   const float w2 = 1.f / (1.f + expf(-P.mpcw[2]));
   const float a2 = ALPHA * ALPHA;
 
-  const IlqrWs WL = ilqr_ws_layout(n, m, T, fout);
+  const IlqrWs WL = ilqr_ws_layout(n, m, T, fout, Q.desired != nullptr);
   float* wsb = Q.ws + (size_t)blockIdx.x * Q.ws_stride;
   float *wsX = wsb + WL.X, *wsXn = wsb + WL.Xn, *wsG = wsb + WL.G, *wsLam = wsb + WL.lam;
   float *wsU = wsb + WL.U, *wsUn = wsb + WL.Un, *wsk = wsb + WL.k, *wsGrad = wsb + WL.grad;
@@ -603,17 +621,281 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       }
     }
 
+
+    // ================================================================== bilevel tail
+    // policy/optimizers.py:59-73 at the planned U, loss = L2MPC.loss (norm/l2_policy.py:12-18).
+    // The dynamics MLP is piecewise linear, so d^2 x_t / dU^2 = 0 almost everywhere and jax.hessian of
+    // the objective is  A = sum_t S_t^T Q_t S_t + blockdiag(R_t),  S_t = d x_t / dU  (S_{t+1} = A_t S_t,
+    // block t <- B_t), with the Jacobians A_t, B_t and Q_T = 2 w2 Jf^T Jf of the last linearisation.
+    if (Q.desired != nullptr) {
+      const int TM = T * m;
+      float* wsD = wsXn;                       // desired states (the trial buffers are free now)
+      float* wsBv = wsUn;                      // loss_grad_wrt_control, kept for the output
+      float* wsS = wsb + WL.S;
+      float* wsQS = wsb + WL.QS;
+      float* wsH = wsb + WL.H;
+      float* wsR = wsb + WL.rhs;
+      float* Qm_s = P_s;                       // [n*n]
+      float* cand_v = T_s;                     // [8]
+      int* cand_i = reinterpret_cast<int*>(T_s + 8 * RT);  // [8]
+      float* part_s = T_s + 16 * RT;           // [8]
+      float* dx_s = p_s;
+      float* dxn_s = pn_s;
+      const float cl2 = 2.f / (float)(T + 1);
+      __syncthreads();
+      {
+        const int per = (T + 1) * n;
+        for (int e = tid; e < RT * per; e += NTHREADS) {
+          const int rr = e / per, rest = e - rr * per;
+          const long long q = q0 + rr;
+          wsD[rest * RT + rr] = (q < P.NQ) ? Q.desired[q * per + rest] : 0.f;
+        }
+      }
+      for (int e = tid; e < TM * TM * RT; e += NTHREADS) wsH[e] = 0.f;
+      for (int e = tid; e < n * TM * RT; e += NTHREADS) wsS[e] = 0.f;
+      __syncthreads();
+      // ---- loss and B = d loss / dU (adjoint scan with q_t = 2/(T+1) (x_t - desired_t), r_t = 0)
+      if (tid < RT) {
+        float s = 0.f;
+        for (int e = 0; e < (T + 1) * n; ++e) {
+          const float d = wsX[e * RT + r] - wsD[e * RT + r];
+          s = fmaf(d, d, s);
+        }
+        if (q0 + r < P.NQ) Q.bl_loss[q0 + r] = s / (float)(T + 1);
+      }
+      for (int e = tid; e < n * RT; e += NTHREADS)
+        p_s[e] = cl2 * (wsX[(size_t)T * n * RT + e] - wsD[(size_t)T * n * RT + e]);
+      __syncthreads();
+#pragma unroll 1
+      for (int t = T - 1; t >= 0; --t) {
+        for (int e = tid; e < (n + m) * RT; e += NTHREADS) {
+          const int row = e >> 5;
+          if (row < n) {
+            const int i = row;
+            float s = cl2 * (wsX[(t * n + i) * RT + r] - wsD[(t * n + i) * RT + r]);
+            const float* Ar = wsA + (size_t)(t * n * n + i) * RT + r;
+            for (int k = 0; k < n; ++k) s = fmaf(Ar[(size_t)k * n * RT], p_s[k * RT + r], s);
+            pn_s[i * RT + r] = s;
+          } else {
+            const int a = row - n;
+            float s = 0.f;
+            const float* Br = wsB + (size_t)(t * n * m + a) * RT + r;
+            for (int k = 0; k < n; ++k) s = fmaf(Br[(size_t)k * m * RT], p_s[k * RT + r], s);
+            wsR[(t * m + a) * RT + r] = s;
+            wsBv[(t * m + a) * RT + r] = s;
+          }
+        }
+        __syncthreads();
+        for (int e = tid; e < n * RT; e += NTHREADS) p_s[e] = pn_s[e];
+        __syncthreads();
+      }
+      if (Q.bl_V != nullptr) {
+        const int per = T * m;
+        for (int e = tid; e < RT * per; e += NTHREADS) {
+          const int rr = e / per, rest = e - rr * per;
+          const long long q = q0 + rr;
+          wsR[rest * RT + rr] = (q < P.NQ) ? Q.bl_V[q * per + rest] : 0.f;
+        }
+        __syncthreads();
+      } else {
+      // ---- Hessian: blockdiag(R_t) + sum_t S_t^T Q_t S_t
+      for (int e = tid; e < T * m * m * RT; e += NTHREADS) {
+        const int ee = e >> 5, t = ee / (m * m), ab = ee - t * m * m, a = ab / m, b = ab - a * m;
+        float uu = 0.f;
+        for (int j = 0; j < m; ++j) uu = fmaf(wsU[(t * m + j) * RT + r], wsU[(t * m + j) * RT + r], uu);
+        const float su = sqrtf(uu + a2);
+        wsH[(size_t)((t * m + a) * TM + t * m + b) * RT + r] =
+            w0 * ((a == b ? 1.f : 0.f) / su - wsU[(t * m + a) * RT + r] * wsU[(t * m + b) * RT + r] / (su * su * su));
+      }
+      __syncthreads();
+#pragma unroll 1
+      for (int t = 0; t <= T; ++t) {
+        const int ncol = t * m;
+        if (ncol > 0) {
+          if (t < T) {
+            for (int e = tid; e < n * RT; e += NTHREADS) d_s[e] = wsX[(size_t)t * n * RT + e] - wsG[(size_t)t * n * RT + e];
+            __syncthreads();
+            if (tid < RT) {
+              float dd = 0.f;
+              for (int i = 0; i < n; ++i) dd = fmaf(d_s[i * RT + r], d_s[i * RT + r], dd);
+              sd_s[r] = sqrtf(dd + a2);
+            }
+            __syncthreads();
+            for (int e = tid; e < n * n * RT; e += NTHREADS) {
+              const int ee = e >> 5, i = ee / n, j = ee - i * n;
+              const float sd = sd_s[r];
+              Qm_s[e] = w1 * ((i == j ? 1.f : 0.f) / sd - d_s[i * RT + r] * d_s[j * RT + r] / (sd * sd * sd));
+            }
+          } else {
+            for (int e = tid; e < n * n * RT; e += NTHREADS) Qm_s[e] = wsQT[e];
+          }
+          __syncthreads();
+          for (int e = tid; e < n * ncol * RT; e += NTHREADS) {  // QS = Q_t S_t
+            const int ee = e >> 5, i = ee / ncol, c = ee - i * ncol;
+            float s = 0.f;
+            for (int j = 0; j < n; ++j) s = fmaf(Qm_s[(i * n + j) * RT + r], wsS[(size_t)(j * TM + c) * RT + r], s);
+            wsQS[(size_t)(i * TM + c) * RT + r] = s;
+          }
+          __syncthreads();
+          for (int e = tid; e < ncol * ncol * RT; e += NTHREADS) {  // lower triangle += S^T (Q S)
+            const int ee = e >> 5, c1 = ee / ncol, c2 = ee - c1 * ncol;
+            if (c2 > c1) continue;
+            float s = 0.f;
+            for (int i = 0; i < n; ++i)
+              s = fmaf(wsS[(size_t)(i * TM + c1) * RT + r], wsQS[(size_t)(i * TM + c2) * RT + r], s);
+            wsH[(size_t)(c1 * TM + c2) * RT + r] += s;
+          }
+          __syncthreads();
+        }
+        if (t < T) {  // S_{t+1} = A_t S_t, block t <- B_t
+          const float* Ag = wsA + (size_t)t * n * n * RT + r;
+          for (int e = tid; e < n * ncol * RT; e += NTHREADS) {
+            const int ee = e >> 5, i = ee / ncol, c = ee - i * ncol;
+            float s = 0.f;
+            for (int j = 0; j < n; ++j) s = fmaf(Ag[(size_t)(i * n + j) * RT], wsS[(size_t)(j * TM + c) * RT + r], s);
+            wsQS[(size_t)(i * TM + c) * RT + r] = s;
+          }
+          __syncthreads();
+          for (int e = tid; e < n * (ncol + m) * RT; e += NTHREADS) {
+            const int ee = e >> 5, i = ee / (ncol + m), c = ee - i * (ncol + m);
+            wsS[(size_t)(i * TM + c) * RT + r] =
+                c < ncol ? wsQS[(size_t)(i * TM + c) * RT + r] : wsB[(size_t)((t * n + i) * m + (c - ncol)) * RT + r];
+          }
+          __syncthreads();
+        }
+      }
+      for (int e = tid; e < TM * TM * RT; e += NTHREADS) {  // mirror the lower triangle
+        const int ee = e >> 5, c1 = ee / TM, c2 = ee - c1 * TM;
+        if (c2 > c1) wsH[e] = wsH[(size_t)(c2 * TM + c1) * RT + r];
+      }
+      __syncthreads();
+      if (Q.bl_hess != nullptr) {
+        const size_t per = (size_t)TM * TM;
+        for (size_t e = tid; e < RT * per; e += NTHREADS) {
+          const size_t rr = e / per, rest = e - rr * per;
+          const long long q = q0 + (long long)rr;
+          if (q < P.NQ) Q.bl_hess[q * per + rest] = wsH[rest * RT + rr];
+        }
+        __syncthreads();
+      }
+      // ---- H = solve(A, B): Gaussian elimination with partial pivoting, one system per lane
+      // (jax.scipy.linalg.solve is LU with partial pivoting; no regularisation, policy/optimizers.py:67)
+#pragma unroll 1
+      for (int k = 0; k < TM; ++k) {
+        float best = -1.f;
+        int bi = k;
+        for (int i = k + w; i < TM; i += NTHREADS / 32) {
+          const float v = fabsf(wsH[(size_t)(i * TM + k) * RT + r]);
+          if (v > best) { best = v; bi = i; }
+        }
+        cand_v[w * RT + r] = best;
+        cand_i[w * RT + r] = bi;
+        __syncthreads();
+        int piv = k;
+        best = -1.f;
+        for (int ww = 0; ww < NTHREADS / 32; ++ww) {
+          const float v = cand_v[ww * RT + r];
+          const int ci = cand_i[ww * RT + r];
+          if (v > best || (v == best && ci < piv)) { best = v; piv = ci; }
+        }
+        if (piv != k) {
+          for (int j = k + w; j < TM; j += NTHREADS / 32) {
+            const float a = wsH[(size_t)(k * TM + j) * RT + r], b = wsH[(size_t)(piv * TM + j) * RT + r];
+            wsH[(size_t)(k * TM + j) * RT + r] = b;
+            wsH[(size_t)(piv * TM + j) * RT + r] = a;
+          }
+          if (w == 0) {
+            const float a = wsR[k * RT + r], b = wsR[piv * RT + r];
+            wsR[k * RT + r] = b;
+            wsR[piv * RT + r] = a;
+          }
+        }
+        __syncthreads();
+        const float pk = wsH[(size_t)(k * TM + k) * RT + r];
+        const float rk = wsR[k * RT + r];
+        for (int i = k + 1 + w; i < TM; i += NTHREADS / 32) {
+          const float f = wsH[(size_t)(i * TM + k) * RT + r] / pk;
+          float* row = wsH + (size_t)i * TM * RT + r;
+          const float* prow = wsH + (size_t)k * TM * RT + r;
+          for (int j = k + 1; j < TM; ++j) row[(size_t)j * RT] = fmaf(-f, prow[(size_t)j * RT], row[(size_t)j * RT]);
+          wsR[i * RT + r] = fmaf(-f, rk, wsR[i * RT + r]);
+        }
+        __syncthreads();
+      }
+#pragma unroll 1
+      for (int k = TM - 1; k >= 0; --k) {  // back substitution, the dot product split over the 8 warps
+        float s = 0.f;
+        for (int j = k + 1 + w; j < TM; j += NTHREADS / 32) s = fmaf(wsH[(size_t)(k * TM + j) * RT + r], wsR[j * RT + r], s);
+        part_s[w * RT + r] = s;
+        __syncthreads();
+        if (w == 0) {
+          float tot = 0.f;
+          for (int ww = 0; ww < NTHREADS / 32; ++ww) tot += part_s[ww * RT + r];
+          wsR[k * RT + r] = (wsR[k * RT + r] - tot) / wsH[(size_t)(k * TM + k) * RT + r];
+        }
+        __syncthreads();
+      }
+      }
+      // ---- tangent rollout along H and the mpc_weights part of grad_theta (H . grad_U J)
+      float g0 = 0.f, g1 = 0.f;
+      for (int e = tid; e < n * RT; e += NTHREADS) dx_s[e] = 0.f;
+      __syncthreads();
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        if (tid < RT) {
+          float uu = 0.f, dd = 0.f, uh = 0.f, ddx = 0.f;
+          for (int j = 0; j < m; ++j) {
+            const float u = wsU[(t * m + j) * RT + r];
+            uu = fmaf(u, u, uu);
+            uh = fmaf(u, wsR[(t * m + j) * RT + r], uh);
+          }
+          for (int i = 0; i < n; ++i) {
+            const float d = wsX[(t * n + i) * RT + r] - wsG[(t * n + i) * RT + r];
+            dd = fmaf(d, d, dd);
+            ddx = fmaf(d, dx_s[i * RT + r], ddx);
+          }
+          g0 += uh / sqrtf(uu + a2);
+          g1 += ddx / sqrtf(dd + a2);
+        }
+        for (int e = tid; e < n * RT; e += NTHREADS) {
+          const int i = e >> 5;
+          float s = 0.f;
+          const float* Ar = wsA + (size_t)((t * n + i) * n) * RT + r;
+          const float* Br = wsB + (size_t)((t * n + i) * m) * RT + r;
+          for (int j = 0; j < n; ++j) s = fmaf(Ar[(size_t)j * RT], dx_s[j * RT + r], s);
+          for (int a = 0; a < m; ++a) s = fmaf(Br[(size_t)a * RT], wsR[(t * m + a) * RT + r], s);
+          dxn_s[e] = s;
+        }
+        __syncthreads();
+        for (int e = tid; e < n * RT; e += NTHREADS) dx_s[e] = dxn_s[e];
+        __syncthreads();
+      }
+      if (tid < RT && q0 + r < P.NQ) {
+        float g2 = 0.f;  // 2 y^T Jf dx_T = q_T . dx_T / w2
+        for (int i = 0; i < n; ++i) {
+          g2 = fmaf(wsqT[i * RT + r], dx_s[i * RT + r], g2);
+          Q.bl_dxT[(q0 + r) * n + i] = dx_s[i * RT + r];
+        }
+        g2 /= w2;
+        Q.bl_gw[(q0 + r) * 3 + 0] = g0 * w0 * (1.f - w0);
+        Q.bl_gw[(q0 + r) * 3 + 1] = g1 * w1 * (1.f - w1);
+        Q.bl_gw[(q0 + r) * 3 + 2] = g2 * w2 * (1.f - w2);
+      }
+      __syncthreads();
+    }
     __syncthreads();
     // ------------------------------------------------------------------ write the tile out
     if (tid < RT && q0 + r < P.NQ) {
       if (P.J_out != nullptr) P.J_out[q0 + r] = obj_s[r];
       if (Q.it_out != nullptr) Q.it_out[q0 + r] = it_s[r];
     }
-    const struct { float* dst; const float* src; int per; } outs[6] = {
+    const bool bl = Q.desired != nullptr;
+    const struct { float* dst; const float* src; int per; } outs[8] = {
         {P.U_out, wsU, T * m},          {P.X_out, wsX, (T + 1) * n}, {P.dU_out, wsGrad, T * m},
-        {P.lam_out, wsLam, (T + 1) * n}, {Q.A_out, wsA, T * n * n},   {Q.B_out, wsB, T * n * m}};
+        {P.lam_out, wsLam, (T + 1) * n}, {Q.A_out, wsA, T * n * n},   {Q.B_out, wsB, T * n * m},
+        {bl ? Q.bl_B : nullptr, wsUn, T * m}, {bl ? Q.bl_H : nullptr, wsb + WL.rhs, T * m}};
 #pragma unroll 1
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 8; ++k) {
       if (outs[k].dst == nullptr) continue;
       const int per = outs[k].per;
       for (int e = tid; e < RT * per; e += NTHREADS) {

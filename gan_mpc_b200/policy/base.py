@@ -1,5 +1,7 @@
 """BaseMPC with the reference's interface (policy/base.py:12-128)."""
 
+import torch
+
 from gan_mpc_b200.policy import eval
 
 
@@ -25,7 +27,28 @@ class BaseMPC(eval.EvalMPC):
     def loss(self, xcseq, useq, params, *args):
         raise NotImplementedError
 
+    def _bilevel(self, x0, init_U, params, goal, desired, ilqr_kwargs=None, **kw):
+        """gmpc_bilevel_l2 on normalised inputs; returns (batched?, result dict)."""
+        if not self._loss_is_l2:
+            raise NotImplementedError(
+                "the bilevel gradient is fused for loss = L2MPC.loss; JS_MPC.generator_loss needs the "
+                "critic's input gradient inside the same kernel (not built)")
+        batched, x0b, Ub, gb = self._prep(x0, init_U, goal)
+        if Ub.shape[1] != 1:
+            raise ValueError("bilevel_optimization plans one action sequence per state")
+        db = (desired if desired.dim() == 3 else desired[None]).to(self.device, torch.float32).contiguous()
+        h = self._handle(x0b.shape[1], Ub.shape[3])
+        self._stage(h, params)
+        ik = dict(self.trajax_ilqr_kwargs if ilqr_kwargs is None else ilqr_kwargs)
+        return batched, h.bilevel_l2(x0b, Ub[:, 0].contiguous(), gb, db, **ik, **kw)
+
     def loss_and_grad(self, history_X, params, batch_loss_args):
-        """policy/base.py:87-128 -- vmap of the bilevel gradient: next scope row."""
-        from gan_mpc_b200.policy import optimizers as opt
-        opt.bilevel_optimization()
+        """policy/base.py:87-128 -- vmap of bilevel_optimization over the batch, mean loss and
+        leaf-wise mean of the per-sample gradient pytrees (here reduced without materialising them).
+        history_X [B,h+1,n], batch_loss_args = (batch_y [B,T+1,n],)."""
+        from gan_mpc_b200.policy import bilevel
+        (batch_y,) = batch_loss_args
+        goal, init_u = self.get_goal_states_init_actions(history_X, params)
+        _, out = self._bilevel(history_X[..., -1, :], init_u, params, goal, batch_y)
+        self.last_bilevel = out
+        return out["loss"].mean(), bilevel.high_level_grad_tree(params, out, reduce_mean=True)

@@ -93,22 +93,58 @@ def loss_grad_wrt_control(loss, dynamics, x0, U, loss_args):
     return pol._l2_loss_grad(x0, U, params, desired)[1]
 
 
-def _next_row(name):
-    raise NotImplementedError(
-        f"{name}: the bilevel (implicit-function) gradient -- (T*m)^2 Hessian, dense solve, mixed "
-        "VJP -- is the next scope row (SURVEY.md 8f-2); it is not part of the fused planner path")
+def bilevel_optimization(cost, dynamics, loss, x0, init_U, params, cost_args, dynamics_args,
+                         loss_args, trajax_ilqr_kwargs=None):
+    """policy/optimizers.py:34-75 for loss = L2MPC.loss: (high_level_loss, low_level_grad,
+    high_level_grad, itr) from ONE kernel launch (gmpc_bilevel_l2: iLQR, loss gradient, (T m)^2 Hessian,
+    LU solve, tangent rollout) plus the cost-MLP mixed VJP (policy/bilevel.py).  Unbatched shapes as in
+    the reference, or batched (then every output, the gradient leaves included, has a leading batch
+    axis -- what jax.vmap of this function returns at policy/base.py:122-125)."""
+    from gan_mpc_b200.policy import bilevel
+    pol = _owner(cost, "cost")
+    if _owner(dynamics, "dynamics") is not pol or _owner(loss, "loss") is not pol:
+        raise ValueError("cost, dynamics and loss must belong to the same policy")
+    if len(dynamics_args) != 0:
+        raise ValueError("MLP dynamics take no extra arguments (policy/eval.py:121)")
+    (desired,) = loss_args
+    batched, out = pol._bilevel(x0, init_U, params, cost_args[0], desired, trajax_ilqr_kwargs)
+    g = bilevel.high_level_grad_tree(params, out, reduce_mean=False)
+    res = (out["loss"], out["low_level_grad"], g, out["iteration"])
+    if not batched:
+        first = lambda t: ({k: first(v) for k, v in t.items()} if isinstance(t, dict)
+                           else (t[0] if isinstance(t, torch.Tensor) else t))
+        res = tuple(first(r) for r in res)
+    return res
 
 
-def bilevel_optimization(*a, **k):
-    """policy/optimizers.py:34-75."""
-    _next_row("bilevel_optimization")
+def cost_hessian_wrt_control(cost, dynamics, x0, U):
+    """policy/optimizers.py:86-90 -- jax.hessian of `objective` w.r.t. U: [T,m,T,m] (or [B,T,m,T,m]).
+    cost / dynamics are optimizers.bind(...) closures."""
+    if not isinstance(cost, Bound) or not isinstance(dynamics, Bound):
+        raise TypeError("cost_hessian_wrt_control() needs optimizers.bind(...) closures")
+    pol, goal = cost.policy, cost.args[0]
+    batched, out = pol._bilevel(x0, U, cost.params, goal, torch.zeros_like(goal),
+                                dict(pol.trajax_ilqr_kwargs, maxiter=0), want_hessian=True)
+    T, m = out["U"].shape[1:]
+    Hs = out["hessian"].reshape(-1, T, m, T, m)
+    return Hs if batched else Hs[0]
 
 
-def cost_hessian_wrt_control(*a, **k):
-    """policy/optimizers.py:86-90."""
-    _next_row("cost_hessian_wrt_control")
-
-
-def cost_vjp(*a, **k):
-    """policy/optimizers.py:93-105."""
-    _next_row("cost_vjp")
+def cost_vjp(cost, dynamics, V, x0, U, params, cost_args):
+    """policy/optimizers.py:93-105 -- grad_params ( V . grad_U objective(U; params) ), non-zero only
+    on the cost side of params.  cost is the policy's bound method, dynamics a bind(...) closure,
+    V is [T*m] (or [B,T*m])."""
+    from gan_mpc_b200.policy import bilevel
+    pol = _owner(cost, "cost")
+    goal = cost_args[0]
+    batched = x0.dim() == 2
+    T, m = U.shape[-2:]
+    Vb = (V if batched else V[None]).reshape(-1, T, m).to(pol.device, torch.float32).contiguous()
+    _, out = pol._bilevel(x0, U, params, goal, torch.zeros_like(goal),
+                          dict(pol.trajax_ilqr_kwargs, maxiter=0), V=Vb)
+    g = bilevel.high_level_grad_tree(params, out, reduce_mean=False)
+    if not batched:
+        first = lambda t: ({k: first(v) for k, v in t.items()} if isinstance(t, dict)
+                           else (t[0] if isinstance(t, torch.Tensor) else t))
+        g = first(g)
+    return g

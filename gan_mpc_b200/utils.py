@@ -62,3 +62,19 @@ def get_critic_model(config):
     else:
         raise ValueError("Choose lstm model.")
     return critic_model.CriticModel(config, nn_model), model_config
+
+
+def tree_clone(tree):
+    """deep copy of a params pytree (dict of dicts of tensors); non-tensor leaves are shared."""
+    import torch
+    if isinstance(tree, dict):
+        return {k: tree_clone(v) for k, v in tree.items()}
+    return tree.clone() if isinstance(tree, torch.Tensor) else tree
+
+
+def tree_map2(fn, a, b):
+    """jax.tree_map over two pytrees of the same structure (tensor leaves only)."""
+    import torch
+    if isinstance(a, dict):
+        return {k: tree_map2(fn, a[k], b[k]) for k in a}
+    return fn(a, b) if isinstance(a, torch.Tensor) else a

@@ -152,6 +152,29 @@ int gmpc_ilqr(gmpc_handle* h, int64_t B, const float* x0, const float* U0, const
               const gmpc_ilqr_options* opt, float* X, float* U, float* obj, float* gradient,
               float* adjoints, int32_t* iteration, float* lqr_A, float* lqr_B, void* stream);
 
+/* bilevel_optimization (policy/optimizers.py:34-75) for loss = L2MPC.loss (norm/l2_policy.py:12-18),
+ * the per-sample body of BaseMPC.loss_and_grad (policy/base.py:87-128), in the same kernel launch
+ * as the iLQR solve it starts with (maxiter = 0 evaluates the tail at U0 itself):
+ *   X, U, obj, low_level_grad, iteration  = ilqr(...)                         (:55)
+ *   loss        = L2MPC.loss(X, desired)                                       (:73)
+ *   loss_grad_U = loss_grad_wrt_control          [B,T,m]   (nullable)          (:61-63, :78-83)
+ *   hessian     = cost_hessian_wrt_control       [B,Tm,Tm] (nullable)          (:64-66, :86-90)
+ *   H           = solve(hessian, loss_grad_U)    [B,T,m]   LU, partial pivoting (:67)
+ * and the pieces of cost_vjp (:69-71, :93-105) that do not involve the cost-MLP weights:
+ *   dxT              [B,n]  tangent of the terminal state along H (d x_T / dU . H)
+ *   grad_mpc_weights [B,3]  d (H . grad_U J) / d mpc_weights (raw, pre-sigmoid values)
+ * The cost-MLP part of cost_vjp is  w2 * grad_theta d/de ||f(x_T + e dxT; theta)||^2  (one forward-
+ * over-reverse pass of the cost MLP per sample), assembled by the host mirror from x_T and dxT.
+ * The dynamics MLP is piecewise linear, so jax.hessian of the objective equals
+ * sum_t S_t^T Q_t S_t + blockdiag(R_t) with S_t = d x_t / dU; that is what is computed.
+ * V (nullable, [B,T,m]): cost_vjp's direction given by the caller (policy/optimizers.py:93) -- used
+ * in place of H, skipping the Hessian and the solve (hessian must then be null; H returns V). */
+int gmpc_bilevel_l2(gmpc_handle* h, int64_t B, const float* x0, const float* U0, const float* goal,
+                    const float* desired, const gmpc_ilqr_options* opt, float* X, float* U,
+                    float* obj, float* low_level_grad, int32_t* iteration, float* loss,
+                    float* loss_grad_U, float* hessian, float* H, float* dxT,
+                    float* grad_mpc_weights, const float* V, void* stream);
+
 /* Work counters of the gmpc_ilqr calls since the last query (synchronises `stream`): tile-level
  * outer iterations and rollouts (1 + line-search trials) summed over the 32-trajectory tiles. */
 int gmpc_ilqr_stats(gmpc_handle* h, int64_t* outer_iterations, int64_t* rollouts, void* stream);

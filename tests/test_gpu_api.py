@@ -100,8 +100,9 @@ def test_batched_policy_and_optimizer_functions(built_lib):
     # cost_trainer.calculate_loss = mean loss of the plans
     test_loss = cost_trainer.calculate_loss(policy, params, (hx, desired))
     assert abs(float(test_loss) - float(loss.mean())) < 1e-5 * abs(float(loss.mean()))
-    with pytest.raises(NotImplementedError, match="next scope row"):
-        policy.loss_and_grad(hx, params, (desired,))
+    # loss_and_grad (the bilevel gradient) returns a params-shaped pytree; parity in test_gpu_bilevel.py
+    bl_loss, bl_grads = policy.loss_and_grad(hx, params, (desired,))
+    assert bl_loss.shape == () and set(bl_grads) == set(params)
 
 
 def test_restaging_follows_parameter_updates(built_lib):

@@ -1,0 +1,156 @@
+"""GPU parity of the bilevel (cost-training) gradient -- gmpc_bilevel_l2 + the host mirror of
+policy/optimizers.py:34-105 and policy/base.py:87-128 -- against oracle/bilevel.py, which restates
+those lines by literal autodiff (torch.autograd standing in for jax.grad / jax.hessian).
+
+The tail is checked AT THE KERNEL'S OWN planned U (the oracle tail is evaluated there), so the
+comparison is not polluted by iLQR accept decisions; the iLQR part has its own tests.
+Tolerances: loss, B, Hessian 1e-4 relative (row-wise); H = solve(A, B) and what is derived from it
+1e-4 x cond-number headroom, stated per test -- the reference solves the same fp32 system without
+regularisation (policy/optimizers.py:67)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gan_mpc_b200 import utils
+from gan_mpc_b200.config import load_config
+from gan_mpc_b200.norm import cost_trainer
+from gan_mpc_b200.norm import runner as norm_runner
+from gan_mpc_b200.policy import optimizers as opt
+from oracle import bilevel as obl
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _case(cfg, seed, B):
+    p, x0, U0, goal = util.case(cfg, seed, B=B)
+    rng = np.random.Generator(np.random.PCG64(seed + 7))
+    desired = (goal + 0.05 * rng.standard_normal(goal.shape)).astype(np.float32)
+    return p, x0, U0[:, 0].copy(), goal, desired
+
+
+@pytest.mark.parametrize("cfg,B,maxiter", [(util.SMALL, 37, 0), (util.ODD, 33, 0), (util.MID, 8, 0),
+                                           (util.SMALL, 12, 3), (util.ODD, 6, 2)])
+def test_bilevel_tail_matches_autodiff_oracle(cfg, B, maxiter, built_lib):
+    p, x0, U0, goal, desired = _case(cfg, 61, B)
+    h = util.make_handle(cfg, p)
+    op = util.to_oracle(p)
+    o = h.bilevel_l2(dev(x0), dev(U0), dev(goal), dev(desired), maxiter=maxiter, want_hessian=True)
+    T, m, n = cfg["T"], cfg["m"], cfg["n"]
+    U = o["U"].double().cpu()
+    if maxiter == 0:
+        assert torch.equal(o["U"].cpu(), torch.from_numpy(U0))
+    worst = dict(loss=0.0, B=0.0, hess=0.0)
+    nb = min(B, 6)
+    for b in range(nb):
+        loss, Bv, A, H, grad = obl.bilevel_tail(util.tt(x0[b]), U[b], util.tt(goal[b]), util.tt(desired[b]), op)
+        rel = lambda k, a, ref: worst.__setitem__(k, max(worst[k], float((a.double().cpu() - ref).norm() / (ref.norm() + 1e-30))))
+        rel("loss", o["loss"][b:b + 1], loss[None])
+        rel("B", o["B"][b], Bv)
+        rel("hess", o["hessian"][b], A)
+        cond = float(torch.linalg.cond(A))
+        e_H = float((o["H"][b].double().cpu() - H).norm() / H.norm())
+        e_g = float((o["grad_mpc_weights"][b].double().cpu() - grad["mpc_weights"]).norm() / grad["mpc_weights"].norm())
+        print(f"b={b}: cond(A) {cond:.2e}, H rel err {e_H:.2e}, grad mpc_weights rel err {e_g:.2e}")
+        # fp32 LU: error <= ~ cond * 2^-24 * growth; headroom 20x
+        bound = max(TOL, 20 * cond * 6e-8)
+        assert e_H < bound, (e_H, bound)
+        assert e_g < 2 * bound, (e_g, bound)
+    print("worst relative errors:", worst)
+    assert worst["loss"] < TOL and worst["B"] < TOL and worst["hess"] < TOL
+
+
+def test_loss_and_grad_and_optimizer_entry_points(built_lib):
+    """BaseMPC.loss_and_grad / bilevel_optimization / cost_hessian_wrt_control / cost_vjp with the
+    reference's signatures on the l2 YAML config (C1 dims), against the autodiff oracle at the
+    kernel's own plans; dynamics / expert leaves get exactly zero (Appendix D.3)."""
+    config = utils.get_config(os.path.join(load_config.CONFIG_DIR, "l2_hyperparameters.yaml"))
+    x_size, u_size, B = 3, 1, 16
+    policy, _, _ = norm_runner.get_policy(config, x_size, u_size)
+    params = norm_runner.get_params(policy, config, x_size, u_size)
+    gen = torch.Generator().manual_seed(9)
+    hx = torch.randn(B, 2, x_size, generator=gen).cuda()
+    T = config.mpc.horizon
+    goal, init_u = policy.get_goal_states_init_actions(hx, params)
+    batch_y = (goal + 0.1 * torch.randn(B, T + 1, x_size, generator=gen).cuda()).contiguous()
+    policy.trajax_ilqr_kwargs = dict(policy.trajax_ilqr_kwargs, maxiter=4)
+    loss, grads = policy.loss_and_grad(hx, params, (batch_y,))
+    out = policy.last_bilevel
+    assert set(grads) == set(params)
+    assert float(grads["dynamics_params"]["params"]["Dense_0"]["kernel"].abs().sum()) == 0.0
+    from tests.test_gpu_api import oracle_params
+    op = oracle_params(params)
+    acc_m, acc_W, losses = 0.0, [0.0] * 3, []
+    for b in range(B):
+        l, _, _, Hh, g = obl.bilevel_tail(hx[b, -1].cpu().double(), out["U"][b].cpu().double(),
+                                          goal[b].cpu().double(), batch_y[b].cpu().double(), op)
+        losses.append(l)
+        acc_m = acc_m + g["mpc_weights"] / B
+        acc_W = [a + w / B for a, w in zip(acc_W, g["cost_W"])]
+    assert abs(float(loss) - float(torch.stack(losses).mean())) < TOL * abs(float(loss))
+    e = float((grads["mpc_weights"].cpu().double() - acc_m).norm() / acc_m.norm())
+    print("mean grad mpc_weights rel err", e)
+    assert e < 1e-3
+    for i in range(3):
+        k = grads["cost_params"]["params"][f"Dense_{i}"]["kernel"].cpu().double()
+        e = float((k - acc_W[i]).norm() / acc_W[i].norm())
+        print(f"mean grad cost Dense_{i} kernel rel err", e)
+        assert e < 1e-3
+    # bilevel_optimization, unbatched, reference argument order
+    l0, low, high, itr = opt.bilevel_optimization(policy.cost, policy.dynamics, policy.loss, hx[0, -1], init_u[0],
+                                                  params, (goal[0],), (), (batch_y[0],), policy.trajax_ilqr_kwargs)
+    assert l0.shape == () and low.shape == (T, u_size) and itr.shape == ()
+    assert torch.equal(l0, out["loss"][0]) and high["mpc_weights"].shape == (3,)
+    # cost_hessian_wrt_control / cost_vjp at a fixed U
+    cost = opt.bind(policy.cost, params, (goal[0],))
+    dyn = opt.bind(policy.dynamics, params)
+    Hs = opt.cost_hessian_wrt_control(cost, dyn, hx[0, -1], init_u[0])
+    oH = obl.cost_hessian_wrt_control(hx[0, -1].cpu().double(), init_u[0].cpu().double(), goal[0].cpu().double(), op)
+    assert Hs.shape == (T, u_size, T, u_size)
+    assert float((Hs.cpu().double() - oH).norm() / oH.norm()) < TOL
+    V = torch.randn(T * u_size, generator=gen).cuda()
+    gv = opt.cost_vjp(policy.cost, dyn, V, hx[0, -1], init_u[0], params, (goal[0],))
+    og = obl.cost_vjp(V.cpu().double(), hx[0, -1].cpu().double(), init_u[0].cpu().double(), goal[0].cpu().double(), op)
+    assert float((gv["mpc_weights"].cpu().double() - og["mpc_weights"]).norm() / og["mpc_weights"].norm()) < TOL
+    k = gv["cost_params"]["params"]["Dense_1"]["kernel"].cpu().double()
+    assert float((k - og["cost_W"][1]).norm() / og["cost_W"][1].norm()) < TOL
+
+
+def test_cost_trainer_train(built_lib):
+    """norm/cost_trainer.train with the reference's signature: losses per update, Polyak blend,
+    untouched masked leaves, inputs not mutated."""
+    config = utils.get_config(os.path.join(load_config.CONFIG_DIR, "l2_hyperparameters.yaml"))
+    x_size, u_size, D = 3, 1, 48
+    policy, _, _ = norm_runner.get_policy(config, x_size, u_size)
+    params = norm_runner.get_params(policy, config, x_size, u_size)
+    policy.trajax_ilqr_kwargs = dict(policy.trajax_ilqr_kwargs, maxiter=5)
+    policy.planner_kwargs["method"] = "ilqr"
+    gen = torch.Generator().manual_seed(11)
+    X = torch.randn(D, 2, x_size, generator=gen).cuda()
+    T = config.mpc.horizon
+    Y = (X[:, -1:, :] + 0.1 * torch.cumsum(torch.randn(D, T + 1, x_size, generator=gen).cuda(), 1)).contiguous()
+    dataset = ((X[:32], Y[:32]), (X[32:], Y[32:]))
+    copt, opt_state = norm_runner.get_optimizer(params, config.mpc.train.cost.no_grads, lr=1e-3)
+    assert sorted(copt.trained) == ["cost_params", "mpc_weights"]
+    before = utils.tree_clone(params)
+    out = cost_trainer.train((policy, copt), opt_state, params, dataset, num_updates=2, batch_size=16,
+                             polyak_factor=0.9, key=0, id=1)
+    new_params, opt_state, train_losses, test_losses, minutes = out
+    assert len(train_losses) == 2 and len(test_losses) == 2 and minutes >= 0.0
+    assert opt_state["count"] == 4
+    assert torch.equal(params["mpc_weights"], before["mpc_weights"])          # inputs not mutated
+    # masked leaves get a zero update; the Polyak blend 0.9 x + 0.1 x (cost_trainer.py:88-92 blends ALL
+    # leaves) only re-rounds them
+    assert torch.allclose(new_params["dynamics_params"]["params"]["Dense_0"]["kernel"],
+                          before["dynamics_params"]["params"]["Dense_0"]["kernel"], rtol=1e-6, atol=0)
+    d = (new_params["mpc_weights"] - before["mpc_weights"]).abs()
+    assert float(d.max()) > 0 and float(d.max()) < 4 * 1e-3 * 0.1 * 1.01     # 4 Adam steps of lr 1e-3, Polyak 0.1
+    assert all(np.isfinite(train_losses)) and all(np.isfinite(test_losses))

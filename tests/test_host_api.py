@@ -75,9 +75,13 @@ def test_arbitrary_closures_are_rejected():
         opt.ilqr_solve(lambda x, u, t, p: 0.0, lambda x, u, t, p: x, None, None, {}, (None,), (), {})
     with pytest.raises(TypeError):
         opt.objective(lambda x, u, t: 0.0, lambda x, u, t: x, None, None)
-    for fn in (opt.bilevel_optimization, opt.cost_hessian_wrt_control, opt.cost_vjp):
-        with pytest.raises(NotImplementedError, match="next scope row"):
-            fn()
+    f = lambda *a: 0.0
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        opt.bilevel_optimization(f, f, f, None, None, {}, (None,), (), (None,), {})
+    with pytest.raises(TypeError):
+        opt.cost_hessian_wrt_control(f, f, None, None)
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        opt.cost_vjp(f, f, None, None, None, {}, (None,))
 
 
 def test_model_factories_and_mask_labels():
