@@ -61,6 +61,8 @@ _SIGS = {
                             _f, _f, _f, _f, _f, C.c_void_p]),
     "gmpc_bilevel_l2": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, _f, C.POINTER(IlqrOptions)] + [_f] * 12
                         + [C.c_void_p]),
+    "gmpc_bilevel_tail": (C.c_int, [C.c_void_p, C.c_int64] + [_f] * 9 + [C.c_void_p]),
+    "gmpc_critic_input_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, _f, C.c_void_p]),
     "gmpc_ilqr_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.c_void_p]),
     "gmpc_critic_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_void_p]),
@@ -319,6 +321,32 @@ class Handle:
             _ptr(o["H"]), _ptr(o["dxT"]), _ptr(o["grad_mpc_weights"]),
             _ptr(V, device=dev, name="V"), _stream(dev)))
         return o
+
+    def bilevel_tail(self, x0, U, goal, dLdX, want_hessian=False):
+        """gmpc_bilevel_tail: the bilevel tail at U for a loss given by its state gradient dLdX."""
+        dev = self.device
+        B, T, n, m = x0.shape[0], self.T, self.n, self.m
+        f = dict(device=dev, dtype=torch.float32)
+        o = dict(B=torch.empty(B, T, m, **f),
+                 hessian=torch.empty(B, T * m, T * m, **f) if want_hessian else None,
+                 H=torch.empty(B, T, m, **f), dxT=torch.empty(B, n, **f),
+                 grad_mpc_weights=torch.empty(B, 3, **f))
+        _check(self.lib.gmpc_bilevel_tail(
+            self._h, B, _ptr(x0, device=dev, name="x0"), _ptr(U, device=dev, name="U"),
+            _ptr(goal, device=dev, name="goal"), _ptr(dLdX, device=dev, name="dLdX"), _ptr(o["B"]),
+            _ptr(o["hessian"]), _ptr(o["H"]), _ptr(o["dxT"]), _ptr(o["grad_mpc_weights"]), _stream(dev)))
+        return o
+
+    def critic_input_grad(self, xseq, params_flat):
+        """(logit [Bc], d logit / d xseq [Bc,T1,n])."""
+        Bc, T1, n = xseq.shape
+        logit = torch.empty(Bc, device=self.device, dtype=torch.float32)
+        dx = torch.empty(Bc, T1, n, device=self.device, dtype=torch.float32)
+        _check(self.lib.gmpc_critic_input_grad(
+            self._h, Bc, T1, _ptr(xseq, device=self.device, name="xseq"),
+            _ptr(params_flat, device=self.device, name="params_flat"), _ptr(logit), _ptr(dx),
+            _stream(self.device)))
+        return logit, dx
 
     def ilqr_stats(self):
         """(tile-level outer iterations, rollouts) of the ilqr calls since the last query."""

@@ -31,10 +31,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 // xseq [*, T1, n]; sample s of the minibatch is row perm[s] (or s when perm == nullptr).
 // losses[s] = unscaled per-sample loss; logits[s] (nullable) = raw score.
 // When do_bwd: partial[blockIdx.x][P] accumulates inv_count * d loss_s / d params.
+// When dx_out != nullptr (input-gradient mode, used by the generator loss gan/js_policy.py:60-68):
+// the backward pass is seeded with d score = 1, no weight gradients are accumulated, and
+// dx_out[s][t][i] = d score_s / d xseq[s][t][i].
 __global__ void critic_kernel(const CriticDims D, const float* __restrict__ xseq,
                               const float* __restrict__ label, const int* __restrict__ perm,
                               const float* __restrict__ prm, float inv_count, long long Bc,
-                              float* losses, float* logits, float* partial, int do_bwd) {
+                              float* losses, float* logits, float* partial, int do_bwd,
+                              float* dx_out = nullptr) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int n = D.n, F = D.F, G = 4 * D.F, T1 = D.T1;
@@ -57,7 +61,10 @@ __global__ void critic_kernel(const CriticDims D, const float* __restrict__ xseq
   // every parameter receives a contribution from every sample, so the CTA's first sample stores
   // and later ones accumulate: no zero-fill pass and no read of the partial buffer for it
   bool first = true;
-  auto acc_part = [&](long long idx, float v) { part[idx] = first ? v : part[idx] + v; };
+  const bool xgrad = dx_out != nullptr;
+  auto acc_part = [&](long long idx, float v) {
+    if (!xgrad) part[idx] = first ? v : part[idx] + v;
+  };
 
   for (long long s = blockIdx.x; s < Bc; s += gridDim.x, first = false) {
     const long long src = perm ? (long long)perm[s] : s;
@@ -116,7 +123,7 @@ __global__ void critic_kernel(const CriticDims D, const float* __restrict__ xseq
     __syncthreads();
     if (!do_bwd) continue;  // (first is irrelevant without a backward pass)
     // ---------------------------------------------------------------- head backward
-    const float ds = scal[0];
+    const float ds = xgrad ? 1.f : scal[0];
     {
       const float* a = hact + (D.L - 1) * W;
       if (tid < D.dlast) {
@@ -163,6 +170,15 @@ __global__ void critic_kernel(const CriticDims D, const float* __restrict__ xseq
         dc[tid] = dcj * gf;
       }
       __syncthreads();
+      if (xgrad) {  // d score / d x_t = Wi dz_t
+        const float* dz = gates + t * G;
+        for (int i = warp; i < n; i += nwarps) {
+          float acc = 0.f;
+          for (int j = lane; j < G; j += 32) acc = fmaf(__ldg(Wi + (size_t)i * G + j), dz[j], acc);
+          acc = warp_sum(acc);
+          if (lane == 0) dx_out[((size_t)s * T1 + t) * n + i] = acc;
+        }
+      }
       if (t > 0) {
         const float* dz = gates + t * G;
         for (int i = warp; i < F; i += nwarps) {
@@ -175,7 +191,7 @@ __global__ void critic_kernel(const CriticDims D, const float* __restrict__ xseq
       __syncthreads();
     }
     // ---------------------------------------------------------------- weight gradients
-    if (tid < G) {
+    if (tid < G && !xgrad) {
       float bsum = 0.f;
       for (int t = 0; t < T1; ++t) bsum += gates[t * G + tid];
       acc_part(D.obh + tid, bsum);

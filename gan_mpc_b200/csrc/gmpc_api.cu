@@ -464,9 +464,10 @@ extern "C" int gmpc_plan(gmpc_handle* h, int64_t B, int32_t K, const float* x0, 
 
 // ilqr_solve (policy/optimizers.py:10-21): the whole trajax iLQR loop as one kernel (csrc/ilqr.cuh).
 struct BilevelArgs {
-  const float* desired;
+  const float* desired;   // L2 mode: desired states; generic mode: d loss / d X (is_dLdX)
   float *loss, *Bvec, *hess, *H, *dxT, *gw;
   const float* V;
+  int is_dLdX;
 };
 
 static int ilqr_launch(gmpc_handle* h, int64_t B, const float* x0, const float* U0,
@@ -529,6 +530,7 @@ static int ilqr_launch(gmpc_handle* h, int64_t B, const float* x0, const float* 
   if (bl) {
     Q.desired = bl->desired; Q.bl_loss = bl->loss; Q.bl_B = bl->Bvec; Q.bl_hess = bl->hess;
     Q.bl_H = bl->H; Q.bl_dxT = bl->dxT; Q.bl_gw = bl->gw; Q.bl_V = bl->V;
+    Q.bl_generic = bl->is_dLdX;
   }
   const int grid = std::min(P.ntiles, h->num_sms);
   if (h->maxt == 1)
@@ -559,9 +561,33 @@ extern "C" int gmpc_bilevel_l2(gmpc_handle* h, int64_t B, const float* x0, const
   if (!desired || !loss || !H || !dxT || !grad_mpc_weights)
     return fail(GMPC_E_ARG, "gmpc_bilevel_l2: null argument");
   if (V && hessian) return fail(GMPC_E_ARG, "gmpc_bilevel_l2: a given direction V skips the Hessian");
-  BilevelArgs bl{desired, loss, loss_grad_U, hessian, H, dxT, grad_mpc_weights, V};
+  BilevelArgs bl{desired, loss, loss_grad_U, hessian, H, dxT, grad_mpc_weights, V, 0};
   return ilqr_launch(h, B, x0, U0, goal, opt, X, U, obj, low_level_grad, nullptr, iteration, nullptr,
                      nullptr, &bl, stream);
+}
+
+// The same tail for ANY loss of the planned states, given its gradient dL/dX at the plan (e.g. the
+// generator loss of gan/js_policy.py:60-68 through gmpc_critic_input_grad): evaluated at U itself.
+extern "C" int gmpc_bilevel_tail(gmpc_handle* h, int64_t B, const float* x0, const float* U,
+                                 const float* goal, const float* dLdX, float* loss_grad_U,
+                                 float* hessian, float* H, float* dxT, float* grad_mpc_weights,
+                                 void* stream) {
+  if (!dLdX || !H || !dxT || !grad_mpc_weights) return fail(GMPC_E_ARG, "gmpc_bilevel_tail: null argument");
+  int rc = check_ready(h, "gmpc_bilevel_tail", B);
+  if (rc) return rc;
+  if (B == 0) return GMPC_OK;
+  const gmpc_config& c = h->cfg;
+  // rollout / objective / plan outputs of the embedded iLQR (0 iterations) are not wanted: scratch
+  const size_t fl = (size_t)B * ((size_t)(c.T + 1) * c.n + (size_t)c.T * c.m + 1);
+  rc = grow(&h->d_scratch, &h->scratch_bytes, fl * sizeof(float));
+  if (rc) return rc;
+  float* sX = (float*)h->d_scratch;
+  float* sU = sX + (size_t)B * (c.T + 1) * c.n;
+  float* sJ = sU + (size_t)B * c.T * c.m;
+  const gmpc_ilqr_options opt{0, 0.f, 1.f, 0.f};
+  BilevelArgs bl{dLdX, nullptr, loss_grad_U, hessian, H, dxT, grad_mpc_weights, nullptr, 1};
+  return ilqr_launch(h, B, x0, U, goal, &opt, sX, sU, sJ, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     &bl, stream);
 }
 
 extern "C" int gmpc_ilqr_stats(gmpc_handle* h, int64_t* outer_iterations, int64_t* rollouts, void* stream) {
@@ -670,7 +696,7 @@ static size_t critic_smem(const CriticDims& d, int T1) {
 static int critic_launch(gmpc_handle* h, const char* who, int64_t Bc, int32_t T1,
                          const float* xseq, const float* label, const int32_t* perm,
                          const float* params, float inv_count, float* loss, float* grad,
-                         float* logits, cudaStream_t st) {
+                         float* logits, cudaStream_t st, float* dx_out = nullptr) {
   if (!h) return fail(GMPC_E_ARG, std::string(who) + ": null handle");
   if (h->cfg.critic_features <= 0) return fail(GMPC_E_STATE, std::string(who) + ": handle was created without a critic");
   if (Bc < 0 || T1 < 1) return fail(GMPC_E_ARG, std::string(who) + ": need Bc >= 0, T1 >= 1");
@@ -694,7 +720,8 @@ static int critic_launch(gmpc_handle* h, const char* who, int64_t Bc, int32_t T1
   const float* lab = label ? label : h->d_losses + h->losses_cap;
   if (!label) CU_CHECK(cudaMemsetAsync(h->d_losses + h->losses_cap, 0, sizeof(float) * (size_t)Bc, st));
   critic_kernel<<<grid, threads, smem, st>>>(d, xseq, lab, perm, params, inv_count, Bc,
-                                             h->d_losses, logits, h->d_partial, grad ? 1 : 0);
+                                             h->d_losses, logits, h->d_partial, (grad || dx_out) ? 1 : 0,
+                                             dx_out);
   ++h->launches;
   if (loss || grad) {
     const int rb = grad ? (int)((d.P + 255) / 256) : 1;
@@ -711,6 +738,14 @@ extern "C" int gmpc_critic_forward(gmpc_handle* h, int64_t Bc, int32_t T1, const
   if (!logit) return fail(GMPC_E_ARG, "gmpc_critic_forward: null argument");
   return critic_launch(h, "gmpc_critic_forward", Bc, T1, xseq, nullptr, nullptr, params_flat, 0.f,
                        nullptr, nullptr, logit, (cudaStream_t)stream);
+}
+
+extern "C" int gmpc_critic_input_grad(gmpc_handle* h, int64_t Bc, int32_t T1, const float* xseq,
+                                      const float* params_flat, float* logit, float* dxseq,
+                                      void* stream) {
+  if (!logit || !dxseq) return fail(GMPC_E_ARG, "gmpc_critic_input_grad: null argument");
+  return critic_launch(h, "gmpc_critic_input_grad", Bc, T1, xseq, nullptr, nullptr, params_flat, 0.f,
+                       nullptr, nullptr, logit, (cudaStream_t)stream, dxseq);
 }
 
 extern "C" int gmpc_critic_loss_grad(gmpc_handle* h, int64_t Bc, int32_t T1, const float* xseq,

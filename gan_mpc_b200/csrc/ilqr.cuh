@@ -48,6 +48,7 @@ struct IlqrParams {
   float* bl_H;          // [B,T,m]    solve(hessian, B)
   float* bl_dxT;        // [B,n]      d x_T / dU . H  (tangent of the terminal state along H)
   float* bl_gw;         // [B,3]      d (H . grad_U J) / d mpc_weights (raw, pre-sigmoid)
+  int bl_generic;       // `desired` holds d loss / d X [B,T+1,n] of an arbitrary loss (bl_loss unused)
   const float* bl_V;    // [B,T,m]    nullable: cost_vjp's direction V given by the caller -- used instead
                         //            of H (no Hessian, no solve; bl_H returns V)
 };
@@ -655,7 +656,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       for (int e = tid; e < n * TM * RT; e += NTHREADS) wsS[e] = 0.f;
       __syncthreads();
       // ---- loss and B = d loss / dU (adjoint scan with q_t = 2/(T+1) (x_t - desired_t), r_t = 0)
-      if (tid < RT) {
+      const bool generic = Q.bl_generic != 0;
+      if (tid < RT && !generic) {
         float s = 0.f;
         for (int e = 0; e < (T + 1) * n; ++e) {
           const float d = wsX[e * RT + r] - wsD[e * RT + r];
@@ -663,8 +665,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
         }
         if (q0 + r < P.NQ) Q.bl_loss[q0 + r] = s / (float)(T + 1);
       }
-      for (int e = tid; e < n * RT; e += NTHREADS)
-        p_s[e] = cl2 * (wsX[(size_t)T * n * RT + e] - wsD[(size_t)T * n * RT + e]);
+      if (!generic) {  // q_t = d loss / d x_t of the L2 loss, in place of the desired states
+        __syncthreads();
+        for (int e = tid; e < (T + 1) * n * RT; e += NTHREADS) wsD[e] = cl2 * (wsX[e] - wsD[e]);
+        __syncthreads();
+      }
+      for (int e = tid; e < n * RT; e += NTHREADS) p_s[e] = wsD[(size_t)T * n * RT + e];
       __syncthreads();
 #pragma unroll 1
       for (int t = T - 1; t >= 0; --t) {
@@ -672,7 +678,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
           const int row = e >> 5;
           if (row < n) {
             const int i = row;
-            float s = cl2 * (wsX[(t * n + i) * RT + r] - wsD[(t * n + i) * RT + r]);
+            float s = wsD[(t * n + i) * RT + r];
             const float* Ar = wsA + (size_t)(t * n * n + i) * RT + r;
             for (int k = 0; k < n; ++k) s = fmaf(Ar[(size_t)k * n * RT], p_s[k * RT + r], s);
             pn_s[i * RT + r] = s;

@@ -74,6 +74,14 @@ class JS_MPC(base.BaseMPC):
         n = actual_xseq.shape[-1]
         return -self.critic_logits(xcseq[..., :n], params)
 
+    def _loss_state_grad(self, X, params, desired):
+        """generator loss per trajectory and its gradient w.r.t. the planned states (the seed of
+        loss_grad_wrt_control, policy/optimizers.py:78-83): loss = -score, dL/dX = -d score/dX."""
+        n = desired.shape[-1]
+        xs = X[..., :n].contiguous()
+        score, dx = self.critic_handle(n).critic_input_grad(xs, self.critic_flat(params))
+        return -score, -dx
+
     def generator_loss_and_grad(self, batch_xseq, params, batch_loss_args):
         return self.loss_and_grad(batch_xseq, params, batch_loss_args)
 

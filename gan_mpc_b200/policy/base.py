@@ -28,11 +28,10 @@ class BaseMPC(eval.EvalMPC):
         raise NotImplementedError
 
     def _bilevel(self, x0, init_U, params, goal, desired, ilqr_kwargs=None, **kw):
-        """gmpc_bilevel_l2 on normalised inputs; returns (batched?, result dict)."""
-        if not self._loss_is_l2:
-            raise NotImplementedError(
-                "the bilevel gradient is fused for loss = L2MPC.loss; JS_MPC.generator_loss needs the "
-                "critic's input gradient inside the same kernel (not built)")
+        """The bilevel solve on normalised inputs; returns (batched?, result dict).
+        L2MPC: one launch (gmpc_bilevel_l2).  Other losses (JS_MPC.generator_loss) supply
+        `_loss_state_grad(X, params, desired) -> (loss [B], dL/dX [B,T+1,n])` and run as
+        gmpc_ilqr -> loss gradient -> gmpc_bilevel_tail at the planned U."""
         batched, x0b, Ub, gb = self._prep(x0, init_U, goal)
         if Ub.shape[1] != 1:
             raise ValueError("bilevel_optimization plans one action sequence per state")
@@ -40,7 +39,17 @@ class BaseMPC(eval.EvalMPC):
         h = self._handle(x0b.shape[1], Ub.shape[3])
         self._stage(h, params)
         ik = dict(self.trajax_ilqr_kwargs if ilqr_kwargs is None else ilqr_kwargs)
-        return batched, h.bilevel_l2(x0b, Ub[:, 0].contiguous(), gb, db, **ik, **kw)
+        if self._loss_is_l2:
+            return batched, h.bilevel_l2(x0b, Ub[:, 0].contiguous(), gb, db, **ik, **kw)
+        if not hasattr(self, "_loss_state_grad"):
+            raise NotImplementedError("bilevel gradient: this policy's loss has no state-gradient kernel")
+        if kw:
+            raise NotImplementedError("cost_hessian_wrt_control / cost_vjp go through an L2MPC policy")
+        X, U, obj, low, _, _, it = h.ilqr(x0b, Ub[:, 0].contiguous(), gb, **ik)
+        loss, dLdX = self._loss_state_grad(X, params, db)
+        out = h.bilevel_tail(x0b, U, gb, dLdX)
+        out.update(X=X, U=U, obj=obj, low_level_grad=low, iteration=it, loss=loss)
+        return batched, out
 
     def loss_and_grad(self, history_X, params, batch_loss_args):
         """policy/base.py:87-128 -- vmap of bilevel_optimization over the batch, mean loss and

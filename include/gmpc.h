@@ -175,6 +175,21 @@ int gmpc_bilevel_l2(gmpc_handle* h, int64_t B, const float* x0, const float* U0,
                     float* loss_grad_U, float* hessian, float* H, float* dxT,
                     float* grad_mpc_weights, const float* V, void* stream);
 
+/* The same tail for an arbitrary loss of the planned states, given dL/dX [B,T+1,n] at the plan U
+ * (policy/optimizers.py:59-71 with loss = JS_MPC.generator_loss, gan/js_policy.py:60-74: dL/dX comes
+ * from gmpc_critic_input_grad): loss_grad_U (nullable) = back-propagation of dL/dX through the
+ * rollout, hessian (nullable), H, dxT, grad_mpc_weights as in gmpc_bilevel_l2. */
+int gmpc_bilevel_tail(gmpc_handle* h, int64_t B, const float* x0, const float* U, const float* goal,
+                      const float* dLdX, float* loss_grad_U, float* hessian, float* H, float* dxT,
+                      float* grad_mpc_weights, void* stream);
+
+/* d score / d xseq of CriticModel.predict (critic/critic_model.py:15-16): BPTT through the LSTM to
+ * its inputs.  xseq[Bc,T1,n] -> logit[Bc], dxseq[Bc,T1,n].  The generator loss of
+ * gan/js_policy.py:60-68, mean(-log p + log(1 - p)) with p = sigmoid(score), equals -score, so its
+ * state gradient is -dxseq. */
+int gmpc_critic_input_grad(gmpc_handle* h, int64_t Bc, int32_t T1, const float* xseq,
+                           const float* params_flat, float* logit, float* dxseq, void* stream);
+
 /* Work counters of the gmpc_ilqr calls since the last query (synchronises `stream`): tile-level
  * outer iterations and rollouts (1 + line-search trials) summed over the 32-trajectory tiles. */
 int gmpc_ilqr_stats(gmpc_handle* h, int64_t* outer_iterations, int64_t* rollouts, void* stream);

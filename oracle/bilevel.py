@@ -25,11 +25,17 @@ def _objective_of(U, x0, goal, params):
     return pl.objective(x0[None], U[None], goal[None], params)[1][0]
 
 
-def loss_grad_wrt_control(x0, U, desired, params):
-    """policy/optimizers.py:78-83 with loss = L2MPC.loss (norm/l2_policy.py:12-18)."""
+def _loss_fn(desired, loss_fn):
+    """loss(X) -> scalar: L2MPC.loss against `desired` (norm/l2_policy.py:12-18) unless a callable
+    (e.g. the generator loss of gan/js_policy.py:60-68 on the oracle critic) is given."""
+    return loss_fn if loss_fn is not None else (lambda X: pl.l2_loss(X, desired))
+
+
+def loss_grad_wrt_control(x0, U, desired, params, loss_fn=None):
+    """policy/optimizers.py:78-83."""
     U = U.detach().clone().requires_grad_(True)
     X = pl.rollout(x0[None], U[None], params)[0]
-    (g,) = torch.autograd.grad(pl.l2_loss(X, desired), U)
+    (g,) = torch.autograd.grad(_loss_fn(desired, loss_fn)(X), U)
     return g
 
 
@@ -54,16 +60,16 @@ def cost_vjp(V, x0, U, goal, params):
     return dict(cost_W=gs[:L], cost_b=gs[L:2 * L], mpc_weights=gs[2 * L])
 
 
-def bilevel_tail(x0, U, goal, desired, params):
+def bilevel_tail(x0, U, goal, desired, params, loss_fn=None):
     """policy/optimizers.py:59-73 at a given planned U (unbatched):
     returns (high_level_loss, B [T,m], A [Tm,Tm], H [T,m], high_level_grad dict)."""
     T, m = U.shape
     X = pl.rollout(x0[None], U[None], params)[0]
-    Bv = loss_grad_wrt_control(x0, U, desired, params).reshape(T * m)
+    Bv = loss_grad_wrt_control(x0, U, desired, params, loss_fn).reshape(T * m)
     A = cost_hessian_wrt_control(x0, U, goal, params).reshape(T * m, T * m)
     H = torch.linalg.solve(A, Bv)
     grad = cost_vjp(H, x0, U, goal, params)
-    return pl.l2_loss(X, desired), Bv.reshape(T, m), A, H.reshape(T, m), grad
+    return _loss_fn(desired, loss_fn)(X), Bv.reshape(T, m), A, H.reshape(T, m), grad
 
 
 def bilevel_optimization(x0, init_U, goal, desired, params, **ilqr_kwargs):

@@ -154,3 +154,52 @@ def test_cost_trainer_train(built_lib):
     d = (new_params["mpc_weights"] - before["mpc_weights"]).abs()
     assert float(d.max()) > 0 and float(d.max()) < 4 * 1e-3 * 0.1 * 1.01     # 4 Adam steps of lr 1e-3, Polyak 0.1
     assert all(np.isfinite(train_losses)) and all(np.isfinite(test_losses))
+
+
+def test_generator_loss_bilevel_through_the_critic(built_lib):
+    """JS_MPC.generator_loss_and_grad (gan/js_policy.py:60-74) = loss_and_grad with the generator
+    loss: gmpc_ilqr -> gmpc_critic_input_grad (BPTT of the LSTM critic to its inputs) ->
+    gmpc_bilevel_tail, against the autodiff oracle with loss = -critic_logit(X)."""
+    from gan_mpc_b200.gan import runner as gan_runner
+    from oracle import critic as ocritic
+    from tests.test_gpu_api import oracle_params
+    config = utils.get_config(os.path.join(load_config.CONFIG_DIR, "gan_hyperparameters.yaml"))
+    x_size, u_size, B = 3, 1, 12
+    policy, _, _ = gan_runner.get_policy(config, x_size, u_size)
+    params = gan_runner.get_params(policy, config, x_size, u_size)
+    cm = policy.critic_model.model
+    F, L, H = cm.lstm_features, cm.num_layers, cm.num_hidden_units
+    T = config.mpc.horizon
+    gen = torch.Generator().manual_seed(21)
+    hx = torch.randn(B, 2, x_size, generator=gen).cuda()
+    flat = policy.critic_flat(params)
+    # the critic's input gradient on its own
+    xs = torch.randn(B, T + 1, x_size, generator=gen).cuda()
+    score, dx = policy.critic_handle(x_size).critic_input_grad(xs, flat)
+    xo = xs.cpu().double().requires_grad_(True)
+    so = ocritic.critic_logit(xo, flat.cpu().double(), x_size, F, L, H)
+    (dxo,) = torch.autograd.grad(so.sum(), xo)
+    assert util.rel_rows(score[:, None], so.detach()[:, None]) < TOL
+    assert util.rel_rows(dx, dxo) < TOL
+    # the bilevel gradient with the generator loss
+    policy.trajax_ilqr_kwargs = dict(policy.trajax_ilqr_kwargs, maxiter=3)
+    actual = torch.zeros(B, T + 1, x_size).cuda()   # generator_loss only reads its last-axis size
+    loss, grads = policy.generator_loss_and_grad(hx, params, (actual,))
+    goal, init_u = policy.get_goal_states_init_actions(hx, params)
+    _, out = policy._bilevel(hx[:, -1], init_u, params, goal, actual)
+    op = oracle_params(params)
+    fo = flat.cpu().double()
+    loss_fn = lambda X: -ocritic.critic_logit(X, fo, x_size, F, L, H)
+    acc_m, losses = 0.0, []
+    for b in range(B):
+        l, Bv, A, Hh, g = obl.bilevel_tail(hx[b, -1].cpu().double(), out["U"][b].cpu().double(),
+                                           goal[b].cpu().double(), None, op, loss_fn)
+        losses.append(l)
+        acc_m = acc_m + g["mpc_weights"] / B
+        assert float((out["B"][b].cpu().double() - Bv).norm() / Bv.norm()) < TOL
+        assert float((out["H"][b].cpu().double() - Hh).norm() / Hh.norm()) < max(TOL, 20 * float(torch.linalg.cond(A)) * 6e-8)
+    assert abs(float(loss) - float(torch.stack(losses).mean())) < TOL * max(1.0, abs(float(loss)))
+    e = float((grads["mpc_weights"].cpu().double() - acc_m).norm() / acc_m.norm())
+    print("generator-loss mean grad mpc_weights rel err", e)
+    assert e < 1e-3
+    assert float(cm.flatten(grads["critic_params"]).abs().sum()) == 0.0   # cost side only (Appendix D.3)
