@@ -78,3 +78,73 @@ def tree_map2(fn, a, b):
     if isinstance(a, dict):
         return {k: tree_map2(fn, a[k], b[k]) for k in a}
     return fn(a, b) if isinstance(a, torch.Tensor) else a
+
+
+# ------------------------------------------------------------------------------------------------
+# On-disk format either side of the path (reference utils.py:117-156): <dir>/<run id>/config.json +
+# params.npy, the params pytree pickled by np.save(..., allow_pickle=True).  Leaves are written as
+# numpy arrays (a pickle of jax.Arrays needs jax to load; numpy leaves load everywhere, and
+# jax.numpy accepts them unchanged), in the flax layout the kernels consume (Dense_i/{kernel[in,out],
+# bias}), so weights trained by the reference flow in without conversion.
+def check_or_create_dir(path):
+    import os
+    if not os.path.exists(path):
+        os.makedirs(path, exist_ok=True)
+
+
+def save_json(data, dir_path, basename):
+    import json
+    import os
+    check_or_create_dir(dir_path)
+    with open(os.path.join(dir_path, basename), "w") as fp:
+        json.dump(data, fp, indent=4, sort_keys=True)
+
+
+def load_json(path):
+    import json
+    with open(path, "r") as fp:
+        return json.load(fp)
+
+
+def _to_numpy_tree(tree):
+    import numpy as np
+    import torch
+    if isinstance(tree, dict):
+        return {k: _to_numpy_tree(v) for k, v in tree.items()}
+    if isinstance(tree, torch.Tensor):
+        return tree.detach().cpu().numpy()
+    return np.asarray(tree) if hasattr(tree, "__array__") else tree
+
+
+def _to_torch_tree(tree, device):
+    import numpy as np
+    import torch
+    if hasattr(tree, "items"):  # dict / FrozenDict-like
+        return {k: _to_torch_tree(v, device) for k, v in tree.items()}
+    if hasattr(tree, "__array__"):
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(tree, dtype=np.float32))).to(device)
+    return tree
+
+
+def save_all_args(dir_path, params, model_config, *other_json_args):
+    """utils.py:135-148: next free integer run id under dir_path; config.json, params.npy and the
+    extra (json_data, name) pairs.  Returns the run directory."""
+    import os
+    import numpy as np
+    check_or_create_dir(dir_path)
+    dir_list = sorted((d for d in os.listdir(dir_path) if d.isdigit()), key=lambda x: -int(x))
+    key = "0" if not dir_list else f"{int(dir_list[0]) + 1}"
+    full_path = os.path.join(dir_path, key)
+    save_json(model_config, full_path, "config.json")
+    np.save(os.path.join(full_path, "params.npy"), _to_numpy_tree(params), allow_pickle=True)
+    for json_data, name in other_json_args:
+        save_json(json_data, full_path, name)
+    return full_path
+
+
+def load_params(params_path, from_np=True, device="cuda"):
+    """utils.py:151-156: the pickled pytree back as torch tensors on `device`."""
+    import numpy as np
+    if not from_np:
+        raise NotImplementedError("params must be saved using numpy.")
+    return _to_torch_tree(np.load(params_path, allow_pickle=True).item(), device)

@@ -115,3 +115,27 @@ def test_shard_range_partitions_the_batch(B, world):
     sizes = [hi - lo for lo, hi in edges]
     assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_params_npy_round_trip(tmp_path):
+    """utils.save_all_args / load_params (reference utils.py:135-156): run-id directories,
+    config.json, params.npy as a pickled pytree with the flax Dense_i/{kernel,bias} layout."""
+    import numpy as np
+    import torch
+    c = utils.get_config(os.path.join(load_config.CONFIG_DIR, "l2_hyperparameters.yaml"))
+    dyn, _ = utils.get_dynamics_model(c, 3)
+    params = {"mpc_weights": torch.tensor([-2.0, 3.0, -3.0]), "dynamics_params": dyn.init(0, 1, device="cpu"),
+              "expert_params": {}}
+    d0 = utils.save_all_args(str(tmp_path / "runs"), params, c.mpc.model.to_dict(), ({"loss": [1.0, 0.5]}, "loss.json"))
+    d1 = utils.save_all_args(str(tmp_path / "runs"), params, c.mpc.model.to_dict())
+    assert os.path.basename(d0) == "0" and os.path.basename(d1) == "1"
+    assert utils.load_json(os.path.join(d0, "loss.json")) == {"loss": [1.0, 0.5]}
+    assert utils.load_json(os.path.join(d0, "config.json"))["dynamics"]["mlp"]["num_hidden_units"] == 200
+    raw = np.load(os.path.join(d0, "params.npy"), allow_pickle=True).item()
+    assert isinstance(raw["dynamics_params"]["params"]["Dense_0"]["kernel"], np.ndarray)
+    back = utils.load_params(os.path.join(d0, "params.npy"), device="cpu")
+    assert torch.equal(back["mpc_weights"], params["mpc_weights"]) and back["expert_params"] == {}
+    for i in range(4):
+        for k in ("kernel", "bias"):
+            assert torch.equal(back["dynamics_params"]["params"][f"Dense_{i}"][k],
+                               params["dynamics_params"]["params"][f"Dense_{i}"][k])

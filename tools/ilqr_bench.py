@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--maxiter", type=int, default=100)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cpu-states", type=int, default=16)
+    ap.add_argument("--bilevel", action="store_true",
+                    help="time gmpc_bilevel_l2 (iLQR + the bilevel tail, policy/optimizers.py:34-75) instead")
     a = ap.parse_args()
     cfg = dict(synthetic.CONFIGS[a.config], K=1)
     if a.B:
@@ -37,13 +39,18 @@ def main():
     h.set_weights([t(w) for w in p["dyn_W"]], [t(b) for b in p["dyn_b"]], [t(w) for w in p["cost_W"]],
                   [t(b) for b in p["cost_b"]], t(p["mpc_weights"]))
     dx0, dU0, dgoal = t(x0), t(U0[:, 0]), t(goal)
+    ddes = (dgoal + 0.05 * torch.randn(dgoal.shape, device=dev, generator=torch.Generator(dev).manual_seed(0))).contiguous()
     J0, *_ = h.objective_grad(dx0, dU0, dgoal, want_grad=False, want_X=False)
     times = []
     for rep in range(a.reps + 1):
         h.ilqr_stats()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        X, U, obj, g, lam, _, it = h.ilqr(dx0, dU0, dgoal, maxiter=a.maxiter)
+        if a.bilevel:
+            o = h.bilevel_l2(dx0, dU0, dgoal, ddes, maxiter=a.maxiter)
+            obj, it = o["obj"], o["iteration"]
+        else:
+            X, U, obj, g, lam, _, it = h.ilqr(dx0, dU0, dgoal, maxiter=a.maxiter)
         e1.record()
         torch.cuda.synchronize()
         outer, rolls = h.ilqr_stats()
@@ -51,13 +58,14 @@ def main():
             times.append(e0.elapsed_time(e1))
     ms = float(np.median(times))
     B = cfg["B"]
-    out = dict(metric="planned states/sec (trajax-iLQR mode, gmpc_ilqr)", value=B / ms * 1e3, unit="states/s",
+    out = dict(metric=("bilevel gradients/sec (gmpc_bilevel_l2: iLQR + Hessian + solve + tangent)" if a.bilevel
+                       else "planned states/sec (trajax-iLQR mode, gmpc_ilqr)"), value=B / ms * 1e3, unit="states/s",
                ms=ms, config=dict(workload=f"{a.config} dims: B={B}, n={cfg['n']}, m={cfg['m']}, T={cfg['T']}, "
                                   f"maxiter={a.maxiter}, grad_norm_threshold=1e-4, alpha_min=5e-5"),
                iterations=dict(median=float(it.float().median()), max=int(it.max()), min=int(it.min())),
                tile_outer_iterations=outer, tile_rollouts=rolls,
                obj_over_initial_median=float((obj / J0).median()))
-    if a.cpu_states > 0:
+    if a.cpu_states > 0 and not a.bilevel:
         from oracle import ilqr as oilqr
         nb = min(a.cpu_states, B)
         torch.set_num_threads(len(os.sched_getaffinity(0)))
