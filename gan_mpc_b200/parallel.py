@@ -64,3 +64,14 @@ def plan_sharded(handle, x0, U0, goal, **plan_kwargs):
     f = lambda t: t[lo:hi].to(dev).contiguous()
     U, X, J, idx, _ = handle.plan(f(x0), f(U0), f(goal), **plan_kwargs)
     return gather_best_plans(U, J, idx, B)
+
+
+def ilqr_sharded(handle, x0, U0, goal, **ilqr_kwargs):
+    """trajax-iLQR planning (gmpc_ilqr) of this rank's block of the global batch, plans gathered on
+    every rank: full-batch (U [B,T,m], obj [B], iteration [B])."""
+    B = x0.shape[0]
+    lo, hi = shard_range(B)
+    dev = handle.device
+    f = lambda t: t[lo:hi].to(dev).contiguous()
+    _, U, obj, _, _, _, it = handle.ilqr(f(x0), f(U0), f(goal), **ilqr_kwargs)
+    return gather_rows(U, B), gather_rows(obj, B), gather_rows(it, B)

@@ -54,10 +54,23 @@ class BaseMPC(eval.EvalMPC):
     def loss_and_grad(self, history_X, params, batch_loss_args):
         """policy/base.py:87-128 -- vmap of bilevel_optimization over the batch, mean loss and
         leaf-wise mean of the per-sample gradient pytrees (here reduced without materialising them).
-        history_X [B,h+1,n], batch_loss_args = (batch_y [B,T+1,n],)."""
+        history_X [B,h+1,n], batch_loss_args = (batch_y [B,T+1,n],).
+        With torch.distributed initialised the batch is sharded over the ranks (contiguous blocks,
+        parallel.shard_range) and the sums are all-reduced once: every rank returns the global mean."""
+        from gan_mpc_b200 import parallel
         from gan_mpc_b200.policy import bilevel
         (batch_y,) = batch_loss_args
-        goal, init_u = self.get_goal_states_init_actions(history_X, params)
-        _, out = self._bilevel(history_X[..., -1, :], init_u, params, goal, batch_y)
-        self.last_bilevel = out
-        return out["loss"].mean(), bilevel.high_level_grad_tree(params, out, reduce_mean=True)
+        B = history_X.shape[0]
+        rank, world = parallel.rank_world()
+        lo, hi = parallel.shard_range(B, rank, world)
+        if hi > lo:
+            hx, by = history_X[lo:hi], batch_y[lo:hi]
+            goal, init_u = self.get_goal_states_init_actions(hx, params)
+            _, out = self._bilevel(hx[..., -1, :], init_u, params, goal, by)
+            self.last_bilevel = out
+            loss_sum = out["loss"].sum()
+            grads = bilevel.high_level_grad_tree(params, out, reduce_mean="sum")
+        else:  # more ranks than samples: this rank contributes zeros
+            loss_sum = torch.zeros((), device=self.device)
+            grads = bilevel.zeros_like_tree(params)
+        return bilevel.allreduce_mean_tree_(loss_sum, grads, B)

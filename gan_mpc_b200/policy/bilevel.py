@@ -46,15 +46,40 @@ def zeros_like_tree(tree, lead=()):
 
 def high_level_grad_tree(params, out, reduce_mean):
     """params-shaped pytree of d (H . grad_U J) / d params from one gmpc_bilevel_l2 result `out`
-    (policy/optimizers.py:69-71).  reduce_mean: leaf-wise batch mean (policy/base.py:126-127),
-    else every leaf keeps a leading batch axis (what vmap of bilevel_optimization returns)."""
+    (policy/optimizers.py:69-71).  reduce_mean: True = leaf-wise batch mean (policy/base.py:126-127),
+    "sum" = batch sum (data-parallel callers divide by the global batch after the all-reduce), False =
+    every leaf keeps a leading batch axis (what vmap of bilevel_optimization returns)."""
     B = out["X"].shape[0]
     w2 = torch.sigmoid(params["mpc_weights"][2])
     gW, gb = cost_mlp_mixed_vjp(params["cost_params"], w2, out["X"][:, -1].contiguous(), out["dxT"])
-    red = (lambda t: t.mean(0)) if reduce_mean else (lambda t: t)
+    red = ((lambda t: t.sum(0)) if reduce_mean == "sum" else (lambda t: t.mean(0))) if reduce_mean else (lambda t: t)
     lead = () if reduce_mean else (B,)
     tree = {k: zeros_like_tree(v, lead) for k, v in params.items()}
     tree["mpc_weights"] = red(out["grad_mpc_weights"])
     tree["cost_params"] = {"params": {f"Dense_{i}": {"kernel": red(gW[i]), "bias": red(gb[i])}
                                       for i in range(len(gW))}}
     return tree
+
+
+def tree_leaves(tree):
+    if isinstance(tree, dict):
+        for k in sorted(tree):
+            yield from tree_leaves(tree[k])
+    elif isinstance(tree, torch.Tensor):
+        yield tree
+
+
+def allreduce_mean_tree_(loss_sum, tree, global_batch):
+    """Data-parallel reduction of (sum of losses, sum of per-sample gradients) over the ranks: ONE
+    sum all-reduce of the flattened pytree (NCCL on the box), then the division by the global batch
+    -- the batch mean of policy/base.py:126-127 with the batch sharded over GPUs."""
+    from gan_mpc_b200 import parallel
+    leaves = list(tree_leaves(tree))
+    flat = torch.cat([loss_sum.reshape(1)] + [t.reshape(-1) for t in leaves])
+    parallel.allreduce_sum_(flat)
+    flat /= float(global_batch)
+    o = 1
+    for t in leaves:
+        t.copy_(flat[o:o + t.numel()].view_as(t))
+        o += t.numel()
+    return flat[0].clone(), tree

@@ -1,5 +1,6 @@
-"""Multi-GPU (one process per GPU, NCCL): sharded planning == single-GPU planning bit for bit,
-and the data-parallel critic step == the single-GPU full-batch step.  Skipped with < 2 GPUs."""
+"""Multi-GPU (one process per GPU, NCCL): sharded planning (first-order and iLQR) == single-GPU
+planning bit for bit, the data-parallel critic step == the single-GPU full-batch step, and the
+data-parallel bilevel gradient == the single-GPU batch mean.  Skipped with < 2 GPUs."""
 
 import os
 import socket
@@ -40,7 +41,31 @@ loss, g = h.critic_loss_grad(xs, lab, flat, inv_count=1.0 / Bc, perm=perm[lo:hi]
 parallel.allreduce_sum_(g); parallel.allreduce_sum_(loss)
 loss1, g1 = h.critic_loss_grad(xs, lab, flat)
 ok_critic = float((g - g1).abs().max()) < 1e-6 * float(g1.abs().max() + 1e-30) + 1e-9 and abs(float(loss) - float(loss1)) < 1e-6
-flag = torch.tensor([int(ok_plan), int(ok_critic)], device=dev)
+# sharded iLQR == single-GPU iLQR (lanes are independent of their tile mates)
+Ui, Ji, iti = parallel.ilqr_sharded(h, t(x0), t(U0[:, 0].copy()), t(goal), maxiter=5)
+fi = h.ilqr(t(x0).to(dev), t(U0[:, 0].copy()).to(dev), t(goal).to(dev), maxiter=5)
+ok_ilqr = torch.equal(Ui, fi[1]) and torch.equal(Ji, fi[2]) and torch.equal(iti, fi[6])
+# data-parallel bilevel gradient (BaseMPC.loss_and_grad): global mean on every rank == one-GPU mean
+from gan_mpc_b200 import utils
+from gan_mpc_b200.config import load_config
+from gan_mpc_b200.norm import runner as norm_runner
+config = utils.get_config(os.path.join(load_config.CONFIG_DIR, "l2_hyperparameters.yaml"))
+policy, _, _ = norm_runner.get_policy(config, 3, 1)
+policy.trajax_ilqr_kwargs = dict(policy.trajax_ilqr_kwargs, maxiter=3)
+params = norm_runner.get_params(policy, config, 3, 1)
+gen = torch.Generator().manual_seed(5)
+hx = torch.randn(37, 2, 3, generator=gen).to(dev)
+by = torch.randn(37, config.mpc.horizon + 1, 3, generator=gen).to(dev)
+l_dp, g_dp = policy.loss_and_grad(hx, params, (by,))
+saved = (dist.get_rank, dist.get_world_size)
+parallel.rank_world = lambda: (0, 1)       # the same call without sharding
+parallel.allreduce_sum_ = lambda x: x
+l_1, g_1 = policy.loss_and_grad(hx, params, (by,))
+k = lambda g: g["cost_params"]["params"]["Dense_1"]["kernel"]
+ok_bl = (abs(float(l_dp) - float(l_1)) < 1e-5 * abs(float(l_1)) and
+         float((k(g_dp) - k(g_1)).norm() / k(g_1).norm()) < 1e-4 and
+         float((g_dp["mpc_weights"] - g_1["mpc_weights"]).norm() / g_1["mpc_weights"].norm()) < 1e-4)
+flag = torch.tensor([int(ok_plan), int(ok_critic), int(ok_ilqr), int(ok_bl)], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("RESULT", flag.tolist())
@@ -61,4 +86,4 @@ def test_sharded_plan_and_dp_critic_match_single_gpu(built_lib, tmp_path):
                           f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                           "--master-port", str(port), str(script)],
                          capture_output=True, text=True, env=env, timeout=600)
-    assert "RESULT [1, 1]" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "RESULT [1, 1, 1, 1]" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
