@@ -65,6 +65,9 @@ _SIGS = {
     "gmpc_critic_input_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, _f, C.c_void_p]),
     "gmpc_ilqr_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.c_void_p]),
+    "gmpc_expert_propose": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, C.c_int32, C.c_int32,
+                                      C.c_int32, _f, _f, C.c_void_p]),
+    "gmpc_expert_param_count": (C.c_int64, [C.c_int32] * 5),
     "gmpc_critic_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_void_p]),
     "gmpc_critic_loss_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_float,
                                         _f, _f, C.c_void_p]),
@@ -353,6 +356,21 @@ class Handle:
         a, b = C.c_int64(0), C.c_int64(0)
         _check(self.lib.gmpc_ilqr_stats(self._h, C.byref(a), C.byref(b), _stream(self.device)))
         return int(a.value), int(b.value)
+
+    def expert_propose(self, history_x, params_flat, lstm_features, num_layers, num_hidden_units):
+        """gmpc_expert_propose: history_x [B,hist+1,n] -> (goal_xseq [B,T+1,n], init_useq [B,T,m])."""
+        dev = self.device
+        B, rows = history_x.shape[0], history_x.shape[1]
+        goal = torch.empty(B, self.T + 1, self.n, device=dev, dtype=torch.float32)
+        useq = torch.empty(B, self.T, self.m, device=dev, dtype=torch.float32)
+        want = self.lib.gmpc_expert_param_count(self.n, self.m, lstm_features, num_layers, num_hidden_units)
+        if params_flat.numel() != want:
+            raise ValueError(f"expert_propose: params_flat has {params_flat.numel()} floats, the network needs {want}")
+        _check(self.lib.gmpc_expert_propose(
+            self._h, B, rows - 1, _ptr(history_x, device=dev, name="history_x"),
+            _ptr(params_flat, device=dev, name="params_flat"), int(lstm_features), int(num_layers),
+            int(num_hidden_units), _ptr(goal), _ptr(useq), _stream(dev)))
+        return goal, useq
 
     # ---------------------------------------------------------------- critic / losses
     def critic_forward(self, xseq, params_flat):

@@ -12,6 +12,7 @@
 #include "../../include/gmpc.h"
 #include "common.cuh"
 #include "critic.cuh"
+#include "expert.cuh"
 #include "diag.cuh"
 #include "plan_ffma.cuh"
 #include "ilqr.cuh"
@@ -683,6 +684,72 @@ extern "C" int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float*
       return rc;
     }
   }
+  return GMPC_OK;
+}
+
+// ----------------------------------------------------------------------------------- expert
+// Flat parameter layout of the expert proposal network (expert/nn.py): trunk, then the next_x head,
+// then the action head; every kernel is flax [in, out] row-major.
+static int expert_dims(int n, int m, int T, int hist, int F, int num_layers, int H, ExpertDims& d) {
+  memset(&d, 0, sizeof(d));
+  d.n = n; d.m = m; d.T = T; d.hist = hist; d.F = F; d.H = H;
+  d.Lh = F > 0 ? num_layers : num_layers - 1;
+  d.Y = F > 0 ? F : H;
+  if (d.Lh < 1 || d.Lh > MAXL) return -1;
+  long long o = 0;
+  if (F > 0) {
+    d.oWi = o; o += (long long)n * 4 * F;
+    d.oWh = o; o += (long long)F * 4 * F;
+    d.obh = o; o += 4 * F;
+  } else {
+    d.oD0 = o; o += (long long)n * H;
+    d.ob0 = o; o += H;
+  }
+  for (int hd = 0; hd < 2; ++hd) {
+    int din = d.Y;
+    for (int l = 0; l < d.Lh; ++l) {
+      const int dout = l == d.Lh - 1 ? (hd == 0 ? n : m) : H;
+      d.oHk[hd][l] = o; o += (long long)din * dout;
+      d.oHb[hd][l] = o; o += dout;
+      din = H;
+    }
+  }
+  d.P = o;
+  return 0;
+}
+
+extern "C" int64_t gmpc_expert_param_count(int32_t n, int32_t m, int32_t lstm_features,
+                                           int32_t num_layers, int32_t num_hidden_units) {
+  ExpertDims d;
+  if (n < 1 || m < 1 || lstm_features < 0 || num_hidden_units < 1 ||
+      expert_dims(n, m, 1, 0, lstm_features, num_layers, num_hidden_units, d))
+    return -1;
+  return d.P;
+}
+
+extern "C" int gmpc_expert_propose(gmpc_handle* h, int64_t B, int32_t hist, const float* history_x,
+                                   const float* params_flat, int32_t lstm_features,
+                                   int32_t num_layers, int32_t num_hidden_units, float* goal_xseq,
+                                   float* init_useq, void* stream) {
+  if (!h) return fail(GMPC_E_ARG, "gmpc_expert_propose: null handle");
+  if (B < 0 || hist < 0) return fail(GMPC_E_ARG, "gmpc_expert_propose: need B >= 0, hist >= 0");
+  if (B == 0) return GMPC_OK;
+  if (!history_x || !params_flat || !goal_xseq || !init_useq)
+    return fail(GMPC_E_ARG, "gmpc_expert_propose: null argument");
+  const gmpc_config& c = h->cfg;
+  ExpertDims d;
+  if (lstm_features < 0 || num_hidden_units < 1 ||
+      expert_dims(c.n, c.m, c.T, hist, lstm_features, num_layers, num_hidden_units, d))
+    return fail(GMPC_E_ARG, "gmpc_expert_propose: bad network shape");
+  const int width = std::max(std::max(4 * d.F, d.H), std::max(c.n, c.m));
+  if (width > 1024) return fail(GMPC_E_UNSUPPORTED, "gmpc_expert_propose: needs 4*lstm_features, hidden, n, m <= 1024");
+  CU_CHECK(cudaSetDevice(c.device));
+  const int threads = std::max(64, ((width + 31) / 32) * 32);
+  const size_t smem = sizeof(float) * ((size_t)2 * c.n + (size_t)6 * d.F + d.Y + 2 * d.H);
+  const int grid = (int)std::min<int64_t>(B, (int64_t)4 * h->num_sms);
+  expert_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(d, history_x, params_flat, B, goal_xseq, init_useq);
+  ++h->launches;
+  CU_CHECK(cudaGetLastError());
   return GMPC_OK;
 }
 

@@ -12,7 +12,9 @@ from gan_mpc_b200.policy import eval
 def get_policy(config, x_size, u_size, expert_model=None):
     cost, _ = utils.get_cost_model(config)
     dynamics, _ = utils.get_dynamics_model(config, x_size)
-    if expert_model is None:
+    if expert_model == "network":   # the reference's expert proposal network (utils.get_expert_model)
+        expert_model = utils.get_expert_model(config, x_size, u_size)
+    elif expert_model is None:      # no checkpoint is shipped: seeded synthetic proposals by default
         expert_model = expert.SyntheticExpert(config, x_size, u_size, seed=config.seed)
     train_policy = l2_policy.L2MPC(config=config, cost_model=cost, dynamics_model=dynamics,
                                    expert_model=expert_model)
@@ -21,10 +23,13 @@ def get_policy(config, x_size, u_size, expert_model=None):
     return train_policy, eval_policy, config.mpc
 
 
-def get_params(policy, config, x_size, u_size):
+def get_params(policy, config, x_size, u_size, load_expert=True):
+    """expert params: load_expert=True reads the trained checkpoint as the reference does
+    (norm/runner.py get_params passes (True,)); False draws flax-default random weights."""
     seed = config.seed
     mpc_weights = tuple(config.mpc.model.cost.weights.to_dict().values())
-    return policy.init(mpc_weights, (seed, x_size), (seed, u_size), (True,))
+    return policy.init(mpc_weights, (seed, x_size), (seed, u_size),
+                       (True,) if load_expert else (False, seed, 1, 1, x_size))
 
 
 def get_optimizer(params, masked_vars, lr):

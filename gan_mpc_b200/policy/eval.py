@@ -43,6 +43,8 @@ class EvalMPC:
         pk.update(planner_kwargs or {})
         self.planner_kwargs = pk
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        if hasattr(expert_model, "bind"):
+            expert_model.bind(self)     # ExpertModel runs on this policy's libgmpc handles
         self.critic_model = None
         self._handles = {}
         self._staged = {}
@@ -179,6 +181,8 @@ class EvalMPC:
             raise ValueError("no expert model: pass goal states / initial actions explicitly to "
                              "policy.solver(xc, useq, params, (goal_xseq,), ())")
         expert_params = params["expert_params"]
+        if hasattr(self.expert_model, "propose"):   # ExpertModel: history carry + proposal, one launch
+            return self.expert_model.propose(self, histroy_x, expert_params)
         x = histroy_x[..., -1, :]
         T = self.config.mpc.horizon
         xseq = torch.cat([x[..., None, :], torch.zeros(*x.shape[:-1], T - 1, x.shape[-1],

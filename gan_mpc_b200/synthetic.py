@@ -103,6 +103,25 @@ def critic_params_flat(seed, n, F, layers, hidden):
     return np.concatenate(parts).astype(np.float32)
 
 
+def expert_params_flat(seed, shapes, lstm_features):
+    """Flat expert-network vector (include/gmpc.h layout) with flax defaults.  `shapes` is the
+    [(path, shape)] list of expert/nn.py:_shapes(): LSTM input kernels lecun_normal, recurrent kernels
+    orthogonal (per gate), Dense kernels lecun_normal, biases zero."""
+    rng = np.random.Generator(np.random.PCG64(seed + 4000003))
+    F = lstm_features
+    parts = []
+    for path, shape in shapes:
+        if len(shape) == 1:
+            parts.append(np.zeros(shape, np.float32))
+        elif path[:2] == ("lstm", "Wh"):
+            parts.append(np.concatenate([orthogonal(rng, F) for _ in range(4)], axis=1).ravel())
+        elif path[:2] == ("lstm", "Wi"):
+            parts.append(np.concatenate([lecun_normal(rng, shape[0], F) for _ in range(4)], axis=1).ravel())
+        else:
+            parts.append(lecun_normal(rng, shape[0], shape[1]).ravel())
+    return np.concatenate(parts).astype(np.float32)
+
+
 def critic_dataset(seed, D, T1, n):
     """Labelled trajectories: +1 goal-style random walks, -1 a second family with drift (a
     stand-in for planner outputs when none are supplied).  Returns xseq [2D,T1,n], label [2D]."""

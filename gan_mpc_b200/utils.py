@@ -53,6 +53,23 @@ def get_dynamics_model(config, x_size):
     return dynamics_model.DynamicsModel(config, nn_model), model_config
 
 
+def get_expert_model(config, x_size, u_size, model_config=None):
+    """utils.py:216-227: the reference reads the model block from the saved expert run
+    (trained_models/expert/<type>/<name>/<id>/config.json); when that file is absent (the reference
+    ships none) the `expert_prediction.model` block of the YAML -- or `model_config` -- is used."""
+    import os
+    from gan_mpc_b200.expert import expert_model
+    if model_config is None:
+        saved = os.path.join("trained_models", "expert", str(config.env.type), str(config.env.expert.name),
+                             str(config.mpc.model.expert.load_id), "config.json")
+        if os.path.exists(saved):
+            model_config = load_config.Config.from_dict(load_json(saved)["model"])
+        else:
+            model_config = config.expert_prediction.model
+    nn_model = expert_model.ExpertModel.get_model(model_config=model_config, x_size=x_size, u_size=u_size)
+    return expert_model.ExpertModel(config, nn_model)
+
+
 def get_critic_model(config):
     model_config = config.mpc.model.critic
     if model_config.use == "lstm":

@@ -206,6 +206,25 @@ int gmpc_range_overflow(gmpc_handle* h, int32_t* count, void* stream);
 /* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 int64_t gmpc_launch_count(const gmpc_handle* h);
 
+/* The expert proposal network in front of the planner: EvalMPC.get_goal_states_init_actions
+ * (policy/eval.py:87-107, policy/base.py:40-61) = ExpertModel.get_history_carry (LSTM carry warmed up
+ * on the history rows with teacher forcing, expert/expert_model.py:60-71) followed by
+ * get_carry_next_state_and_action_seq with teacher_forcing=False (:73-91) on the scanned cell of
+ * expert/nn.py:22-60.  history_x[B,hist+1,n] (last row = current state) ->
+ * goal_xseq[B,T+1,n] (row 0 = current state), init_useq[B,T,m]: exactly the planner's inputs, so
+ * acting is expert -> plan with no host round trip.
+ * lstm_features > 0: ScanLSTM (OptimizedLSTMCell(F), heads MLPCell(num_layers));
+ * lstm_features = 0: ScanMLP (Dense(H)+relu trunk, heads MLPCell(num_layers - 1)).
+ * params_flat layout (flax kernels [in,out], gates i,f,g,o):
+ *   LSTM trunk  Wi[n,4F] | Wh[F,4F] | bh[4F]        or   MLP trunk  D0[n,H] | b0[H]
+ *   then the next_x head {Dk, Db}* | Wo[.,n] | bo[n], then the action head {Dk, Db}* | Wo[.,m] | bo[m]. */
+int gmpc_expert_propose(gmpc_handle* h, int64_t B, int32_t hist, const float* history_x,
+                        const float* params_flat, int32_t lstm_features, int32_t num_layers,
+                        int32_t num_hidden_units, float* goal_xseq, float* init_useq, void* stream);
+/* Number of floats of that layout (-1 for an invalid shape). */
+int64_t gmpc_expert_param_count(int32_t n, int32_t m, int32_t lstm_features, int32_t num_layers,
+                                int32_t num_hidden_units);
+
 /* CriticModel.predict (critic/critic_model.py:15-16, critic/nn.py:27-42):
  * xseq[Bc,T1,n], params_flat -> logit[Bc].  T1 = number of rows (T+1 in the reference). */
 int gmpc_critic_forward(gmpc_handle* h, int64_t Bc, int32_t T1, const float* xseq,

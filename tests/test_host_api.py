@@ -139,3 +139,35 @@ def test_params_npy_round_trip(tmp_path):
         for k in ("kernel", "bias"):
             assert torch.equal(back["dynamics_params"]["params"][f"Dense_{i}"][k],
                                params["dynamics_params"]["params"][f"Dense_{i}"][k])
+
+
+def test_expert_network_layout_and_oracle():
+    """flat layout <-> flax-named pytree, parameter counts, and the oracle's call sequence
+    (history warm-up then free-running proposal; row 0 of the goals is the current state)."""
+    import numpy as np
+    import torch
+    from gan_mpc_b200 import synthetic
+    from gan_mpc_b200.expert import expert_model, nn as expert_nn
+    from oracle import expert as oexpert
+    c = utils.get_config(os.path.join(load_config.CONFIG_DIR, "l2_hyperparameters.yaml"))
+    em = utils.get_expert_model(c, 3, 1)
+    md = em.model.model
+    assert isinstance(em, expert_model.ExpertModel) and isinstance(md, expert_nn.ScanLSTM)
+    F, H = 128, 128
+    want = 3 * 4 * F + F * 4 * F + 4 * F + 2 * (F * H + H + H * H + H) + (H * 3 + 3) + (H * 1 + 1)
+    assert md.param_count() == want
+    flat = torch.from_numpy(synthetic.expert_params_flat(0, md._shapes(), F))
+    tree = md.unflatten(flat)
+    assert torch.equal(md.flatten(tree), flat)
+    hx = torch.randn(4, 3, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    goal, useq = oexpert.propose(hx, flat.double(), md._shapes(), F, md.head_layers, 5)
+    assert goal.shape == (4, 6, 3) and useq.shape == (4, 5, 1) and torch.equal(goal[:, 0], hx[:, -1])
+    # the history matters through the LSTM carry only
+    hx2 = hx.clone(); hx2[:, 0] += 1.0
+    g2, _ = oexpert.propose(hx2, flat.double(), md._shapes(), F, md.head_layers, 5)
+    assert not torch.allclose(g2[:, 1:], goal[:, 1:])
+    mlp = expert_nn.ScanMLP(3, 16, 3, 1)
+    fm = torch.from_numpy(synthetic.expert_params_flat(0, mlp._shapes(), 0)).double()
+    g3, _ = oexpert.propose(hx, fm, mlp._shapes(), 0, mlp.head_layers, 5)
+    g4, _ = oexpert.propose(hx2, fm, mlp._shapes(), 0, mlp.head_layers, 5)
+    assert torch.equal(g3, g4)          # the MLP cell has no carry besides x
