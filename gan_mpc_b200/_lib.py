@@ -65,6 +65,9 @@ _SIGS = {
     "gmpc_critic_input_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, _f, C.c_void_p]),
     "gmpc_ilqr_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.c_void_p]),
+    "gmpc_dynamics_fit": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_float, C.c_int32, _f,
+                                    C.POINTER(_f), C.POINTER(_f), C.c_void_p]),
+    "gmpc_dynamics_fit_columns": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int32]),
     "gmpc_expert_propose": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, C.c_int32, C.c_int32,
                                       C.c_int32, _f, _f, C.c_void_p]),
     "gmpc_expert_param_count": (C.c_int64, [C.c_int32] * 5),
@@ -356,6 +359,25 @@ class Handle:
         a, b = C.c_int64(0), C.c_int64(0)
         _check(self.lib.gmpc_ilqr_stats(self._h, C.byref(a), C.byref(b), _stream(self.device)))
         return int(a.value), int(b.value)
+
+    def dynamics_fit(self, xseq, useq, next_xseq, discount_factor, teacher_forcing, dims):
+        """gmpc_dynamics_fit: (loss [B], act [L x [K_l,R]], cot [L x [N_l,R]]); dims = the dynamics MLP's
+        layer widths [n+m, H, ..., n]."""
+        dev = self.device
+        B, S = xseq.shape[0], xseq.shape[1]
+        R = int(self.lib.gmpc_dynamics_fit_columns(self._h, B, S))
+        L = len(dims) - 1
+        loss = torch.empty(B, device=dev, dtype=torch.float32)
+        act = [torch.empty(dims[l], R, device=dev, dtype=torch.float32) for l in range(L)]
+        cot = [torch.empty(dims[l + 1], R, device=dev, dtype=torch.float32) for l in range(L)]
+        pa, pc = (_f * L)(), (_f * L)()
+        for l in range(L):
+            pa[l], pc[l] = act[l].data_ptr(), cot[l].data_ptr()
+        _check(self.lib.gmpc_dynamics_fit(
+            self._h, B, S, _ptr(xseq, device=dev, name="xseq"), _ptr(useq, device=dev, name="useq"),
+            _ptr(next_xseq, device=dev, name="next_xseq"), float(discount_factor), int(bool(teacher_forcing)),
+            _ptr(loss), pa, pc, _stream(dev)))
+        return loss, act, cot
 
     def expert_propose(self, history_x, params_flat, lstm_features, num_layers, num_hidden_units):
         """gmpc_expert_propose: history_x [B,hist+1,n] -> (goal_xseq [B,T+1,n], init_useq [B,T,m])."""

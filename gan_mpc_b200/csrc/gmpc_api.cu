@@ -16,6 +16,7 @@
 #include "diag.cuh"
 #include "plan_ffma.cuh"
 #include "ilqr.cuh"
+#include "dynfit.cuh"
 #include "plan_tc.cuh"
 #include "plan_h16.cuh"
 
@@ -82,6 +83,9 @@ struct gmpc_handle {
   TcState tc;
   H16State h16;
   // iLQR kernel scratch (allocated on first use)
+  uint32_t* d_fit_masks = nullptr;   // dynfit kernel ReLU masks (grown on demand)
+  size_t fit_masks_bytes = 0;
+  bool fit_attr = false;
   float* d_ilqr_ws = nullptr;
   size_t ilqr_ws_bytes = 0;
   long long* d_ilqr_stats = nullptr;
@@ -260,7 +264,7 @@ extern "C" int gmpc_destroy(gmpc_handle* h) {
   cudaFree(h->ws_X); cudaFree(h->ws_G); cudaFree(h->ws_U); cudaFree(h->ws_M); cudaFree(h->ws_V);
   cudaFree(h->ws_mask); cudaFree(h->d_scratch); cudaFree(h->d_stage);
   cudaFree(h->d_partial); cudaFree(h->d_losses); cudaFree(h->d_fuse);
-  cudaFree(h->d_ilqr_ws); cudaFree(h->d_ilqr_stats);
+  cudaFree(h->d_ilqr_ws); cudaFree(h->d_ilqr_stats); cudaFree(h->d_fit_masks);
   delete h;
   return GMPC_OK;
 }
@@ -684,6 +688,72 @@ extern "C" int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float*
       return rc;
     }
   }
+  return GMPC_OK;
+}
+
+// ----------------------------------------------------------------------------------- dynamics fit
+extern "C" int64_t gmpc_dynamics_fit_columns(const gmpc_handle* h, int64_t B, int32_t S) {
+  if (!h || B < 0 || S < 1) return -1;
+  return (int64_t)RT * ((B + RT - 1) / RT) * S;
+}
+
+// predict_loss (norm/dynamics_trainer.py:13-44) for a batch of windows and the factors of its weight
+// gradient (csrc/dynfit.cuh).
+extern "C" int gmpc_dynamics_fit(gmpc_handle* h, int64_t B, int32_t S, const float* xseq,
+                                 const float* useq, const float* next_xseq, float discount_factor,
+                                 int32_t teacher_forcing, float* loss, float* const* act,
+                                 float* const* cot, void* stream) {
+  int rc = check_ready(h, "gmpc_dynamics_fit", B);
+  if (rc) return rc;
+  if (B == 0) return GMPC_OK;
+  if (S < 1 || !xseq || !useq || !next_xseq || !loss || !act || !cot)
+    return fail(GMPC_E_ARG, "gmpc_dynamics_fit: null argument or S < 1");
+  const gmpc_config& c = h->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  DynFitParams Q;
+  memset(&Q, 0, sizeof(Q));
+  PlanParams& P = Q.pp;
+  make_dirs(h->dyn, P.dir[DIR_DYN_F], P.dir[DIR_DYN_B]);
+  P.n = c.n; P.m = c.m; P.T = c.T; P.K = 1;
+  P.hpad = h->hpad;
+  P.iters = S;     // SCHED_FIT: S forward passes then S adjoint passes
+  P.NQ = B;
+  P.ntiles = (int)((B + RT - 1) / RT);
+  const int L = h->dyn.L;
+  for (int l = 0; l < L; ++l) {
+    if (!act[l] || !cot[l]) return fail(GMPC_E_ARG, "gmpc_dynamics_fit: null act/cot pointer");
+    Q.act[l] = act[l];
+    Q.cot[l] = cot[l];
+  }
+  Q.S = S;
+  Q.teacher_forcing = teacher_forcing ? 1 : 0;
+  Q.gamma = discount_factor;
+  Q.xseq = xseq; Q.useq = useq; Q.yseq = next_xseq;
+  Q.loss = loss;
+  Q.R = (long long)RT * P.ntiles * S;
+  const int grid = std::min(P.ntiles, h->num_sms);
+  const size_t need = (size_t)grid * S * std::max(1, L - 1) * h->maxt * NTHREADS * sizeof(uint32_t);
+  if (need > h->fit_masks_bytes) {
+    CU_CHECK(cudaStreamSynchronize(st));
+    rc = grow((void**)&h->d_fit_masks, &h->fit_masks_bytes, need);
+    if (rc) return rc;
+  }
+  Q.masks = h->d_fit_masks;
+  const int n4 = rup4(c.n), nm4 = rup4(c.n + c.m);
+  const size_t smem = sizeof(float) * ((size_t)2 * h->hpad * RT + (size_t)NSTAGE * STAGE_FLOATS +
+                                       (size_t)(2 * nm4 + 2 * n4) * RT);
+  if (!h->fit_attr) {
+    CU_CHECK(cudaFuncSetAttribute(dynfit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(dynfit_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    h->fit_attr = true;
+  }
+  if (smem > 227 * 1024) return fail(GMPC_E_UNSUPPORTED, "gmpc_dynamics_fit: shape needs more shared memory than one SM has");
+  if (h->maxt == 1)
+    dynfit_kernel<1><<<grid, NTHREADS, smem, st>>>(Q);
+  else
+    dynfit_kernel<2><<<grid, NTHREADS, smem, st>>>(Q);
+  ++h->launches;
+  CU_CHECK(cudaGetLastError());
   return GMPC_OK;
 }
 

@@ -29,8 +29,9 @@ struct WeightPipe {
 
 // Pass schedules: the planner's (pass_kind), and the two phases of the iLQR kernel (ilqr.cuh):
 // SCHED_LIN  = per step one forward pass + n adjoint passes (the Jacobian rows), then the cost MLP
-//              forward + fout adjoint passes;  SCHED_ROLL = T forward passes + the cost MLP.
-enum { SCHED_PLAN = 0, SCHED_LIN = 1, SCHED_ROLL = 2 };
+//              forward + fout adjoint passes;  SCHED_ROLL = T forward passes + the cost MLP;
+// SCHED_FIT  = P.iters forward passes then P.iters adjoint passes of the dynamics MLP (dynfit.cuh).
+enum { SCHED_PLAN = 0, SCHED_LIN = 1, SCHED_ROLL = 2, SCHED_FIT = 3 };
 
 __device__ __forceinline__ int pass_kind(const PlanParams& P, int p) {
   const int period = 2 * P.T + (P.use_cost ? 2 : 0);
@@ -59,6 +60,8 @@ __device__ __forceinline__ int sched_kind(const PlanParams& P, int sched, int p)
     if (p == nd) return DIR_COST_F;
     return (p - nd <= P.fout) ? DIR_COST_B : DIR_END;
   }
+  if (sched == SCHED_FIT)  // dynfit.cuh: P.iters forward passes then P.iters adjoint passes
+    return p < P.iters ? DIR_DYN_F : (p < 2 * P.iters ? DIR_DYN_B : DIR_END);
   return p < P.T ? DIR_DYN_F : (p == P.T ? DIR_COST_F : DIR_END);
 }
 
@@ -187,11 +190,12 @@ enum { EPI_BIAS = 1, EPI_RELU = 2, EPI_MASK_OUT = 4, EPI_MASK_IN = 8, EPI_RESID 
 
 // Write the accumulators out.  swz_out: hidden buffer (swizzled, all padded columns written);
 // otherwise a small linear array where only columns o < No are touched.
-// gout (nullable): also store rows o < No linearly to a global [No][RT] slab (trajectory log).
+// gout (nullable): also store rows o < No linearly to a global [No][gstride] slab (trajectory log;
+// gstride > RT when the slab is a column block of a wider [No][R] matrix, dynfit.cuh).
 template <int MAXT>
 __device__ __forceinline__ void epilogue(const LayerDesc& L, int flags, float* out_s, bool swz_out,
                                          uint32_t* maskp, float* gout, const Tiles<MAXT>& tl,
-                                         float (&acc)[MAXT][8][4]) {
+                                         float (&acc)[MAXT][8][4], size_t gstride = RT) {
 #pragma unroll
   for (int j = 0; j < MAXT; ++j) {
     if (!tl.act[j]) continue;
@@ -226,7 +230,7 @@ __device__ __forceinline__ void epilogue(const LayerDesc& L, int flags, float* o
       *reinterpret_cast<float4*>(p0) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(p1) = make_float4(v[4], v[5], v[6], v[7]);
       if (gout != nullptr && in_range) {
-        float* g = gout + o * RT + tl.rg[j] * 8;
+        float* g = gout + (size_t)o * gstride + tl.rg[j] * 8;
         *reinterpret_cast<float4*>(g) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(g + 4) = make_float4(v[4], v[5], v[6], v[7]);
       }

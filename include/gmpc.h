@@ -206,6 +206,22 @@ int gmpc_range_overflow(gmpc_handle* h, int32_t* count, void* stream);
 /* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 int64_t gmpc_launch_count(const gmpc_handle* h);
 
+/* The dynamics trainer's loss (norm/dynamics_trainer.py:13-44 predict_loss, vmapped at :66-77) and the
+ * factors of its weight gradient.  For B windows of S recorded steps: roll the dynamics MLP from the
+ * recorded state at every step (teacher_forcing != 0) or from its own prediction, and
+ *   loss[b] = sum_t discount^t |x'_t - next_xseq[b,t]|^2                 (utils.discounted_sum).
+ * xseq[B,S,n], useq[B,S,m], next_xseq[B,S,n] -> loss[B], and for every Dense layer l of the dynamics
+ * MLP two GEMM-ready matrices with R = gmpc_dynamics_fit_columns(h, B, S) columns (one column per
+ * (window, step); padded windows are zero in cot):
+ *   act[l] [K_l, R]  the layer's inputs,      cot[l] [N_l, R]  d (sum_b loss[b]) / d (layer output),
+ * including the back-propagation through time of the state adjoint when free running.
+ * The gradient of the batch-mean loss is then  dW_l = act[l] cot[l]^T / B,  db_l = rowsum(cot[l]) / B:
+ * one plain GEMM per layer, left to the caller's BLAS (cuBLAS; the host mirror uses torch.matmul). */
+int gmpc_dynamics_fit(gmpc_handle* h, int64_t B, int32_t S, const float* xseq, const float* useq,
+                      const float* next_xseq, float discount_factor, int32_t teacher_forcing,
+                      float* loss, float* const* act, float* const* cot, void* stream);
+int64_t gmpc_dynamics_fit_columns(const gmpc_handle* h, int64_t B, int32_t S);
+
 /* The expert proposal network in front of the planner: EvalMPC.get_goal_states_init_actions
  * (policy/eval.py:87-107, policy/base.py:40-61) = ExpertModel.get_history_carry (LSTM carry warmed up
  * on the history rows with teacher forcing, expert/expert_model.py:60-71) followed by

@@ -223,3 +223,21 @@ def test_golden_critic():
     loss, g = ocritic.critic_loss_and_grad(xs, lab, flat, n, F, L, H)
     assert np.allclose(float(loss), float(z["loss"]), rtol=1e-10)
     assert np.allclose(g.numpy(), z["grad"], rtol=1e-8, atol=1e-12)
+
+
+def test_dynfit_oracle_teacher_forcing_and_discount():
+    """oracle/dynfit.py: with teacher forcing the window is S independent one-step regressions;
+    discount 0 keeps only step 0; free running equals teacher forcing on a window of one step."""
+    from oracle import dynfit as ofit
+    p, *_ = util.case(util.ODD, 3, B=1)
+    op = util.to_oracle(p)
+    g = torch.Generator().manual_seed(0)
+    xs = torch.randn(4, 5, 5, generator=g, dtype=torch.float64)
+    us = torch.randn(4, 5, 3, generator=g, dtype=torch.float64)
+    ys = torch.randn(4, 5, 5, generator=g, dtype=torch.float64)
+    tf = ofit.predict_loss(op, xs, us, ys, 0.9, True)
+    ref = sum(0.9 ** t * ((oracle.dynamics_mlp(xs[:, t], us[:, t], op["dyn_W"], op["dyn_b"]) - ys[:, t]) ** 2).sum(-1)
+              for t in range(5))
+    assert torch.allclose(tf, ref)
+    assert torch.allclose(ofit.predict_loss(op, xs, us, ys, 0.0, True), ofit.predict_loss(op, xs[:, :1], us[:, :1], ys[:, :1], 0.9, False))
+    assert not torch.allclose(tf, ofit.predict_loss(op, xs, us, ys, 0.9, False))
