@@ -129,3 +129,35 @@ def test_ilqr_rejects_unsupported_options(built_lib):
         h.ilqr(dev(x0), dev(U0), dev(goal), make_psd=True)
     with pytest.raises(TypeError):
         h.ilqr(dev(x0), dev(U0), dev(goal), bogus=1)
+
+
+TINY = dict(n=2, m=3, T=1, dyn_layers=2, dyn_hidden=12, cost_layers=2, cost_hidden=9, cost_fout=3)  # T=1, m > n
+LONG = dict(n=4, m=2, T=24, dyn_layers=3, dyn_hidden=64, cost_layers=3, cost_hidden=32, cost_fout=5)
+
+
+@pytest.mark.parametrize("cfg,B,maxiter", [(TINY, 35, 4), (LONG, 20, 2), (util.WIDE, 8, 2)])
+def test_ilqr_edge_shapes(cfg, B, maxiter, built_lib):
+    """horizon 1 with more actions than states, a long horizon, hidden width 512 (two output tiles
+    per thread)."""
+    h, op, x0, U0, goal = _setup(cfg, 59, B)
+    X, U, obj, g, lam, _, it = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=maxiter)
+    oX, oU, oobj, og, olam, _, oit = oilqr.ilqr(util.tt(x0), util.tt(U0), util.tt(goal), op, maxiter=maxiter)
+    assert int((it.cpu() == oit).sum()) >= B - max(1, B // 8)
+    util.assert_rows_close("U", U, oU, tol=TOL, outlier_frac=0.2, cap=2.0)
+    util.assert_rows_close("obj", obj[:, None], oobj[:, None], tol=TOL, outlier_frac=0.2, cap=1.0)
+
+
+def test_ilqr_alpha0_below_alpha_min_and_bad_shapes(built_lib):
+    """alpha_0 <= alpha_min: no trial can run, one iteration is counted and U is unchanged (the
+    while_loop of line_search_ddp never enters); a state size whose Riccati tile does not fit
+    shared memory is refused, not silently truncated."""
+    from gan_mpc_b200 import _lib
+    h, op, x0, U0, goal = _setup(util.SMALL, 61, 5)
+    X, U, obj, g, lam, _, it = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=7, alpha_0=1e-5, alpha_min=1e-4)
+    o = oilqr.ilqr(util.tt(x0), util.tt(U0), util.tt(goal), op, maxiter=7, alpha_0=1e-5, alpha_min=1e-4)
+    assert torch.equal(U.cpu(), torch.from_numpy(U0)) and torch.equal(it.cpu(), o[6]) and int(it.max()) == 0
+    big = dict(util.SMALL, n=40, m=2)
+    p, bx0, bU0, bgoal = util.case(big, 1, B=2)
+    hb = util.make_handle(big, p)
+    with pytest.raises(_lib.GmpcError, match="shared memory"):
+        hb.ilqr(dev(bx0), dev(bU0[:, 0].copy()), dev(bgoal), maxiter=1)

@@ -50,9 +50,10 @@ from gan_mpc_b200 import utils
 from gan_mpc_b200.config import load_config
 from gan_mpc_b200.norm import runner as norm_runner
 config = utils.get_config(os.path.join(load_config.CONFIG_DIR, "l2_hyperparameters.yaml"))
-policy, _, _ = norm_runner.get_policy(config, 3, 1)
+# the expert NETWORK proposes per row (the synthetic stand-in draws per batch position)
+policy, _, _ = norm_runner.get_policy(config, 3, 1, expert_model="network")
 policy.trajax_ilqr_kwargs = dict(policy.trajax_ilqr_kwargs, maxiter=3)
-params = norm_runner.get_params(policy, config, 3, 1)
+params = norm_runner.get_params(policy, config, 3, 1, load_expert=False)
 gen = torch.Generator().manual_seed(5)
 hx = torch.randn(37, 2, 3, generator=gen).to(dev)
 by = torch.randn(37, config.mpc.horizon + 1, 3, generator=gen).to(dev)
