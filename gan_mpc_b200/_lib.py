@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgmpc.so")
+LIB_PATH = os.environ.get("GMPC_LIB_PATH", os.path.join(_HERE, "libgmpc.so"))  # override: experiments only
 
 METHOD_GRAD, METHOD_ADAM = 0, 1
 PATH_AUTO, PATH_FFMA, PATH_TC, PATH_TC16, PATH_TC16S = 0, 1, 2, 3, 4

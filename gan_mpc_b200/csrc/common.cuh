@@ -7,7 +7,10 @@ namespace gmpc {
 
 constexpr int RT = 32;              // trajectories per tile (one lane-row of 32 floats per feature)
 constexpr int NTHREADS = 256;       // threads per CTA of the FFMA kernel
-constexpr int NSTAGE = 3;           // cp.async weight-ring depth
+#ifndef GMPC_NSTAGE
+#define GMPC_NSTAGE 3
+#endif
+constexpr int NSTAGE = GMPC_NSTAGE; // cp.async weight-ring depth
 constexpr int STAGE_FLOATS = 4096;  // floats per ring stage (16 KB)
 constexpr int MAXL = 8;             // max Dense layers per MLP
 constexpr float ALPHA = 1e-2f;      // cost/cost_model.py:22

@@ -137,14 +137,24 @@ LONG = dict(n=4, m=2, T=24, dyn_layers=3, dyn_hidden=64, cost_layers=3, cost_hid
 
 @pytest.mark.parametrize("cfg,B,maxiter", [(TINY, 35, 4), (LONG, 20, 2), (util.WIDE, 8, 2)])
 def test_ilqr_edge_shapes(cfg, B, maxiter, built_lib):
-    """horizon 1 with more actions than states, a long horizon, hidden width 512 (two output tiles
-    per thread)."""
+    """horizon 1 with more actions than states (G = R + B^T P B has a direction held only by the 1e-5
+    eigenvalue of the pseudo-Huber Hessian), a long horizon, hidden width 512 (two output tiles per
+    thread).  These are ill-conditioned: the ORACLE's own fp32 run misses the fp64 one by more than
+    1e-4, so the bar is the fp32 noise floor measured by the oracle itself (x4 median, x8 max), and
+    iteration counts exact up to one row in eight."""
     h, op, x0, U0, goal = _setup(cfg, 59, B)
     X, U, obj, g, lam, _, it = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=maxiter)
     oX, oU, oobj, og, olam, _, oit = oilqr.ilqr(util.tt(x0), util.tt(U0), util.tt(goal), op, maxiter=maxiter)
+    f32 = torch.float32
+    p32 = {k: ([w.to(f32) for w in v] if isinstance(v, list) else v.to(f32)) for k, v in op.items()}
+    _, sU, sobj, *_ = oilqr.ilqr(util.tt(x0, f32), util.tt(U0, f32), util.tt(goal, f32), p32, maxiter=maxiter)
     assert int((it.cpu() == oit).sum()) >= B - max(1, B // 8)
-    util.assert_rows_close("U", U, oU, tol=TOL, outlier_frac=0.2, cap=2.0)
-    util.assert_rows_close("obj", obj[:, None], oobj[:, None], tol=TOL, outlier_frac=0.2, cap=1.0)
+    for name, k, s32, o64 in (("U", U, sU, oU), ("obj", obj[:, None], sobj[:, None], oobj[:, None])):
+        ek, es = util.rel_each(k, o64), util.rel_each(s32, o64)
+        print(f"{name}: kernel median {float(ek.median()):.2e} max {float(ek.max()):.2e}; "
+              f"fp32 oracle median {float(es.median()):.2e} max {float(es.max()):.2e}")
+        assert float(ek.median()) <= max(TOL / 4, 4 * float(es.median()))
+        assert float(ek.max()) <= max(TOL, 8 * float(es.max()))
 
 
 def test_ilqr_alpha0_below_alpha_min_and_bad_shapes(built_lib):
