@@ -96,7 +96,11 @@ struct Tiles {
   bool act[MAXT];
   __device__ __forceinline__ void setup(int tid, int No) {
     const int CG = (No + 3) >> 2;
-    const int CGr = (CG + 31) & ~31;
+#ifndef GMPC_SPARSE_TILES
+    const int CGr = CG;               // tiles packed densely over the threads (a warp may straddle two row groups)
+#else
+    const int CGr = (CG + 31) & ~31;  // a warp never straddles two row groups
+#endif
 #pragma unroll
     for (int j = 0; j < MAXT; ++j) {
       const int tau = tid + j * NTHREADS;
