@@ -203,3 +203,26 @@ def test_generator_loss_bilevel_through_the_critic(built_lib):
     print("generator-loss mean grad mpc_weights rel err", e)
     assert e < 1e-3
     assert float(cm.flatten(grads["critic_params"]).abs().sum()) == 0.0   # cost side only (Appendix D.3)
+
+
+def test_bilevel_solve_residual_at_c2_dims(built_lib):
+    """C2 dims (192 x 192 Hessian per state): size-independent properties of the tail -- the Hessian is
+    symmetric, H satisfies A H = B to fp32 LU accuracy, and the given-direction mode (cost_vjp's V = H)
+    reproduces the tangent quantities of the solve mode."""
+    from gan_mpc_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS["C2"], K=1, B=40)
+    p = synthetic.planner_params(0, **cfg)
+    x0, U0, goal = synthetic.planner_inputs(0, **cfg)
+    rng = np.random.Generator(np.random.PCG64(3))
+    desired = (goal + 0.05 * rng.standard_normal(goal.shape)).astype(np.float32)
+    h = util.make_handle(cfg, p)
+    o = h.bilevel_l2(dev(x0), dev(U0[:, 0].copy()), dev(goal), dev(desired), maxiter=1, want_hessian=True)
+    A, H, Bv = o["hessian"].double(), o["H"].double().reshape(40, -1), o["B"].double().reshape(40, -1)
+    assert float((A - A.transpose(1, 2)).abs().max()) == 0.0
+    res = (torch.einsum("bij,bj->bi", A, H) - Bv).norm(dim=1) / Bv.norm(dim=1)
+    cond = torch.linalg.cond(A)
+    print(f"solve residual max {float(res.max()):.2e}, cond(A) median {float(cond.median()):.2e}")
+    assert float(res.max()) < 1e-3
+    o2 = h.bilevel_l2(dev(x0), o["U"], dev(goal), dev(desired), maxiter=0, V=o["H"].contiguous())
+    assert util.rel_rows(o2["dxT"], o["dxT"].double().cpu()) < 1e-4
+    assert util.rel_rows(o2["grad_mpc_weights"], o["grad_mpc_weights"].double().cpu()) < 1e-4

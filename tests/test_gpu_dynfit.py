@@ -75,3 +75,30 @@ def test_dynamics_trainer_entry_points(built_lib):
     assert torch.equal(new_params["cost_params"]["params"]["Dense_0"]["kernel"],
                        before["cost_params"]["params"]["Dense_0"]["kernel"])            # masked leaves
     assert torch.equal(new_params["mpc_weights"], before["mpc_weights"])
+
+
+def test_dynamics_fit_full_size_finite_difference(built_lib):
+    """C2 dims, 4096 windows of 8 steps, free running: the loss is the sum of per-step terms, and the
+    weight gradient predicts the loss change of a small step along itself (directional finite
+    difference through the kernel's own loss) -- no oracle run needed at this size."""
+    from gan_mpc_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS["C2"], K=1)
+    p = synthetic.planner_params(0, bias_scale=0.1, **cfg)
+    xs, us, ys = _windows(cfg, 7, 4096, 8)
+    g = lambda a: torch.from_numpy(a).cuda()
+    dims = [p["dyn_W"][0].shape[0]] + [w.shape[1] for w in p["dyn_W"]]
+    h = util.make_handle(cfg, p)
+    loss, act, cot = h.dynamics_fit(g(xs), g(us), g(ys), 0.9, False, dims)
+    B = loss.shape[0]
+    dW = [(a @ c.t()) / B for a, c in zip(act, cot)]
+    gn2 = sum(float((w.double() ** 2).sum()) for w in dW)
+    eps = 1e-3 / gn2 ** 0.5
+    p2 = dict(p, dyn_W=[w + eps * d.cpu().numpy() for w, d in zip(p["dyn_W"], dW)])
+    h2 = util.make_handle(cfg, p2)
+    loss2, _, _ = h2.dynamics_fit(g(xs), g(us), g(ys), 0.9, False, dims)
+    fd = (float(loss2.double().mean()) - float(loss.double().mean())) / eps
+    print(f"directional derivative: finite difference {fd:.6e}, gradient norm^2 {gn2:.6e}")
+    assert abs(fd - gn2) < 2e-2 * gn2
+    tf_loss, _, _ = h.dynamics_fit(g(xs[:, :1].copy()), g(us[:, :1].copy()), g(ys[:, :1].copy()), 0.9, True, dims)
+    fr_loss, _, _ = h.dynamics_fit(g(xs[:, :1].copy()), g(us[:, :1].copy()), g(ys[:, :1].copy()), 0.9, False, dims)
+    assert torch.equal(tf_loss, fr_loss)        # a window of one step has nothing to force

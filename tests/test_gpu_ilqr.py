@@ -171,3 +171,26 @@ def test_ilqr_alpha0_below_alpha_min_and_bad_shapes(built_lib):
     hb = util.make_handle(big, p)
     with pytest.raises(_lib.GmpcError, match="shared memory"):
         hb.ilqr(dev(bx0), dev(bU0[:, 0].copy()), dev(bgoal), maxiter=1)
+
+
+def test_ilqr_full_size_properties(built_lib):
+    """BASELINE config C2 at full size (4096 states, n=17, m=6, T=32): properties that need no oracle
+    run -- descent, the returned objective / gradient agree with the first-order kernels evaluated at
+    the returned U (cross-kernel consistency), iteration bounds, bitwise determinism."""
+    from gan_mpc_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS["C2"], K=1)
+    p = synthetic.planner_params(0, **cfg)
+    x0, U0, goal = synthetic.planner_inputs(0, **cfg)
+    h = util.make_handle(cfg, p)
+    dx0, dU0, dgoal = dev(x0), dev(U0[:, 0].copy()), dev(goal)
+    h.set_path("ffma")
+    J0, *_ = h.objective_grad(dx0, dU0, dgoal, want_grad=False, want_X=False)
+    X, U, obj, g, lam, _, it = h.ilqr(dx0, dU0, dgoal, maxiter=3)
+    assert bool((obj <= J0 * (1 + 1e-5)).all()) and float((obj / J0).median()) < 0.9
+    assert int(it.min()) >= 0 and int(it.max()) <= 3
+    J1, dU1, X1, lam1 = h.objective_grad(dx0, U.contiguous(), dgoal, want_lam=True)
+    assert util.rel_rows(X, X1.double().cpu()) < 1e-5
+    assert util.rel_rows(obj[:, None], J1.double().cpu()[:, None]) < 1e-5
+    util.assert_rows_close("gradient vs BPTT kernel", g, dU1.double().cpu(), tol=1e-3, outlier_frac=0.02, cap=1.0)
+    again = h.ilqr(dx0, dU0, dgoal, maxiter=3)
+    assert torch.equal(again[1], U) and torch.equal(again[2], obj) and torch.equal(again[6], it)
