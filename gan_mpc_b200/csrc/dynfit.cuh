@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dynfit_kernel(const __grid_consta
     WeightPipe wp;
     wp.p = 0; wp.li = 0; wp.ci = 0; wp.issued = 0; wp.consumed = 0;
     wp.sched = SCHED_FIT;
+    wp.na = wp.nb = 0;
     wp.kind = DIR_DYN_F;
     __syncthreads();
 #pragma unroll

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -532,6 +533,7 @@ static int ilqr_launch(gmpc_handle* h, int64_t B, const float* x0, const float* 
   Q.ws = h->d_ilqr_ws;
   Q.ws_stride = (long long)WL.total;
   Q.stats = h->d_ilqr_stats;
+  Q.pack_small = getenv("GMPC_ILQR_NO_PACK") ? 0 : 1;   // experiment switch: lane = trajectory everywhere
   if (bl) {
     Q.desired = bl->desired; Q.bl_loss = bl->loss; Q.bl_B = bl->Bvec; Q.bl_hess = bl->hess;
     Q.bl_H = bl->H; Q.bl_dxT = bl->dxT; Q.bl_gw = bl->gw; Q.bl_V = bl->V;

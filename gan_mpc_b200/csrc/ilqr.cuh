@@ -48,6 +48,7 @@ struct IlqrParams {
   float* bl_H;          // [B,T,m]    solve(hessian, B)
   float* bl_dxT;        // [B,n]      d x_T / dU . H  (tangent of the terminal state along H)
   float* bl_gw;         // [B,3]      d (H . grad_U J) / d mpc_weights (raw, pre-sigmoid)
+  int pack_small;       // small tiles pack (trajectory, Jacobian row) pairs into the lanes
   int bl_generic;       // `desired` holds d loss / d X [B,T+1,n] of an arbitrary loss (bl_loss unused)
   const float* bl_V;    // [B,T,m]    nullable: cost_vjp's direction V given by the caller -- used instead
                         //            of H (no Hessian, no solve; bl_H returns V)
@@ -251,13 +252,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
     bool init = true;
     float alpha = Q.alpha0;
     WeightPipe wp;
+    wp.na = n; wp.nb = fout;
+    const int nv = (int)((P.NQ - q0) < (long long)RT ? (P.NQ - q0) : (long long)RT);  // trajectories in this tile
+    const bool packed = Q.pack_small && nv * n <= RT && nv * fout <= RT;
+    int NA = 0;  // number of line-search step sizes alpha_0 2^-j > alpha_min
+    for (float aa = Q.alpha0; aa > Q.alpha_min && NA < 64; aa *= 0.5f) ++NA;
+    const bool pls_ok = Q.pack_small && NA >= 1 && nv * NA <= RT;
+    if (packed) {  // lanes that carry no trajectory are never written by the packed linearisation
+      for (int e = tid; e < T * n * n * RT; e += NTHREADS) if (r >= nv) wsA[e] = 0.f;
+      for (int e = tid; e < T * n * m * RT; e += NTHREADS) if (r >= nv) wsB[e] = 0.f;
+      for (int e = tid; e < fout * n * RT; e += NTHREADS) if (r >= nv) wsJf[e] = 0.f;
+    }
 
 #pragma unroll 1
     while (true) {
       // ================================================================ rollout (plain or feedback)
-      // trajax rollout (first pass) / ddp_rollout: u = U[t] + alpha k[t] + K[t] (x_new[t] - X[t])
+      // trajax rollout (first pass) / ddp_rollout: u = U[t] + alpha k[t] + K[t] (x_new[t] - X[t]).
+      // Full tiles: lane = trajectory, one rollout per line-search trial.  Tiny tiles (nv NA <= 32, NA =
+      // number of step sizes alpha_0 2^-j above alpha_min; the single state of an acting call): lane =
+      // (trajectory, trial) pair, ONE rollout evaluates every step size and the decision takes the
+      // first strict decrease in trial order -- what the sequential backtracking loop would return.
       float* Xd = init ? wsX : wsXn;
       float* Ud = init ? wsU : wsUn;
+      const bool pls = !init && pls_ok;
+      const int lt = pls ? (r < nv * NA ? r / NA : -1) : r;   // trajectory whose plan lane r rolls out
+      float al = alpha;                                       // this lane's step size
+      if (pls) {
+        al = Q.alpha0;
+        for (int j = (r < nv * NA ? r % NA : 0); j > 0; --j) al *= 0.5f;
+      }
       wp.p = 0; wp.li = 0; wp.ci = 0; wp.issued = 0; wp.consumed = 0;
       wp.sched = SCHED_ROLL;
       wp.kind = DIR_DYN_F;
@@ -265,7 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
 #pragma unroll
       for (int s = 0; s < NSTAGE - 1; ++s) pipe_issue(P, wp, ring, tid);
       for (int i = tid; i < n * RT; i += NTHREADS) {
-        const float v = wsX[i];
+        const float v = lt < 0 ? 0.f : wsX[(i & ~31) + lt];
         q_s[i] = v;
         if (!init) Xd[i] = v;
       }
@@ -276,26 +299,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       for (int t = 0; t < T; ++t) {
         for (int e = tid; e < m * RT; e += NTHREADS) {
           const int a = e >> 5;
-          float u = wsU[(t * m + a) * RT + r];
-          if (!init) {
-            float s = alpha * wsk[(t * m + a) * RT + r];
-            const float* Kr = wsK + (size_t)((t * m + a) * n) * RT + r;
-            const float* Xr = wsX + (size_t)(t * n) * RT + r;
+          float u = lt < 0 ? 0.f : wsU[(t * m + a) * RT + lt];
+          if (!init && lt >= 0) {
+            float s = al * wsk[(t * m + a) * RT + lt];
+            const float* Kr = wsK + (size_t)((t * m + a) * n) * RT + lt;
+            const float* Xr = wsX + (size_t)(t * n) * RT + lt;
             for (int j = 0; j < n; ++j) s = fmaf(Kr[j * RT], q_s[j * RT + r] - Xr[j * RT], s);
             u += s;
-            Ud[(t * m + a) * RT + r] = u;
           }
+          if (!init) Ud[(t * m + a) * RT + r] = u;
           q_s[(n + a) * RT + r] = u;
         }
         __syncthreads();
-        if (tid < RT) {  // cost/cost_model.py:20-28 staging cost at (x_t, u_t, goal_t)
+        if (tid < RT && lt >= 0) {  // cost/cost_model.py:20-28 staging cost at (x_t, u_t, goal_t)
           float uu = 0.f, dd = 0.f;
           for (int j = 0; j < m; ++j) {
             const float u = q_s[(n + j) * RT + r];
             uu = fmaf(u, u, uu);
           }
           for (int i = 0; i < n; ++i) {
-            const float d = q_s[i * RT + r] - wsG[(t * n + i) * RT + r];
+            const float d = q_s[i * RT + r] - wsG[(t * n + i) * RT + lt];
             dd = fmaf(d, d, dd);
           }
           Jr += w0 * (sqrtf(uu + a2) - ALPHA) + w1 * (sqrtf(dd + a2) - ALPHA);
@@ -314,19 +337,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
           yy = fmaf(y, y, yy);
         }
         Jr += w2 * yy;  // cost/cost_model.py:30-31
-        // ---------------------------------------------------------------- line_search_ddp decision
+        objn_s[r] = Jr;
+      }
+      __syncthreads();
+      // ---------------------------------------------------------------- line_search_ddp decision
+      if (tid < RT) {
         if (init) {
           obj_s[r] = Jr;
-        } else if (srch_s[r]) {
+        } else if (srch_s[r] && !pls) {
           const float o = obj_s[r];
           const float oc = (o != o) ? INFINITY : o;  // NaN objective -> inf
           const float on = (Jr != Jr) ? oc : Jr;     // NaN trial -> rejected
           const bool better = on < oc;               // strict decrease only
-          acc_s[r] = better ? 1 : 0;
+          acc_s[r] = better ? r + 1 : 0;             // source lane + 1 of the accepted trial
           if (better) obj_s[r] = on;
           const float ar = 0.5f * alpha;
           alpha_s[r] = ar;
           srch_s[r] = (!better && ar > Q.alpha_min) ? 1 : 0;
+        } else if (srch_s[r] && pls && r < nv) {
+          const float o = obj_s[r];
+          const float oc = (o != o) ? INFINITY : o;
+          float aj = Q.alpha0;
+          int src = 0;
+          for (int j = 0; j < NA; ++j, aj *= 0.5f) {  // trials in backtracking order
+            const float v = objn_s[r * NA + j];
+            const float on = (v != v) ? oc : v;
+            alpha_s[r] = 0.5f * aj;
+            if (on < oc) { src = r * NA + j + 1; obj_s[r] = on; break; }
+          }
+          acc_s[r] = src;
+          srch_s[r] = 0;
         } else {
           acc_s[r] = 0;
         }
@@ -334,9 +374,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       __syncthreads();
       if (!init) {
         for (int e = tid; e < (T + 1) * n * RT; e += NTHREADS)
-          if (acc_s[r]) wsX[e] = wsXn[e];
+          if (acc_s[r]) wsX[e] = wsXn[(e & ~31) + acc_s[r] - 1];
         for (int e = tid; e < T * m * RT; e += NTHREADS)
-          if (acc_s[r]) wsU[e] = wsUn[e];
+          if (acc_s[r]) wsU[e] = wsUn[(e & ~31) + acc_s[r] - 1];
         const int more = __syncthreads_or(tid < RT && srch_s[r]);
         if (more) {
           alpha *= 0.5f;
@@ -345,46 +385,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       }
 
       // ================================================================ linearize (get_lqr_params)
+      // Full tiles: lane = trajectory, one adjoint pass per Jacobian row (n per step, fout for the cost
+      // MLP).  Small tiles (nv trajectories with nv n <= 32 and nv fout <= 32, e.g. the single state of
+      // an acting call): lane = (trajectory, row) pair, so ONE adjoint pass yields the whole Jacobian.
+      // Per lane the arithmetic is the same sequence either way (results are bitwise identical).
+      const int nbd = packed ? 1 : n, nbc = packed ? 1 : fout;
       wp.p = 0; wp.li = 0; wp.ci = 0; wp.issued = 0; wp.consumed = 0;
       wp.sched = SCHED_LIN;
+      wp.na = nbd; wp.nb = nbc;
       wp.kind = DIR_DYN_F;
       __syncthreads();
 #pragma unroll
       for (int s = 0; s < NSTAGE - 1; ++s) pipe_issue(P, wp, ring, tid);
+      const int lr_d = packed ? (r < nv * n ? r / n : -1) : r;      // trajectory whose data lane r carries
+      const int li_d = packed ? (r < nv * n ? r % n : -1) : 0;      // Jacobian row lane r is seeded with
+      const int lr_c = packed ? (r < nv * fout ? r / fout : -1) : r;
+      const int li_c = packed ? (r < nv * fout ? r % fout : -1) : 0;
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
         for (int e = tid; e < (n + m) * RT; e += NTHREADS) {
           const int row = e >> 5;
-          q_s[e] = row < n ? wsX[(t * n + row) * RT + r] : wsU[(t * m + row - n) * RT + r];
+          q_s[e] = lr_d < 0 ? 0.f
+                            : (row < n ? wsX[(t * n + row) * RT + lr_d] : wsU[(t * m + row - n) * RT + lr_d]);
         }
         __syncthreads();
         mlp_forward<MAXT>(P, P.dir[DIR_DYN_F], q_s, dq_s, 0, nullptr, dynMask, bufA, bufB, ring, wp, tid);
 #pragma unroll 1
-        for (int i = 0; i < n; ++i) {
+        for (int i = 0; i < nbd; ++i) {
           __syncthreads();
-          for (int e = tid; e < s4 * RT; e += NTHREADS) seed_s[e] = ((e >> 5) == i) ? 1.f : 0.f;
+          const int row_seed = packed ? li_d : i;
+          for (int e = tid; e < s4 * RT; e += NTHREADS) seed_s[e] = ((e >> 5) == row_seed) ? 1.f : 0.f;
           mlp_backward<MAXT>(P, P.dir[DIR_DYN_B], seed_s, dq_s, dynMask, bufA, bufB, ring, wp, tid);
           __syncthreads();
-          for (int e = tid; e < (n + m) * RT; e += NTHREADS) {
-            const int j = e >> 5;
-            const float v = dq_s[e];
-            if (j < n) wsA[(size_t)((t * n + i) * n + j) * RT + r] = v + (i == j ? 1.f : 0.f);
-            else wsB[(size_t)((t * n + i) * m + (j - n)) * RT + r] = v;
+          if (lr_d >= 0) {
+            const int ii = packed ? li_d : i;
+            for (int e = tid; e < (n + m) * RT; e += NTHREADS) {
+              const int j = e >> 5;
+              const float v = dq_s[e];
+              if (j < n) wsA[(size_t)((t * n + ii) * n + j) * RT + lr_d] = v + (ii == j ? 1.f : 0.f);
+              else wsB[(size_t)((t * n + ii) * m + (j - n)) * RT + lr_d] = v;
+            }
           }
         }
         __syncthreads();
       }
-      for (int e = tid; e < n * RT; e += NTHREADS) q_s[e] = wsX[(size_t)T * n * RT + e];
+      for (int e = tid; e < n * RT; e += NTHREADS) q_s[e] = lr_c < 0 ? 0.f : wsX[(size_t)T * n * RT + (e & ~31) + lr_c];
       __syncthreads();
       mlp_forward<MAXT>(P, P.dir[DIR_COST_F], q_s, y_s, 0, nullptr, costMask, bufA, bufB, ring, wp, tid);
 #pragma unroll 1
-      for (int o = 0; o < fout; ++o) {
+      for (int o = 0; o < nbc; ++o) {
         __syncthreads();
-        for (int e = tid; e < s4 * RT; e += NTHREADS) seed_s[e] = ((e >> 5) == o) ? 1.f : 0.f;
+        const int row_seed = packed ? li_c : o;
+        for (int e = tid; e < s4 * RT; e += NTHREADS) seed_s[e] = ((e >> 5) == row_seed) ? 1.f : 0.f;
         mlp_backward<MAXT>(P, P.dir[DIR_COST_B], seed_s, dq_s, costMask, bufA, bufB, ring, wp, tid);
         __syncthreads();
-        for (int e = tid; e < n * RT; e += NTHREADS) wsJf[(size_t)o * n * RT + e] = dq_s[e];
+        if (lr_c >= 0) {
+          const int oo = packed ? li_c : o;
+          for (int e = tid; e < n * RT; e += NTHREADS) wsJf[(size_t)(oo * n + (e >> 5)) * RT + lr_c] = dq_s[e];
+        }
       }
+      const int yl = packed ? r * fout : r;  // a lane that holds y of trajectory r (r < nv when packed)
       cp_async_wait<0>();
       __syncthreads();
       // terminal quadratisation: Q_T = 2 w2 Jf^T Jf, q_T = 2 w2 Jf^T y
@@ -397,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       for (int e = tid; e < n * RT; e += NTHREADS) {
         const int i = e >> 5;
         float s = 0.f;
-        for (int o = 0; o < fout; ++o) s = fmaf(wsJf[(o * n + i) * RT + r], y_s[o * RT + r], s);
+        for (int o = 0; o < fout; ++o) s = fmaf(wsJf[(o * n + i) * RT + r], y_s[o * RT + (yl < RT ? yl : r)], s);
         s *= 2.f * w2;
         wsqT[e] = s;
         p_s[e] = s;

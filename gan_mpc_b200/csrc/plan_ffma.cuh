@@ -25,11 +25,13 @@ struct WeightPipe {
   int kind;       // DIR_* of pass p
   int issued, consumed;
   int sched;      // SCHED_*: which pass schedule the prefetch cursor follows
+  int na, nb;     // SCHED_LIN: adjoint passes per dynamics step / after the cost MLP forward
 };
 
 // Pass schedules: the planner's (pass_kind), and the two phases of the iLQR kernel (ilqr.cuh):
 // SCHED_LIN  = per step one forward pass + n adjoint passes (the Jacobian rows), then the cost MLP
-//              forward + fout adjoint passes;  SCHED_ROLL = T forward passes + the cost MLP;
+//              forward + fout adjoint passes (n / fout become 1 when a small tile packs the
+//              (trajectory, seed) pairs into the 32 lanes);  SCHED_ROLL = T forward passes + the cost MLP;
 // SCHED_FIT  = P.iters forward passes then P.iters adjoint passes of the dynamics MLP (dynfit.cuh).
 enum { SCHED_PLAN = 0, SCHED_LIN = 1, SCHED_ROLL = 2, SCHED_FIT = 3 };
 
@@ -52,13 +54,14 @@ __device__ __forceinline__ int pass_kind(const PlanParams& P, int p) {
   return DIR_END;
 }
 
-__device__ __forceinline__ int sched_kind(const PlanParams& P, int sched, int p) {
+__device__ __forceinline__ int sched_kind(const PlanParams& P, const WeightPipe& w, int p) {
+  const int sched = w.sched;
   if (sched == SCHED_PLAN) return pass_kind(P, p);
   if (sched == SCHED_LIN) {
-    const int per = P.n + 1, nd = P.T * per;
+    const int per = w.na + 1, nd = P.T * per;
     if (p < nd) return (p % per == 0) ? DIR_DYN_F : DIR_DYN_B;
     if (p == nd) return DIR_COST_F;
-    return (p - nd <= P.fout) ? DIR_COST_B : DIR_END;
+    return (p - nd <= w.nb) ? DIR_COST_B : DIR_END;
   }
   if (sched == SCHED_FIT)  // dynfit.cuh: P.iters forward passes then P.iters adjoint passes
     return p < P.iters ? DIR_DYN_F : (p < 2 * P.iters ? DIR_DYN_B : DIR_END);
@@ -82,7 +85,7 @@ __device__ __forceinline__ void pipe_issue(const PlanParams& P, WeightPipe& w, f
       if (++w.li == D.L) {
         w.li = 0;
         ++w.p;
-        w.kind = sched_kind(P, w.sched, w.p);
+        w.kind = sched_kind(P, w, w.p);
       }
     }
   }
