@@ -226,3 +226,29 @@ def test_bilevel_solve_residual_at_c2_dims(built_lib):
     o2 = h.bilevel_l2(dev(x0), o["U"], dev(goal), dev(desired), maxiter=0, V=o["H"].contiguous())
     assert util.rel_rows(o2["dxT"], o["dxT"].double().cpu()) < 1e-4
     assert util.rel_rows(o2["grad_mpc_weights"], o["grad_mpc_weights"].double().cpu()) < 1e-4
+
+
+def test_gan_generator_training_through_cost_trainer(built_lib):
+    """The GAN's generator half (gan/runner.py:161 calls cost_trainer.train with the JS policy):
+    loss_and_grad = bilevel gradient of the generator loss; cost side moves, critic does not."""
+    from gan_mpc_b200.gan import runner as gan_runner
+    config = utils.get_config(os.path.join(load_config.CONFIG_DIR, "gan_hyperparameters.yaml"))
+    x_size, u_size, D = 3, 1, 40
+    policy, _, _ = gan_runner.get_policy(config, x_size, u_size)
+    params = gan_runner.get_params(policy, config, x_size, u_size)
+    policy.trajax_ilqr_kwargs = dict(policy.trajax_ilqr_kwargs, maxiter=3)
+    policy.planner_kwargs["method"] = "ilqr"
+    gen = torch.Generator().manual_seed(31)
+    T = config.mpc.horizon
+    X = torch.randn(D, 2, x_size, generator=gen).cuda()
+    Y = (X[:, -1:, :] + 0.1 * torch.cumsum(torch.randn(D, T + 1, x_size, generator=gen).cuda(), 1)).contiguous()
+    copt, opt_state = gan_runner.get_optimizer(params, config.mpc.train.cost.no_grads, lr=1e-3)
+    assert "critic_params" not in copt.trained and "cost_params" in copt.trained
+    before = utils.tree_clone(params)
+    new_params, opt_state, tr, te, minutes = cost_trainer.train(
+        (policy, copt), opt_state, params, ((X[:32], Y[:32]), (X[32:], Y[32:])), num_updates=1, batch_size=16,
+        polyak_factor=0.9, key=0, id=1)
+    assert len(tr) == 1 and len(te) == 1 and np.isfinite(tr[0]) and np.isfinite(te[0])
+    k = lambda p: p["cost_params"]["params"]["Dense_1"]["kernel"]
+    assert float((k(new_params) - k(before)).abs().max()) > 0
+    assert torch.allclose(policy.critic_flat(new_params), policy.critic_flat(before), rtol=1e-6, atol=0)
