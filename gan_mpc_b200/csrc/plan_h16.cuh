@@ -320,7 +320,18 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
     // running 32-bit words, the split at k-step 8 (operand part 1) is hoisted out of the loop, the
     // pass schedule is walked without divisions, timers exist only in the TIMED instantiation.
     const int which = (warp == 1) ? 0 : 1;
-    if (elect_one()) {
+    // GMPC_H16_WARP_ISSUER (experiment): the whole warp walks the schedule and computes the descriptors
+    // (warp-uniform values can then live in uniform registers, no R2UR in front of every MMA); only the
+    // elected lane issues.  Default: the elected lane runs the role alone.
+    const bool leader = elect_one();
+#ifdef GMPC_H16_WARP_ISSUER
+    const bool run_role = true;
+#define H16_LEAD(stmt) do { if (leader) { stmt; } } while (0)
+#else
+    const bool run_role = leader;
+#define H16_LEAD(stmt) do { stmt; } while (0)
+#endif
+    if (run_role) {
       uint32_t act_ph0 = 0, act_ph1 = 0, lc = 0;
       long long t_act = 0, t_full = 0, tt = 0, t_actl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_iss1 = 0, n_iss1 = 0, tl0 = 0, t_b0a = 0, t_b0b = 0, t_p1 = 0, t_b1 = 0, tl1 = 0;
       const uint32_t idesc = which == 0 ? h16_idesc(2 * H_NB, 0, 1) : h16_idesc(H_NB, 0, 1);
@@ -338,7 +349,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
       // loop invariants the compiler would otherwise re-derive from special registers / the
       // constant bank inside every chunk (S2UR SR_CgaSize -> UIMAD -> LDCU chains in the SASS)
       uint32_t NSr = (uint32_t)NS, mc = C > 1 ? 1u : 0u, cmask_r = cmask, full_r = full_a, alo0_r = a_lo0;
+#ifndef GMPC_H16_WARP_ISSUER
       asm volatile("" : "+r"(NSr), "+r"(mc), "+r"(cmask_r), "+r"(full_r), "+r"(alo0_r));
+#endif
       // per-block A geometry (set by the layer loop): low-word addend that selects this issuer's unit
       // and carries the LBO field, and the descriptor advance from the first to the second k-step
       uint32_t a_blk = 0, a_k2 = 0;
@@ -371,12 +384,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
         for (int u = 0; u < U; ++u) {
           const uint64_t ad = ((uint64_t)a_hi << 32) | (au[u] + a_blk);
           const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + u * 2 * KS);
-          umma_f16(d0, ad, bd, idesc, (u == 0) ? acc : 1u);
-          if (u + 1 < U || NKL == 2) umma_f16(d0, ad + a_k2, bd + KS, idesc, 1u);  // second k-step of the group
+          H16_LEAD(umma_f16(d0, ad, bd, idesc, (u == 0) ? acc : 1u));
+          if (u + 1 < U || NKL == 2) H16_LEAD(umma_f16(d0, ad + a_k2, bd + KS, idesc, 1u));  // second k-step of the group
           if (mc)
-            umma_commit_mc_a(fbu[u] + EMPTY_OFF, (uint16_t)cmask_r);
+            H16_LEAD(umma_commit_mc_a(fbu[u] + EMPTY_OFF, (uint16_t)cmask_r));
           else
-            umma_commit_a(fbu[u] + EMPTY_OFF);
+            H16_LEAD(umma_commit_a(fbu[u] + EMPTY_OFF));
         }
       };
       using I1 = std::integral_constant<int, 1>;
@@ -405,7 +418,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             if (!live) {  // no tile this round: keep the cluster's ring protocol going
               for (int i = 0; i < nblk * ngrp; ++i) {
                 mbar_wait_a(fb, ph);
-                umma_commit_mc_a(fb + EMPTY_OFF, cmask);
+                H16_LEAD(umma_commit_mc_a(fb + EMPTY_OFF, cmask));
                 fb += 8;
                 a_lo += (H_GROUP_BYTES >> 4);
                 if (--left == 0) { fb = full_a; a_lo = a_lo0; left = (uint32_t)NS; ph ^= 1; }
@@ -434,7 +447,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
                 set_block(Y.rows[b]);
                 issue(0, ngrp, odd, d_base + b * H_TMEM_BLK, b_lo0, b_hi, 0u);
               }
-              umma_commit_a(acc_a);
+              H16_LEAD(umma_commit_a(acc_a));
               continue;
             }
             set_block(Y.rows[0]);
@@ -453,17 +466,17 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
             } else {
               issue(0, ngrp, odd, d_base, b_lo0, b_hi, 0u);
             }
-            umma_commit_a(acc_a);
+            H16_LEAD(umma_commit_a(acc_a));
             if (nblk > 1) {
               set_block(Y.rows[1]);
               issue(0, ngrp, odd, d_base + H_TMEM_BLK, b_lo0, b_hi, 0u);
-              umma_commit_a(acc_a + 8);
+              H16_LEAD(umma_commit_a(acc_a + 8));
             }
             if (probe) { const long long t1 = clock64(); t_b1 += t1 - tl1; t_iss1 += t1 - tl0; ++n_iss1; }
           }
         }
       }
-      if (TIMED) {
+      if (TIMED && leader) {
         P.dbg[blockIdx.x * 16 + 0 + 9 * which] = t_act;
         P.dbg[blockIdx.x * 16 + 1 + 9 * which] = t_full;
         if (blockIdx.x == 0)
@@ -474,6 +487,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
                  t_actl[0], t_actl[1], t_actl[2], t_actl[3], t_actl[4], t_actl[5], t_actl[6], t_actl[7]);
       }
     }
+#undef H16_LEAD
     __syncwarp();
   } else {
     // ================================================================== epilogue / elementwise
