@@ -59,6 +59,8 @@ _SIGS = {
                                  _f, _f, _f, C.c_void_p]),
     "gmpc_ilqr": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.POINTER(IlqrOptions), _f, _f, _f,
                             _f, _f, _f, _f, _f, C.c_void_p]),
+    "gmpc_ilqr_host": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.POINTER(IlqrOptions)] + [_f] * 6
+                       + [C.c_void_p]),
     "gmpc_bilevel_l2": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, _f, C.POINTER(IlqrOptions)] + [_f] * 12
                         + [C.c_void_p]),
     "gmpc_bilevel_tail": (C.c_int, [C.c_void_p, C.c_int64] + [_f] * 9 + [C.c_void_p]),
@@ -296,6 +298,26 @@ class Handle:
             _ptr(goal, device=dev, name="goal"), C.byref(opt), _ptr(X), _ptr(U), _ptr(obj),
             _ptr(grad), _ptr(lam), _ptr(it, dtype=torch.int32), _ptr(A), _ptr(Bm), _stream(dev)))
         return X, U, obj, grad, lam, ((A, Bm) if want_lqr else None), it
+
+    def ilqr_host(self, x0, U0, goal, maxiter=100, grad_norm_threshold=1e-4, alpha_0=1.0,
+                  alpha_min=0.00005):
+        """gmpc_ilqr_host: HOST (cpu) tensors in and out, synchronous: (X, U, obj, gradient, adjoints,
+        None, iteration)."""
+        cpu = torch.device("cpu")
+        B = x0.shape[0]
+        f = dict(dtype=torch.float32)
+        X = torch.empty(B, self.T + 1, self.n, **f)
+        U = torch.empty(B, self.T, self.m, **f)
+        obj = torch.empty(B, **f)
+        grad = torch.empty(B, self.T, self.m, **f)
+        lam = torch.empty(B, self.T + 1, self.n, **f)
+        it = torch.empty(B, dtype=torch.int32)
+        opt = IlqrOptions(int(maxiter), float(grad_norm_threshold), float(alpha_0), float(alpha_min))
+        _check(self.lib.gmpc_ilqr_host(
+            self._h, B, _ptr(x0, device=cpu, name="x0"), _ptr(U0, device=cpu, name="U0"),
+            _ptr(goal, device=cpu, name="goal"), C.byref(opt), _ptr(X), _ptr(U), _ptr(obj), _ptr(grad),
+            _ptr(lam), _ptr(it, dtype=torch.int32), _stream(self.device)))
+        return X, U, obj, grad, lam, None, it
 
     def bilevel_l2(self, x0, U0, goal, desired, maxiter=100, grad_norm_threshold=1e-4, alpha_0=1.0,
                    alpha_min=0.00005, want_hessian=False, V=None, **unsupported):

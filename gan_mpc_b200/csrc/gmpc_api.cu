@@ -557,6 +557,48 @@ extern "C" int gmpc_ilqr(gmpc_handle* h, int64_t B, const float* x0, const float
                      nullptr, stream);
 }
 
+// gmpc_ilqr with HOST buffers: the end-to-end call of a caller that is not GPU aware (acting loop of
+// utils.run_dm_policy: one state in, one plan out).  Synchronises `stream` before returning.
+extern "C" int gmpc_ilqr_host(gmpc_handle* h, int64_t B, const float* x0_host, const float* U0_host,
+                              const float* goal_host, const gmpc_ilqr_options* opt, float* X_host,
+                              float* U_host, float* obj_host, float* gradient_host,
+                              float* adjoints_host, int32_t* iteration_host, void* stream) {
+  int rc = check_ready(h, "gmpc_ilqr_host", B);
+  if (rc) return rc;
+  if (B == 0) return GMPC_OK;
+  if (!x0_host || !U0_host || !goal_host || !opt || !X_host || !U_host || !obj_host)
+    return fail(GMPC_E_ARG, "gmpc_ilqr_host: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const gmpc_config& c = h->cfg;
+  const size_t ub = (size_t)B * c.T * c.m, xb = (size_t)B * (c.T + 1) * c.n, x0b = (size_t)B * c.n;
+  const size_t tot = x0b + 2 * ub + 2 * xb + B /*obj*/ + ub /*grad*/ + xb /*adjoints*/ + B /*iteration*/;
+  rc = grow(&h->d_stage, &h->stage_bytes, tot * sizeof(float));
+  if (rc) return rc;
+  float* d_x0 = (float*)h->d_stage;
+  float* d_U0 = d_x0 + x0b;
+  float* d_goal = d_U0 + ub;
+  float* d_X = d_goal + xb;
+  float* d_U = d_X + xb;
+  float* d_obj = d_U + ub;
+  float* d_g = d_obj + B;
+  float* d_lam = d_g + ub;
+  int32_t* d_it = (int32_t*)(d_lam + xb);
+  CU_CHECK(cudaMemcpyAsync(d_x0, x0_host, x0b * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_CHECK(cudaMemcpyAsync(d_U0, U0_host, ub * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_CHECK(cudaMemcpyAsync(d_goal, goal_host, xb * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = gmpc_ilqr(h, B, d_x0, d_U0, d_goal, opt, d_X, d_U, d_obj, gradient_host ? d_g : nullptr,
+                 adjoints_host ? d_lam : nullptr, iteration_host ? d_it : nullptr, nullptr, nullptr, st);
+  if (rc) return rc;
+  CU_CHECK(cudaMemcpyAsync(X_host, d_X, xb * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaMemcpyAsync(U_host, d_U, ub * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaMemcpyAsync(obj_host, d_obj, B * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (gradient_host) CU_CHECK(cudaMemcpyAsync(gradient_host, d_g, ub * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (adjoints_host) CU_CHECK(cudaMemcpyAsync(adjoints_host, d_lam, xb * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (iteration_host) CU_CHECK(cudaMemcpyAsync(iteration_host, d_it, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaStreamSynchronize(st));
+  return GMPC_OK;
+}
+
 // bilevel_optimization (policy/optimizers.py:34-75) for loss = L2MPC.loss: iLQR + the bilevel tail in
 // the same kernel launch.
 extern "C" int gmpc_bilevel_l2(gmpc_handle* h, int64_t B, const float* x0, const float* U0,
@@ -565,6 +607,7 @@ extern "C" int gmpc_bilevel_l2(gmpc_handle* h, int64_t B, const float* x0, const
                                int32_t* iteration, float* loss, float* loss_grad_U, float* hessian,
                                float* H, float* dxT, float* grad_mpc_weights, const float* V,
                                void* stream) {
+  if (h && B == 0) return GMPC_OK;
   if (!desired || !loss || !H || !dxT || !grad_mpc_weights)
     return fail(GMPC_E_ARG, "gmpc_bilevel_l2: null argument");
   if (V && hessian) return fail(GMPC_E_ARG, "gmpc_bilevel_l2: a given direction V skips the Hessian");
@@ -579,6 +622,7 @@ extern "C" int gmpc_bilevel_tail(gmpc_handle* h, int64_t B, const float* x0, con
                                  const float* goal, const float* dLdX, float* loss_grad_U,
                                  float* hessian, float* H, float* dxT, float* grad_mpc_weights,
                                  void* stream) {
+  if (h && B == 0) return GMPC_OK;
   if (!dLdX || !H || !dxT || !grad_mpc_weights) return fail(GMPC_E_ARG, "gmpc_bilevel_tail: null argument");
   int rc = check_ready(h, "gmpc_bilevel_tail", B);
   if (rc) return rc;

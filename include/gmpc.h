@@ -152,6 +152,14 @@ int gmpc_ilqr(gmpc_handle* h, int64_t B, const float* x0, const float* U0, const
               const gmpc_ilqr_options* opt, float* X, float* U, float* obj, float* gradient,
               float* adjoints, int32_t* iteration, float* lqr_A, float* lqr_B, void* stream);
 
+/* Same as gmpc_ilqr with HOST pointers everywhere (pinned or pageable): copies in, solves, copies out
+ * and synchronises `stream` -- the call a non-GPU-aware acting loop binds (EvalMPC.get_optimal_action,
+ * policy/eval.py:126-128, once per environment step).  gradient / adjoints / iteration are nullable. */
+int gmpc_ilqr_host(gmpc_handle* h, int64_t B, const float* x0_host, const float* U0_host,
+                   const float* goal_host, const gmpc_ilqr_options* opt, float* X_host, float* U_host,
+                   float* obj_host, float* gradient_host, float* adjoints_host,
+                   int32_t* iteration_host, void* stream);
+
 /* bilevel_optimization (policy/optimizers.py:34-75) for loss = L2MPC.loss (norm/l2_policy.py:12-18),
  * the per-sample body of BaseMPC.loss_and_grad (policy/base.py:87-128), in the same kernel launch
  * as the iLQR solve it starts with (maxiter = 0 evaluates the tail at U0 itself):

@@ -194,3 +194,21 @@ def test_ilqr_full_size_properties(built_lib):
     util.assert_rows_close("gradient vs BPTT kernel", g, dU1.double().cpu(), tol=1e-3, outlier_frac=0.02, cap=1.0)
     again = h.ilqr(dx0, dU0, dgoal, maxiter=3)
     assert torch.equal(again[1], U) and torch.equal(again[2], obj) and torch.equal(again[6], it)
+
+
+def test_ilqr_host_buffers_and_empty_batch(built_lib):
+    """gmpc_ilqr_host (host pointers, synchronous) returns what the device call returns; B = 0 is a
+    no-op for the iLQR, bilevel, dynamics-fit and expert entry points."""
+    h, op, x0, U0, goal = _setup(util.SMALL, 67, 35)
+    dv = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=4)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    ho = h.ilqr_host(t(x0), t(U0), t(goal), maxiter=4)
+    for i in (0, 1, 2, 3, 4, 6):
+        assert torch.equal(ho[i], dv[i].cpu()), i
+    e = lambda *s: torch.empty(*s, device="cuda")
+    out = h.ilqr(e(0, 3), e(0, 5, 1), e(0, 6, 3), maxiter=3)
+    assert out[1].shape == (0, 5, 1)
+    o = h.bilevel_l2(e(0, 3), e(0, 5, 1), e(0, 6, 3), e(0, 6, 3), maxiter=1)
+    assert o["H"].shape == (0, 5, 1)
+    loss, act, cot = h.dynamics_fit(e(0, 4, 3), e(0, 4, 1), e(0, 4, 3), 0.9, True, [4, 200, 200, 200, 3])
+    assert loss.shape == (0,) and act[0].shape == (4, 0)
