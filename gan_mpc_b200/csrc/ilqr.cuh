@@ -48,6 +48,7 @@ struct IlqrParams {
   float* bl_H;          // [B,T,m]    solve(hessian, B)
   float* bl_dxT;        // [B,n]      d x_T / dU . H  (tangent of the terminal state along H)
   float* bl_gw;         // [B,3]      d (H . grad_U J) / d mpc_weights (raw, pre-sigmoid)
+  int tile_traj;        // trajectories per tile (<= 32)
   int pack_small;       // small tiles pack (trajectory, Jacobian row) pairs into the lanes
   int bl_generic;       // `desired` holds d loss / d X [B,T+1,n] of an arbitrary loss (bl_loss unused)
   const float* bl_V;    // [B,T,m]    nullable: cost_vjp's direction V given by the caller -- used instead
@@ -217,20 +218,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
 
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-    const long long q0 = (long long)tile * RT;
+    const long long q0 = (long long)tile * Q.tile_traj;
+    // trajectories of this tile (lanes r < nv); Q.tile_traj <= 32 is chosen by the host so that a batch
+    // smaller than 32 x SMs still spreads over all SMs (fewer lanes in lock step per tile)
+    const int nv = (int)((P.NQ - q0) < (long long)Q.tile_traj ? (P.NQ - q0) : (long long)Q.tile_traj);
     __syncthreads();
     // ------------------------------------------------------------------ stage the tile
     for (int e = tid; e < RT * n; e += NTHREADS) {
       const int rr = e / n, i = e - rr * n;
       const long long q = q0 + rr;
-      wsX[i * RT + rr] = (q < P.NQ) ? P.x0[q * n + i] : 0.f;
+      wsX[i * RT + rr] = (rr < nv) ? P.x0[q * n + i] : 0.f;
     }
     {
       const int per = (T + 1) * n;
       for (int e = tid; e < RT * per; e += NTHREADS) {
         const int rr = e / per, rest = e - rr * per;
         const long long q = q0 + rr;
-        wsG[rest * RT + rr] = (q < P.NQ) ? P.goal[q * per + rest] : 0.f;
+        wsG[rest * RT + rr] = (rr < nv) ? P.goal[q * per + rest] : 0.f;
       }
     }
     {
@@ -238,11 +242,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       for (int e = tid; e < RT * per; e += NTHREADS) {
         const int rr = e / per, rest = e - rr * per;
         const long long q = q0 + rr;
-        wsU[rest * RT + rr] = (q < P.NQ) ? P.U_in[q * per + rest] : 0.f;
+        wsU[rest * RT + rr] = (rr < nv) ? P.U_in[q * per + rest] : 0.f;
       }
     }
     if (tid < RT) {
-      act_s[r] = (q0 + r < P.NQ) ? 1 : 0;
+      act_s[r] = (r < nv) ? 1 : 0;
       srch_s[r] = 0;
       acc_s[r] = 0;
       it_s[r] = 0;
@@ -253,16 +257,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
     float alpha = Q.alpha0;
     WeightPipe wp;
     wp.na = n; wp.nb = fout;
-    const int nv = (int)((P.NQ - q0) < (long long)RT ? (P.NQ - q0) : (long long)RT);  // trajectories in this tile
-    const bool packed = Q.pack_small && nv * n <= RT && nv * fout <= RT;
+    const bool packed_d = Q.pack_small && nv * n <= RT;     // dynamics Jacobian rows fit the lanes
+    const bool packed_c = Q.pack_small && nv * fout <= RT;  // cost-MLP Jacobian rows fit the lanes
     int NA = 0;  // number of line-search step sizes alpha_0 2^-j > alpha_min
     for (float aa = Q.alpha0; aa > Q.alpha_min && NA < 64; aa *= 0.5f) ++NA;
     const bool pls_ok = Q.pack_small && NA >= 1 && nv * NA <= RT;
-    if (packed) {  // lanes that carry no trajectory are never written by the packed linearisation
+    if (packed_d) {  // lanes that carry no trajectory are never written by the packed linearisation
       for (int e = tid; e < T * n * n * RT; e += NTHREADS) if (r >= nv) wsA[e] = 0.f;
       for (int e = tid; e < T * n * m * RT; e += NTHREADS) if (r >= nv) wsB[e] = 0.f;
-      for (int e = tid; e < fout * n * RT; e += NTHREADS) if (r >= nv) wsJf[e] = 0.f;
     }
+    if (packed_c)
+      for (int e = tid; e < fout * n * RT; e += NTHREADS) if (r >= nv) wsJf[e] = 0.f;
 
 #pragma unroll 1
     while (true) {
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       // MLP).  Small tiles (nv trajectories with nv n <= 32 and nv fout <= 32, e.g. the single state of
       // an acting call): lane = (trajectory, row) pair, so ONE adjoint pass yields the whole Jacobian.
       // Per lane the arithmetic is the same sequence either way (results are bitwise identical).
-      const int nbd = packed ? 1 : n, nbc = packed ? 1 : fout;
+      const int nbd = packed_d ? 1 : n, nbc = packed_c ? 1 : fout;
       wp.p = 0; wp.li = 0; wp.ci = 0; wp.issued = 0; wp.consumed = 0;
       wp.sched = SCHED_LIN;
       wp.na = nbd; wp.nb = nbc;
@@ -397,10 +402,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       __syncthreads();
 #pragma unroll
       for (int s = 0; s < NSTAGE - 1; ++s) pipe_issue(P, wp, ring, tid);
-      const int lr_d = packed ? (r < nv * n ? r / n : -1) : r;      // trajectory whose data lane r carries
-      const int li_d = packed ? (r < nv * n ? r % n : -1) : 0;      // Jacobian row lane r is seeded with
-      const int lr_c = packed ? (r < nv * fout ? r / fout : -1) : r;
-      const int li_c = packed ? (r < nv * fout ? r % fout : -1) : 0;
+      const int lr_d = packed_d ? (r < nv * n ? r / n : -1) : r;      // trajectory whose data lane r carries
+      const int li_d = packed_d ? (r < nv * n ? r % n : -1) : 0;      // Jacobian row lane r is seeded with
+      const int lr_c = packed_c ? (r < nv * fout ? r / fout : -1) : r;
+      const int li_c = packed_c ? (r < nv * fout ? r % fout : -1) : 0;
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
         for (int e = tid; e < (n + m) * RT; e += NTHREADS) {
@@ -413,12 +418,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
 #pragma unroll 1
         for (int i = 0; i < nbd; ++i) {
           __syncthreads();
-          const int row_seed = packed ? li_d : i;
+          const int row_seed = packed_d ? li_d : i;
           for (int e = tid; e < s4 * RT; e += NTHREADS) seed_s[e] = ((e >> 5) == row_seed) ? 1.f : 0.f;
           mlp_backward<MAXT>(P, P.dir[DIR_DYN_B], seed_s, dq_s, dynMask, bufA, bufB, ring, wp, tid);
           __syncthreads();
           if (lr_d >= 0) {
-            const int ii = packed ? li_d : i;
+            const int ii = packed_d ? li_d : i;
             for (int e = tid; e < (n + m) * RT; e += NTHREADS) {
               const int j = e >> 5;
               const float v = dq_s[e];
@@ -435,16 +440,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
 #pragma unroll 1
       for (int o = 0; o < nbc; ++o) {
         __syncthreads();
-        const int row_seed = packed ? li_c : o;
+        const int row_seed = packed_c ? li_c : o;
         for (int e = tid; e < s4 * RT; e += NTHREADS) seed_s[e] = ((e >> 5) == row_seed) ? 1.f : 0.f;
         mlp_backward<MAXT>(P, P.dir[DIR_COST_B], seed_s, dq_s, costMask, bufA, bufB, ring, wp, tid);
         __syncthreads();
         if (lr_c >= 0) {
-          const int oo = packed ? li_c : o;
+          const int oo = packed_c ? li_c : o;
           for (int e = tid; e < n * RT; e += NTHREADS) wsJf[(size_t)(oo * n + (e >> 5)) * RT + lr_c] = dq_s[e];
         }
       }
-      const int yl = packed ? r * fout : r;  // a lane that holds y of trajectory r (r < nv when packed)
+      const int yl = packed_c ? r * fout : r;  // a lane that holds y of trajectory r (r < nv when packed)
       cp_async_wait<0>();
       __syncthreads();
       // terminal quadratisation: Q_T = 2 w2 Jf^T Jf, q_T = 2 w2 Jf^T y
@@ -709,7 +714,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
         for (int e = tid; e < RT * per; e += NTHREADS) {
           const int rr = e / per, rest = e - rr * per;
           const long long q = q0 + rr;
-          wsD[rest * RT + rr] = (q < P.NQ) ? Q.desired[q * per + rest] : 0.f;
+          wsD[rest * RT + rr] = (rr < nv) ? Q.desired[q * per + rest] : 0.f;
         }
       }
       for (int e = tid; e < TM * TM * RT; e += NTHREADS) wsH[e] = 0.f;
@@ -723,7 +728,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
           const float d = wsX[e * RT + r] - wsD[e * RT + r];
           s = fmaf(d, d, s);
         }
-        if (q0 + r < P.NQ) Q.bl_loss[q0 + r] = s / (float)(T + 1);
+        if (r < nv) Q.bl_loss[q0 + r] = s / (float)(T + 1);
       }
       if (!generic) {  // q_t = d loss / d x_t of the L2 loss, in place of the desired states
         __syncthreads();
@@ -760,7 +765,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
         for (int e = tid; e < RT * per; e += NTHREADS) {
           const int rr = e / per, rest = e - rr * per;
           const long long q = q0 + rr;
-          wsR[rest * RT + rr] = (q < P.NQ) ? Q.bl_V[q * per + rest] : 0.f;
+          wsR[rest * RT + rr] = (rr < nv) ? Q.bl_V[q * per + rest] : 0.f;
         }
         __syncthreads();
       } else {
@@ -840,7 +845,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
         for (size_t e = tid; e < RT * per; e += NTHREADS) {
           const size_t rr = e / per, rest = e - rr * per;
           const long long q = q0 + (long long)rr;
-          if (q < P.NQ) Q.bl_hess[q * per + rest] = wsH[rest * RT + rr];
+          if ((int)rr < nv) Q.bl_hess[q * per + rest] = wsH[rest * RT + rr];
         }
         __syncthreads();
       }
@@ -936,7 +941,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
         for (int e = tid; e < n * RT; e += NTHREADS) dx_s[e] = dxn_s[e];
         __syncthreads();
       }
-      if (tid < RT && q0 + r < P.NQ) {
+      if (tid < RT && r < nv) {
         float g2 = 0.f;  // 2 y^T Jf dx_T = q_T . dx_T / w2
         for (int i = 0; i < n; ++i) {
           g2 = fmaf(wsqT[i * RT + r], dx_s[i * RT + r], g2);
@@ -951,7 +956,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
     }
     __syncthreads();
     // ------------------------------------------------------------------ write the tile out
-    if (tid < RT && q0 + r < P.NQ) {
+    if (tid < RT && r < nv) {
       if (P.J_out != nullptr) P.J_out[q0 + r] = obj_s[r];
       if (Q.it_out != nullptr) Q.it_out[q0 + r] = it_s[r];
     }
@@ -967,7 +972,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       for (int e = tid; e < RT * per; e += NTHREADS) {
         const int rr = e / per, rest = e - rr * per;
         const long long q = q0 + rr;
-        if (q < P.NQ) outs[k].dst[q * per + rest] = outs[k].src[(size_t)rest * RT + rr];
+        if (rr < nv) outs[k].dst[q * per + rest] = outs[k].src[(size_t)rest * RT + rr];
       }
     }
   }
