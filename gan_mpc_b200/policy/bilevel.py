@@ -4,36 +4,51 @@ policy/base.py:87-128 of the reference -- over libgmpc's gmpc_bilevel_l2.
 The kernel does the iLQR solve, loss_grad_wrt_control, cost_hessian_wrt_control, the (T m)^2 solve,
 the tangent rollout along H and the mpc_weights part of cost_vjp.  What is left of cost_vjp is the
 derivative of  w2 * d/de ||f(x_T + e dx_T; theta)||^2  w.r.t. the cost-MLP weights theta: one
-forward-over-reverse pass of a 3-layer MLP per sample, assembled here from x_T and dx_T with
-torch.func on the device (plumbing-sized: 2 x the cost MLP's weight count in FLOPs per sample).
+forward-over-reverse pass of a 3-layer MLP per sample, assembled here from x_T and dx_T as a handful of
+batched matmuls on the device (plumbing-sized: a few times the cost MLP's weight count in FLOPs per sample).
 
 Reference quirks kept: the + sign of the high-level gradient, gradients only
 on the cost side of `params` (dynamics / expert / critic leaves are exactly zero)."""
 
 import torch
-from torch.func import grad, jvp, vmap
 
 from gan_mpc_b200.dynamics.nn import dense_stack_lists
 
 
-def _mlp(x, Ws, bs):
-    z = x
-    for W, b in zip(Ws[:-1], bs[:-1]):
-        z = torch.relu(z @ W + b)
-    return z @ Ws[-1] + bs[-1]
-
-
-def _phi(Ws, bs, x, dx):
-    """d/de ||f(x + e dx)||^2 = 2 f(x) . (Jf dx)   (cost/nn.py:23-29)."""
-    y, yd = jvp(lambda xx: _mlp(xx, Ws, bs), (x,), (dx,))
-    return 2.0 * (y * yd).sum()
-
-
-def cost_mlp_mixed_vjp(cost_params, w2, xT, dxT):
-    """per-sample gradients of w2 * _phi w.r.t. the cost MLP leaves: lists of [B, ...] tensors."""
+def cost_mlp_mixed_vjp(cost_params, w2, xT, dxT, reduce=None):
+    """Gradients of  w2 * phi,  phi = d/de ||f(x_T + e dx_T)||^2 = 2 f(x_T) . (Jf dx_T)  (cost/nn.py:23-29),
+    w.r.t. the cost-MLP kernels and biases, by two explicit back-propagations through the ReLU masks:
+    the cotangent 2 (Jf dx) through the primal network (activations a_l) and the cotangent 2 f(x) through
+    the tangent network (tangent activations da_l; linear, no bias):
+        dW_l = a_l (x) c_l + da_l (x) d_l,   db_l = c_l.
+    reduce None: per-sample gradients [B, ...]; "sum" / "mean": reduced over the batch (plain matmuls)."""
     Ws, bs = dense_stack_lists(cost_params)
-    gW, gb = vmap(grad(_phi, argnums=(0, 1)), in_dims=(None, None, 0, 0))(tuple(Ws), tuple(bs), xT, dxT)
-    return [w2 * g for g in gW], [w2 * g for g in gb]
+    L = len(Ws)
+    a, da, masks = [xT], [dxT], []
+    for l in range(L - 1):
+        z = a[-1] @ Ws[l] + bs[l]
+        mk = (z > 0).to(z.dtype)
+        masks.append(mk)
+        a.append(z * mk)
+        da.append((da[-1] @ Ws[l]) * mk)
+    y = a[-1] @ Ws[-1] + bs[-1]
+    dy = da[-1] @ Ws[-1]
+    c, d = 2.0 * w2 * dy, 2.0 * w2 * y        # cotangents of the last layer's output / tangent output
+    gW, gb = [None] * L, [None] * L
+    B = xT.shape[0]
+    for l in range(L - 1, -1, -1):
+        if reduce is None:
+            gW[l] = a[l][:, :, None] * c[:, None, :] + da[l][:, :, None] * d[:, None, :]
+            gb[l] = c
+        else:
+            gW[l] = a[l].t() @ c + da[l].t() @ d
+            gb[l] = c.sum(0)
+            if reduce == "mean":
+                gW[l], gb[l] = gW[l] / B, gb[l] / B
+        if l > 0:
+            c = (c @ Ws[l].t()) * masks[l - 1]
+            d = (d @ Ws[l].t()) * masks[l - 1]
+    return gW, gb
 
 
 def zeros_like_tree(tree, lead=()):
@@ -51,13 +66,13 @@ def high_level_grad_tree(params, out, reduce_mean):
     every leaf keeps a leading batch axis (what vmap of bilevel_optimization returns)."""
     B = out["X"].shape[0]
     w2 = torch.sigmoid(params["mpc_weights"][2])
-    gW, gb = cost_mlp_mixed_vjp(params["cost_params"], w2, out["X"][:, -1].contiguous(), out["dxT"])
+    mode = None if not reduce_mean else ("sum" if reduce_mean == "sum" else "mean")
+    gW, gb = cost_mlp_mixed_vjp(params["cost_params"], w2, out["X"][:, -1].contiguous(), out["dxT"], mode)
     red = ((lambda t: t.sum(0)) if reduce_mean == "sum" else (lambda t: t.mean(0))) if reduce_mean else (lambda t: t)
     lead = () if reduce_mean else (B,)
     tree = {k: zeros_like_tree(v, lead) for k, v in params.items()}
     tree["mpc_weights"] = red(out["grad_mpc_weights"])
-    tree["cost_params"] = {"params": {f"Dense_{i}": {"kernel": red(gW[i]), "bias": red(gb[i])}
-                                      for i in range(len(gW))}}
+    tree["cost_params"] = {"params": {f"Dense_{i}": {"kernel": gW[i], "bias": gb[i]} for i in range(len(gW))}}
     return tree
 
 
