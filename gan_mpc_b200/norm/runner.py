@@ -1,8 +1,9 @@
 """Runner entry points with the reference's names (norm/runner.py:13-177).
 
-get_policy / get_params / get_optimizer are drop-in.  train / run need dm_control, a pre-trained
-expert checkpoint and trajectories.json -- none of which the reference ships -- and drive the
-bilevel cost trainer (next scope row): they keep their signatures and raise."""
+get_policy / get_params / get_optimizer are drop-in.  train / run interleave dm_control episodes with
+the trainers and need a pre-trained expert checkpoint and trajectories.json -- none of which the
+reference ships: they keep their signatures and raise.  Everything they call between two simulator
+episodes is built: cost_trainer.train, dynamics_trainer.train_params, (gan) critic_trainer.train."""
 
 from gan_mpc_b200 import expert, optim, utils
 from gan_mpc_b200.norm import l2_policy
@@ -40,8 +41,9 @@ def get_optimizer(params, masked_vars, lr):
 
 
 def train(*args, **kwargs):
-    raise NotImplementedError("norm.runner.train drives the dm_control simulator and the bilevel "
-                              "cost trainer: outside the B200 hot path (SURVEY.md section 2, #13)")
+    raise NotImplementedError("norm.runner.train drives the dm_control simulator: outside the B200 hot path "
+                              "(SURVEY.md section 2, #13); call cost_trainer.train / dynamics_trainer.train_params "
+                              "on recorded data")
 
 
 def run(config_path, dataset_path=None):
