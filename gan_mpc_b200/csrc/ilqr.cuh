@@ -101,7 +101,7 @@ __host__ __device__ inline IlqrSmem ilqr_smem_layout(int n, int m, int fout, int
   const int mlp = 2 * hpad * RT + NSTAGE * STAGE_FLOATS;
   const int ric = (2 * n * n + 3 * m * n + 2 * m * m + 3 * n + 3 * m + 2) * RT;
   s.un_floats = mlp > ric ? mlp : ric;
-  s.small_floats = (2 * nm4 + s4 + f4 + 11 + 4) * RT + 32;
+  s.small_floats = (2 * nm4 + s4 + f4 + 11 + 4) * RT + 2 * RT;
   s.bytes = sizeof(float) * ((size_t)s.un_floats + s.small_floats);
   return s;
 }
@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
   int* srch_s = act_s + RT;
   int* acc_s = srch_s + RT;
   int* it_s = acc_s + RT;
+  int* slist_s = it_s + RT;           // [32] compacted list of the searching lanes, [32] = their number
   for (int i = tid; i < SL.small_floats; i += NTHREADS) q_s[i] = 0.f;
 
   const float w0 = 1.f / (1.f + expf(-P.mpcw[0]));
@@ -254,14 +255,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       obj_s[r] = 0.f;
     }
     bool init = true;
-    float alpha = Q.alpha0;
+    int j0 = 0;   // line-search trials already done in the current outer iteration
     WeightPipe wp;
     wp.na = n; wp.nb = fout;
     const bool packed_d = Q.pack_small && nv * n <= RT;     // dynamics Jacobian rows fit the lanes
     const bool packed_c = Q.pack_small && nv * fout <= RT;  // cost-MLP Jacobian rows fit the lanes
     int NA = 0;  // number of line-search step sizes alpha_0 2^-j > alpha_min
     for (float aa = Q.alpha0; aa > Q.alpha_min && NA < 64; aa *= 0.5f) ++NA;
-    const bool pls_ok = Q.pack_small && NA >= 1 && nv * NA <= RT;
     if (packed_d) {  // lanes that carry no trajectory are never written by the packed linearisation
       for (int e = tid; e < T * n * n * RT; e += NTHREADS) if (r >= nv) wsA[e] = 0.f;
       for (int e = tid; e < T * n * m * RT; e += NTHREADS) if (r >= nv) wsB[e] = 0.f;
@@ -273,19 +273,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
     while (true) {
       // ================================================================ rollout (plain or feedback)
       // trajax rollout (first pass) / ddp_rollout: u = U[t] + alpha k[t] + K[t] (x_new[t] - X[t]).
-      // Full tiles: lane = trajectory, one rollout per line-search trial.  Tiny tiles (nv NA <= 32, NA =
-      // number of step sizes alpha_0 2^-j above alpha_min; the single state of an acting call): lane =
-      // (trajectory, trial) pair, ONE rollout evaluates every step size and the decision takes the
-      // first strict decrease in trial order -- what the sequential backtracking loop would return.
+      // Line search: the ns lanes still searching are compacted, and each gets G = min(32 / ns, trials
+      // left) lanes that roll out G consecutive step sizes alpha_0 2^-j at once; the decision takes the
+      // first strict decrease in trial order -- what the sequential backtracking loop returns, trial by
+      // trial (G = 1 while every lane searches).  A single state evaluates all 15 step sizes in ONE rollout.
       float* Xd = init ? wsX : wsXn;
       float* Ud = init ? wsU : wsUn;
-      const bool pls = !init && pls_ok;
-      const int lt = pls ? (r < nv * NA ? r / NA : -1) : r;   // trajectory whose plan lane r rolls out
-      float al = alpha;                                       // this lane's step size
-      if (pls) {
-        al = Q.alpha0;
-        for (int j = (r < nv * NA ? r % NA : 0); j > 0; --j) al *= 0.5f;
+      int ns = 0, G = 1;
+      if (!init) {
+        if (tid < RT) {
+          const unsigned mask = __ballot_sync(0xffffffffu, srch_s[r] != 0);
+          if (srch_s[r]) slist_s[__popc(mask & ((1u << r) - 1u))] = r;
+          if (r == 0) slist_s[RT] = __popc(mask);
+        }
+        __syncthreads();
+        ns = slist_s[RT];
+        G = Q.pack_small ? RT / ns : 1;
+        if (G > NA - j0) G = NA - j0;
       }
+      const int lk = init ? r : r / G;                          // searching trajectory this lane works for
+      const int lt = init ? r : (lk < ns ? slist_s[lk] : -1);    // its lane (-1: this lane idles)
+      float al = Q.alpha0;                                      // this lane's step size
+      if (!init)
+        for (int j = j0 + (r % G); j > 0; --j) al *= 0.5f;
       wp.p = 0; wp.li = 0; wp.ci = 0; wp.issued = 0; wp.consumed = 0;
       wp.sched = SCHED_ROLL;
       wp.kind = DIR_DYN_F;
@@ -347,34 +357,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       __syncthreads();
       // ---------------------------------------------------------------- line_search_ddp decision
       if (tid < RT) {
-        if (init) {
-          obj_s[r] = Jr;
-        } else if (srch_s[r] && !pls) {
-          const float o = obj_s[r];
-          const float oc = (o != o) ? INFINITY : o;  // NaN objective -> inf
-          const float on = (Jr != Jr) ? oc : Jr;     // NaN trial -> rejected
-          const bool better = on < oc;               // strict decrease only
-          acc_s[r] = better ? r + 1 : 0;             // source lane + 1 of the accepted trial
-          if (better) obj_s[r] = on;
-          const float ar = 0.5f * alpha;
-          alpha_s[r] = ar;
-          srch_s[r] = (!better && ar > Q.alpha_min) ? 1 : 0;
-        } else if (srch_s[r] && pls && r < nv) {
-          const float o = obj_s[r];
-          const float oc = (o != o) ? INFINITY : o;
-          float aj = Q.alpha0;
-          int src = 0;
-          for (int j = 0; j < NA; ++j, aj *= 0.5f) {  // trials in backtracking order
-            const float v = objn_s[r * NA + j];
-            const float on = (v != v) ? oc : v;
-            alpha_s[r] = 0.5f * aj;
-            if (on < oc) { src = r * NA + j + 1; obj_s[r] = on; break; }
-          }
-          acc_s[r] = src;
-          srch_s[r] = 0;
-        } else {
-          acc_s[r] = 0;
+        if (init) obj_s[r] = Jr;
+        acc_s[r] = 0;
+      }
+      __syncthreads();
+      if (!init && tid < ns) {  // thread k decides for the k-th searching trajectory
+        const int tl = slist_s[tid];
+        const float o = obj_s[tl];
+        const float oc = (o != o) ? INFINITY : o;  // NaN objective -> inf
+        float aj = Q.alpha0;
+        for (int j = j0; j > 0; --j) aj *= 0.5f;
+        int src = 0;
+        float ar = 0.f;
+        for (int jj = 0; jj < G; ++jj, aj *= 0.5f) {  // trials in backtracking order
+          const float v = objn_s[tid * G + jj];
+          const float on = (v != v) ? oc : v;       // NaN trial -> rejected
+          ar = 0.5f * aj;
+          if (on < oc) { src = tid * G + jj + 1; obj_s[tl] = on; break; }  // strict decrease only
         }
+        acc_s[tl] = src;                            // source lane + 1 of the accepted trial
+        alpha_s[tl] = ar;
+        srch_s[tl] = (src == 0 && ar > Q.alpha_min) ? 1 : 0;
       }
       __syncthreads();
       if (!init) {
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
           if (acc_s[r]) wsU[e] = wsUn[(e & ~31) + acc_s[r] - 1];
         const int more = __syncthreads_or(tid < RT && srch_s[r]);
         if (more) {
-          alpha *= 0.5f;
+          j0 += G;
           continue;
         }
       }
@@ -677,7 +680,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       }
       // line search setup: every lane still iterating searches from alpha_0
       if (tid < RT) srch_s[r] = (act_s[r] && Q.alpha0 > Q.alpha_min) ? 1 : 0;
-      alpha = Q.alpha0;
+      j0 = 0;
       init = false;
       __syncthreads();
       if (!__syncthreads_or(tid < RT && srch_s[r])) {
