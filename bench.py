@@ -33,6 +33,7 @@ import torch  # noqa: E402
 from gan_mpc_b200 import synthetic  # noqa: E402
 
 METRIC = "planned states/sec (fused rollout+BPTT+update)"
+METRIC_ILQR = "planned states/sec (trajax-iLQR mode, gmpc_ilqr)"
 UNIT = "states/s"
 L2_FLUSH_BYTES = 256 << 20
 
@@ -135,10 +136,51 @@ def time_cpu_port(cfg, params, x0, U0, goal, lr, target_s=15.0, reps=1):
                        f"installable offline)"), best, sample
 
 
+ILQR_KW = dict(maxiter=100, grad_norm_threshold=1e-4, alpha_0=1.0, alpha_min=0.00005)  # policy/eval.py:10-20
+
+
+def time_cpu_ilqr(cfg, params, x0, U0, goal, target_s=15.0):
+    """fp32 oracle port of trajax iLQR (oracle/ilqr.py) on a bounded sample, all host threads."""
+    from oracle import ilqr as oilqr
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    op = oracle_params(params, torch.float32)
+    f = lambda a, b: torch.from_numpy(np.ascontiguousarray(a[:b]))
+    probe = min(8, x0.shape[0])
+    t0 = time.perf_counter()
+    oilqr.ilqr(f(x0, probe), f(U0[:, 0], probe), f(goal, probe), op, **ILQR_KW)
+    dt = time.perf_counter() - t0
+    sample = int(min(x0.shape[0], max(probe, 8 * int(probe * target_s / max(dt, 1e-3) / 8))))
+    t0 = time.perf_counter()
+    oilqr.ilqr(f(x0, sample), f(U0[:, 0], sample), f(goal, sample), op, **ILQR_KW)
+    best = time.perf_counter() - t0
+    return dict(value=sample / best, unit=UNIT, cores=cores, kind="port",
+                sample=f"{sample} of {x0.shape[0]} states of workload, one pass of {best:.2f} s (fp32 torch-CPU "
+                       f"oracle port of trajax iLQR, all {cores} host threads; JAX/trajax not installable offline)"), best, sample
+
+
 def run_reference(args, cfg, rank):
     if rank != 0:
         return
     lr = args.lr
+    if args.planner == "ilqr":
+        params = synthetic.planner_params(0, **cfg)
+        x0, U0, goal = synthetic.planner_inputs(0, **cfg)
+        tot_t = tot_s = 0.0
+        for i in range(args.warmup + args.steps):
+            cb, dt, sample = time_cpu_ilqr(cfg, params, x0, U0, goal, target_s=args.ref_seconds)
+            if i >= args.warmup:
+                tot_t, tot_s = tot_t + dt, tot_s + sample
+        value = tot_s / tot_t
+        cb["value"] = value
+        print(json.dumps({"impl": "reference", "metric": METRIC_ILQR, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": workload_config(args, cfg, lr, "cpu-oracle-port"),
+                          "cpu_baseline": cb,
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+              flush=True)
+        return
     params = synthetic.planner_params(0, **cfg)
     x0, U0, goal = synthetic.planner_inputs(0, **cfg)
     times = []
@@ -167,9 +209,12 @@ def workload_config(args, cfg, lr, path):
                         f"n={cfg['n']}, m={cfg['m']}, horizon T={cfg['T']}, {cfg['iters']} planning "
                         f"iterations, dyn MLP {synthetic.dyn_dims(cfg['n'], cfg['m'], cfg['dyn_layers'], cfg['dyn_hidden'])}, "
                         f"cost MLP {synthetic.cost_dims(cfg['n'], cfg['cost_layers'], cfg['cost_hidden'], cfg['cost_fout'])}",
-            "states_per_gpu": cfg["B"], "planner": {"method": "adam", "lr": lr, "b1": 0.9,
-                                                    "b2": 0.999, "eps": 1e-8},
-            "note": "first-order planner on the reference's objective (reference planner is trajax iLQR)",
+            "states_per_gpu": cfg["B"],
+            "planner": ({"method": "ilqr", **ILQR_KW} if args.planner == "ilqr" else
+                        {"method": "adam", "lr": lr, "b1": 0.9, "b2": 0.999, "eps": 1e-8}),
+            "note": ("the reference's own planner step: trajax iLQR with the options of policy/eval.py:10-20"
+                     if args.planner == "ilqr" else
+                     "first-order planner on the reference's objective (reference planner is trajax iLQR)"),
             "weights": "random-init flax defaults (lecun_normal, zero bias), seed 0",
             "cache": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
             "path": path, "parallelism": f"dp{args.gpus} (start states sharded, no data-path collective; "
@@ -184,6 +229,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--path", default="auto", choices=["auto", "ffma", "tc", "tc16", "tc16s"])
+    ap.add_argument("--planner", default="adam", choices=["adam", "ilqr"],
+                    help="adam: the north-star first-order planner (the BASELINE metric, default); ilqr: the "
+                         "reference's own step, trajax iLQR with its full options (gmpc_ilqr; secondary line)")
     ap.add_argument("--lr", type=float, default=1e-2)
     ap.add_argument("--batch", type=int, default=0, help="override states per GPU")
     ap.add_argument("--ref-seconds", type=float, default=15.0)
@@ -232,10 +280,20 @@ def main():
         gather_bufs = [torch.empty(world * t.numel(), device=dev, dtype=t.dtype)
                        for t in (out[0], out[2], out[3])]
 
+    ilqr = args.planner == "ilqr"
+    d_U0i = d_U0[:, 0].contiguous() if ilqr else None
+    if ilqr and K != 1:
+        raise SystemExit("--planner ilqr plans one action sequence per state (K = 1 workloads)")
+
     def step():
-        h.plan(d_x0, d_U0, d_goal, method="adam", iters=cfg["iters"], lr=args.lr, out=out)
-        if world > 1:  # gather of the best plans (U*, J*, idx) -- 776 B/state at C2
-            for buf, t in zip(gather_bufs, (out[0], out[2], out[3])):
+        if ilqr:
+            res = h.ilqr(d_x0, d_U0i, d_goal, **ILQR_KW)
+            plans = (res[1], res[2], res[6])
+        else:
+            h.plan(d_x0, d_U0, d_goal, method="adam", iters=cfg["iters"], lr=args.lr, out=out)
+            plans = (out[0], out[2], out[3])
+        if world > 1:  # gather of the best plans (U*, J*, idx / iteration) -- 776 B/state at C2
+            for buf, t in zip(gather_bufs, plans):
                 dist.all_gather_into_tensor(buf, t.reshape(-1))
 
     def barrier():
@@ -247,6 +305,8 @@ def main():
         step()
         flush.fill_(1.0)
     barrier()
+    if ilqr:
+        h.ilqr_stats()  # reset the work counters: the timed steps are counted below
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -271,29 +331,53 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e through the host-buffer C-ABI call (pinned host tensors in and out)
+    ilqr_work = h.ilqr_stats() if ilqr else None   # (tile outer iterations, tile rollouts) of the timed steps
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_x0, h_U0, h_goal = pin(x0), pin(U0), pin(goal)
-    h_out = h.alloc_plan_outputs(B, K, True, device=torch.device("cpu"), pin=True)
+    if ilqr:
+        h_U0 = pin(U0[:, 0])
+        host_call = lambda: h.ilqr_host(h_x0, h_U0, h_goal, **ILQR_KW)
+    else:
+        h_out = h.alloc_plan_outputs(B, K, True, device=torch.device("cpu"), pin=True)
+        host_call = lambda: h.plan_host(h_x0, h_U0, h_goal, method="adam", iters=cfg["iters"], lr=args.lr,
+                                        out=h_out)
     for _ in range(2):
-        h.plan_host(h_x0, h_U0, h_goal, method="adam", iters=cfg["iters"], lr=args.lr, out=h_out)
+        h_res = host_call()
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        h.plan_host(h_x0, h_U0, h_goal, method="adam", iters=cfg["iters"], lr=args.lr, out=h_out)
+        h_res = host_call()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(e2e_s.item())
-    h2d = 4 * (x0.size + U0.size + goal.size)
-    d2h = sum(t.numel() * t.element_size() for t in h_out)
+    h2d = 4 * (x0.size + h_U0.numel() + goal.size)
+    d2h = sum(t.numel() * t.element_size() for t in h_res if t is not None)
 
     if rank == 0:
         peaks = measured_peaks()
         value = world * B * args.steps / total_s
         ms_per_step = 1e3 * total_s / args.steps
         fl = flops_per_state(cfg) * B                    # algorithmic FLOPs of one launch (one GPU)
+        if ilqr:
+            # data-dependent work, counted by the kernel: per 32-lane tile, every linearisation is T (1 + n)
+            # dynamics passes + (1 + fout) cost passes, every rollout T dynamics passes + 1 cost pass;
+            # a pass is 2 FLOP x MACs x the trajectories of the tile (algorithmic: B / tiles on average)
+            dd = synthetic.dyn_dims(cfg["n"], cfg["m"], cfg["dyn_layers"], cfg["dyn_hidden"])
+            cd = synthetic.cost_dims(cfg["n"], cfg["cost_layers"], cfg["cost_hidden"], cfg["cost_fout"])
+            m_dyn = sum(a * b for a, b in zip(dd[:-1], dd[1:]))
+            m_cost = sum(a * b for a, b in zip(cd[:-1], cd[1:]))
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            tile_traj = max(1, -(-B // sms))       # the host's tile rule (gmpc_ilqr): small batches get small tiles
+            tile_traj = 32 if tile_traj > 16 else tile_traj
+            tiles = -(-B // tile_traj)
+            n_lin = ilqr_work[0] / args.steps + tiles
+            n_roll = ilqr_work[1] / args.steps
+            lanes = B / tiles
+            fl = 2.0 * lanes * (n_lin * (cfg["T"] * (1 + cfg["n"]) * m_dyn + (1 + cfg["cost_fout"]) * m_cost)
+                                + n_roll * (cfg["T"] * m_dyn + m_cost))
         kernel_s = (sum(step_ms) / len(step_ms)) * 1e-3  # the plan kernel IS the step (K=1: +1 memset)
         achieved = fl / kernel_s / 1e12
         traffic = None
@@ -302,7 +386,7 @@ def main():
             traffic = json.load(open(tpath)).get(f"{args.workload}:{h.last_path}")
         fp32_peak = _lib.measure_fp32_peak(local)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC_ILQR if ilqr else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, cfg, args.lr, h.last_path),
@@ -320,8 +404,18 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
             "step_ms_min_med_max": [min(step_ms), float(np.median(step_ms)), max(step_ms)],
         }
+        if ilqr:  # fp32 CUDA-core kernel: the roofline that bounds it is the measured FFMA peak
+            line["roofline"].update(bound="fp32-ffma (not one of the contract's hbm|tensor: this optional line is "
+                                          "outside the BASELINE metric)", peak=fp32_peak,
+                                    frac=achieved / fp32_peak if fp32_peak else None,
+                                    peak_source="measured FP32 FFMA peak (gmpc_measure_fp32_peak)", traffic=None)
+            line["ilqr_work_per_step"] = {"tile_outer_iterations": ilqr_work[0] / args.steps,
+                                          "tile_rollouts": ilqr_work[1] / args.steps}
         if world == 1 and not args.no_cpu_baseline:
-            cb, _, _ = time_cpu_port(cfg, params, x0, U0, goal, args.lr, target_s=args.ref_seconds)
+            if ilqr:
+                cb, _, _ = time_cpu_ilqr(cfg, params, x0, U0, goal, target_s=args.ref_seconds)
+            else:
+                cb, _, _ = time_cpu_port(cfg, params, x0, U0, goal, args.lr, target_s=args.ref_seconds)
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -66,6 +66,8 @@ def main():
                tile_outer_iterations=outer, tile_rollouts=rolls,
                obj_over_initial_median=float((obj / J0).median()))
     if a.cpu_states > 0 and not a.bilevel:
+        # (CPU leg kept for interactive use; the contract-conformant CPU baseline of the iLQR mode is
+        # `python bench.py --planner ilqr [--impl reference]`)
         from oracle import ilqr as oilqr
         nb = min(a.cpu_states, B)
         torch.set_num_threads(len(os.sched_getaffinity(0)))
