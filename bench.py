@@ -228,7 +228,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(synthetic.CONFIGS))
-    ap.add_argument("--path", default="auto", choices=["auto", "ffma", "tc", "tc16", "tc16s"])
+    ap.add_argument("--path", default="auto", choices=["auto", "ffma", "tc16", "tc16s", "t128"])
     ap.add_argument("--planner", default="adam", choices=["adam", "ilqr"],
                     help="adam: the north-star first-order planner (the BASELINE metric, default); ilqr: the "
                          "reference's own step, trajax iLQR with its full options (gmpc_ilqr; secondary line)")

@@ -14,9 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GMPC_LIB_PATH", os.path.join(_HERE, "libgmpc.so"))  # override: experiments only
 
 METHOD_GRAD, METHOD_ADAM = 0, 1
-PATH_AUTO, PATH_FFMA, PATH_TC, PATH_TC16, PATH_TC16S = 0, 1, 2, 3, 4
+PATH_AUTO, PATH_FFMA, PATH_TC, PATH_TC16, PATH_TC16S, PATH_T128 = 0, 1, 2, 3, 4, 5
 METHODS = {"grad": METHOD_GRAD, "adam": METHOD_ADAM}
-PATHS = {"auto": PATH_AUTO, "ffma": PATH_FFMA, "tc": PATH_TC, "tc16": PATH_TC16, "tc16s": PATH_TC16S}
+PATHS = {"auto": PATH_AUTO, "ffma": PATH_FFMA, "tc16": PATH_TC16, "tc16s": PATH_TC16S, "t128": PATH_T128}
 
 
 class GmpcError(RuntimeError):
@@ -86,8 +86,7 @@ _SIGS = {
                                          _f, _f, C.c_void_p]),
     "gmpc_l2_loss": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, _f, C.c_void_p]),
     "gmpc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
-    "gmpc_tc_probe": (C.c_int, [C.c_int] * 4 + [C.c_uint32] * 11 + [C.c_void_p] * 3),
-    "gmpc_tc_mma_bench": (C.c_int, [C.c_int] * 5 + [C.c_uint32] * 7 + [C.c_int, C.POINTER(C.c_double)]),
+    "gmpc_measure_f16_mma_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -163,7 +162,7 @@ class Handle:
 
     @property
     def last_path(self):
-        return {PATH_FFMA: "ffma", PATH_TC: "tc", PATH_TC16: "tc16", PATH_TC16S: "tc16s"}[self.lib.gmpc_last_path(self._h)]
+        return {PATH_FFMA: "ffma", PATH_TC16: "tc16", PATH_TC16S: "tc16s", PATH_T128: "t128"}[self.lib.gmpc_last_path(self._h)]
 
     def range_overflow(self):
         """CTAs of the fp16-split kernel that clamped an operand since the last call (synchronises)."""
@@ -493,24 +492,8 @@ def measure_fp32_peak(device=0):
     return float(out.value)
 
 
-def tc_probe(A, B, a_major, a_lbo, a_sbo, a_s1, a_s2, a_kstep, b_lbo, b_sbo, b_s1, b_s2,
-             a_bytes, smem_bytes, device=0):
-    """Run one tcgen05 tf32 contraction D = A @ B.T (A [128,K], B [NB,K] float32 numpy) with the
-    given shared-memory image strides and descriptor fields; returns D [128, NB]."""
-    import numpy as np
-    A = np.ascontiguousarray(A, np.float32)
-    B = np.ascontiguousarray(B, np.float32)
-    D = np.zeros((128, B.shape[0]), np.float32)
-    _check(load().gmpc_tc_probe(int(device), B.shape[1], B.shape[0], int(a_major), a_lbo, a_sbo,
-                                a_s1, a_s2, a_kstep, b_lbo, b_sbo, b_s1, b_s2, a_bytes,
-                                smem_bytes, A.ctypes.data, B.ctypes.data, D.ctypes.data))
-    return D
-
-
-def tc_mma_bench(N, ksteps, reps, a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, layout_type=0,
-                 two_mma=0, grid=1, device=0):
-    """cycles per tcgen05.mma (M=128, N, K=8 tf32) for the given operand layout."""
-    out = C.c_double(0.0)
-    _check(load().gmpc_tc_mma_bench(int(device), grid, N, ksteps, reps, a_lbo, a_sbo, a_kstep,
-                                    b_lbo, b_sbo, b_kstep, layout_type, two_mma, C.byref(out)))
+def measure_f16_mma_peak(device=0):
+    """Measured dense kind::f16 tcgen05 TFLOP/s of `device` (the pipe the planner kernels use)."""
+    out = C.c_float(0.0)
+    _check(load().gmpc_measure_f16_mma_peak(int(device), C.byref(out)))
     return float(out.value)

@@ -18,8 +18,8 @@
 #include "plan_ffma.cuh"
 #include "ilqr.cuh"
 #include "dynfit.cuh"
-#include "plan_tc.cuh"
 #include "plan_h16.cuh"
+#include "plan_t128.cuh"
 
 using namespace gmpc;
 
@@ -80,9 +80,14 @@ struct gmpc_handle {
   unsigned long long fuse_tickets = 0;  // tickets handed out so far (the device counter only grows)
   size_t losses_cap = 0;
   int critic_grid = 0;
-  // tensor-core path state (3xTF32 kernel and the fp16-split kernel)
-  TcState tc;
+  // tensor-core path state: the 32-trajectory fp16-split kernel (latency tile, wide layers) and the
+  // 128-trajectory tile kernel (activations in tensor memory)
   H16State h16;
+  T128State t128;
+  size_t smem_optin = 0;        // cudaDevAttrMaxSharedMemoryPerBlockOptin, read once
+  bool ilqr_full_tiles = false; // GMPC_ILQR_FULL_TILES / GMPC_ILQR_NO_PACK: experiment switches, read once at create
+  bool ilqr_no_pack = false;
+  bool ilqr_attr = false;
   // iLQR kernel scratch (allocated on first use)
   uint32_t* d_fit_masks = nullptr;   // dynfit kernel ReLU masks (grown on demand)
   size_t fit_masks_bytes = 0;
@@ -246,8 +251,12 @@ extern "C" int gmpc_create(const gmpc_config* cfg, gmpc_handle** out) {
     gmpc_destroy(h);
     return fail(GMPC_E_CUDA, std::string("gmpc_create: ") + cudaGetErrorString(e));
   }
-  int rc = tc_create(h->tc, c, h->dyn.dims, h->cost.dims, prop);
-  if (rc == GMPC_OK) rc = h16_create(h->h16, c, h->dyn.dims, h->cost.dims, prop);
+  h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+  h->ilqr_full_tiles = getenv("GMPC_ILQR_FULL_TILES") != nullptr;
+  h->ilqr_no_pack = getenv("GMPC_ILQR_NO_PACK") != nullptr;
+  int rc = h16_create(h->h16, c, h->dyn.dims, h->cost.dims, prop);
+  if (rc == GMPC_OK)
+    rc = t128_create(h->t128, c, h->dyn.dims, h->cost.dims, prop.multiProcessorCount, (size_t)prop.sharedMemPerBlockOptin);
   if (rc != GMPC_OK) {
     gmpc_destroy(h);
     return fail(rc, "gmpc_create: tensor-core path setup failed (CUDA error)");
@@ -259,8 +268,8 @@ extern "C" int gmpc_create(const gmpc_config* cfg, gmpc_handle** out) {
 extern "C" int gmpc_destroy(gmpc_handle* h) {
   if (!h) return GMPC_OK;
   cudaSetDevice(h->cfg.device);
-  tc_destroy(h->tc);
   h16_destroy(h->h16);
+  t128_destroy(h->t128);
   cudaFree(h->d_wpack); cudaFree(h->d_mpcw);
   cudaFree(h->ws_X); cudaFree(h->ws_G); cudaFree(h->ws_U); cudaFree(h->ws_M); cudaFree(h->ws_V);
   cudaFree(h->ws_mask); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -275,9 +284,12 @@ extern "C" int64_t gmpc_critic_param_count(const gmpc_handle* h) {
 }
 
 extern "C" int gmpc_set_path(gmpc_handle* h, int path) {
-  if (!h || path < GMPC_PATH_AUTO || path > GMPC_PATH_TC16S) return fail(GMPC_E_ARG, "gmpc_set_path: bad argument");
-  if (path == GMPC_PATH_TC && !h->tc.supported)
-    return fail(GMPC_E_UNSUPPORTED, "gmpc_set_path: tensor-core path unsupported for this shape: " + h->tc.why);
+  if (!h || path < GMPC_PATH_AUTO || path > GMPC_PATH_T128) return fail(GMPC_E_ARG, "gmpc_set_path: bad argument");
+  if (path == GMPC_PATH_TC)
+    return fail(GMPC_E_UNSUPPORTED, "gmpc_set_path: the 3xTF32 kernel was superseded by the fp16-split kernels and is "
+                                    "no longer part of the library (unsupported)");
+  if (path == GMPC_PATH_T128 && !h->t128.supported)
+    return fail(GMPC_E_UNSUPPORTED, "gmpc_set_path: tensor-core path unsupported for this shape: " + h->t128.why);
   if ((path == GMPC_PATH_TC16 || path == GMPC_PATH_TC16S) && !h->h16.supported)
     return fail(GMPC_E_UNSUPPORTED, "gmpc_set_path: tensor-core path unsupported for this shape: " + h->h16.why);
   h->path = path;
@@ -312,7 +324,7 @@ extern "C" int gmpc_set_weights(gmpc_handle* h, const float* const* dyn_W,
   rc = pack_mlp(h, h->cost, cost_W, cost_b, st);
   if (rc) return rc;
   CU_CHECK(cudaMemcpyAsync(h->d_mpcw, mpc_weights, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  rc = tc_set_weights(h->tc, dyn_W, dyn_b, cost_W, cost_b, st, &h->launches);
+  rc = t128_set_weights(h->t128, dyn_W, dyn_b, cost_W, cost_b, st, &h->launches);
   if (rc) return rc;
   rc = h16_set_weights(h->h16, dyn_W, dyn_b, cost_W, cost_b, st, &h->launches);
   if (rc) return rc;
@@ -321,11 +333,16 @@ extern "C" int gmpc_set_weights(gmpc_handle* h, const float* const* dyn_W,
   return GMPC_OK;
 }
 
-// Which kernel family serves a call: explicit choice, else the fp16-split tensor-core kernel when
-// the tile is a real dense contraction, else the fp32 CUDA-core kernel.
+// Which kernel family serves a call: explicit choice, else a tensor-core kernel when the tile is a
+// real dense contraction (batch tile >= 64, hidden >= 64: the north star's rule), else the fp32
+// CUDA-core kernel.  Both tensor-core defaults rescale the forward operands per trajectory: states
+// of any magnitude stay inside the fp16 hi/lo range (the un-scaled GMPC_PATH_TC16 is opt-in only).
 static int pick_path(gmpc_handle* h, int64_t NQ) {
   if (h->path != GMPC_PATH_AUTO) return h->path;
-  if (h->h16.supported && h16_worthwhile(h->h16, NQ)) return GMPC_PATH_TC16;
+  if (h->h16.supported && h16_worthwhile(h->h16, NQ)) {
+    if (h->t128.supported) return GMPC_PATH_T128;
+    return GMPC_PATH_TC16S;
+  }
   return GMPC_PATH_FFMA;
 }
 
@@ -345,9 +362,9 @@ static int launch_ffma(gmpc_handle* h, PlanParams& P, cudaStream_t st) {
   const int grid = std::min(P.ntiles, h->num_sms);
   if (grid <= 0) return GMPC_OK;
   const int path = pick_path(h, P.NQ);
-  if (path == GMPC_PATH_TC || path == GMPC_PATH_TC16 || path == GMPC_PATH_TC16S) {
-    int rc = path == GMPC_PATH_TC ? tc_launch(h->tc, P, st, &h->launches)
-                                  : h16_launch(h->h16, P, path == GMPC_PATH_TC16S, st, &h->launches);
+  if (path == GMPC_PATH_T128 || path == GMPC_PATH_TC16 || path == GMPC_PATH_TC16S) {
+    int rc = path == GMPC_PATH_T128 ? t128_launch(h->t128, P, st, &h->launches)
+                                    : h16_launch(h->h16, P, path == GMPC_PATH_TC16S, st, &h->launches);
     if (rc) return fail(rc, "tensor-core planner launch failed");
     h->last_path = path;
     return GMPC_OK;
@@ -489,9 +506,7 @@ static int ilqr_launch(gmpc_handle* h, int64_t B, const float* x0, const float* 
   if (c.m > IL_MAXM) return fail(GMPC_E_UNSUPPORTED, "gmpc_ilqr: action size above 16");
   cudaStream_t st = (cudaStream_t)stream;
   const IlqrSmem SL = ilqr_smem_layout(c.n, c.m, c.cost_fout, h->hpad);
-  cudaDeviceProp prop;
-  CU_CHECK(cudaGetDeviceProperties(&prop, c.device));
-  if (SL.bytes > (size_t)prop.sharedMemPerBlockOptin)
+  if (SL.bytes > h->smem_optin)
     return fail(GMPC_E_UNSUPPORTED, "gmpc_ilqr: the Riccati matrices of a 32-trajectory tile do not fit shared memory (state size too large)");
   const IlqrWs WL = ilqr_ws_layout(c.n, c.m, c.T, c.cost_fout, bl != nullptr);
   const size_t need = (size_t)h->num_sms * WL.total * sizeof(float);
@@ -503,10 +518,11 @@ static int ilqr_launch(gmpc_handle* h, int64_t B, const float* x0, const float* 
   if (!h->d_ilqr_stats) {
     CU_CHECK(cudaMalloc(&h->d_ilqr_stats, 2 * sizeof(long long)));
     CU_CHECK(cudaMemset(h->d_ilqr_stats, 0, 2 * sizeof(long long)));
-    CU_CHECK(cudaFuncSetAttribute(ilqr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)prop.sharedMemPerBlockOptin));
-    CU_CHECK(cudaFuncSetAttribute(ilqr_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)prop.sharedMemPerBlockOptin));
+  }
+  if (!h->ilqr_attr) {
+    CU_CHECK(cudaFuncSetAttribute(ilqr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    CU_CHECK(cudaFuncSetAttribute(ilqr_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    h->ilqr_attr = true;
   }
   IlqrParams Q;
   memset(&Q, 0, sizeof(Q));
@@ -526,7 +542,7 @@ static int ilqr_launch(gmpc_handle* h, int64_t B, const float* x0, const float* 
   int tile_traj = (int)std::max<int64_t>(1, (B + h->num_sms - 1) / h->num_sms);
   // measured (C1 dims, one B200): 128 states 68 ms vs 366 ms with full tiles, 1024 states 337 vs 478 ms;
   // from about half-full tiles on there is nothing left to gain (4096 states: 28-lane tiles are no faster)
-  if (tile_traj > RT / 2 || getenv("GMPC_ILQR_FULL_TILES")) tile_traj = RT;
+  if (tile_traj > RT / 2 || h->ilqr_full_tiles) tile_traj = RT;
   Q.tile_traj = tile_traj;
   P.ntiles = (int)((B + tile_traj - 1) / tile_traj);
   P.x0 = x0; P.U_in = U0; P.goal = goal;
@@ -541,7 +557,7 @@ static int ilqr_launch(gmpc_handle* h, int64_t B, const float* x0, const float* 
   Q.ws = h->d_ilqr_ws;
   Q.ws_stride = (long long)WL.total;
   Q.stats = h->d_ilqr_stats;
-  Q.pack_small = getenv("GMPC_ILQR_NO_PACK") ? 0 : 1;   // experiment switch: lane = trajectory everywhere
+  Q.pack_small = h->ilqr_no_pack ? 0 : 1;   // experiment switch: lane = trajectory everywhere
   if (bl) {
     Q.desired = bl->desired; Q.bl_loss = bl->loss; Q.bl_B = bl->Bvec; Q.bl_hess = bl->hess;
     Q.bl_H = bl->H; Q.bl_dxT = bl->dxT; Q.bl_gw = bl->gw; Q.bl_V = bl->V;
@@ -668,14 +684,16 @@ extern "C" int gmpc_ilqr_stats(gmpc_handle* h, int64_t* outer_iterations, int64_
 extern "C" int gmpc_range_overflow(gmpc_handle* h, int32_t* count, void* stream) {
   if (!h || !count) return fail(GMPC_E_ARG, "gmpc_range_overflow: null argument");
   *count = 0;
-  if (!h->h16.supported || h->h16.d_ovf == nullptr) return GMPC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   CU_CHECK(cudaSetDevice(h->cfg.device));
-  uint32_t v = 0;
-  CU_CHECK(cudaMemcpyAsync(&v, h->h16.d_ovf, sizeof(v), cudaMemcpyDeviceToHost, st));
+  uint32_t v[2] = {0, 0};
+  uint32_t* src[2] = {h->h16.supported ? h->h16.d_ovf : nullptr, h->t128.supported ? h->t128.d_ovf : nullptr};
+  for (int i = 0; i < 2; ++i)
+    if (src[i]) CU_CHECK(cudaMemcpyAsync(&v[i], src[i], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CU_CHECK(cudaStreamSynchronize(st));
-  if (v != 0) CU_CHECK(cudaMemsetAsync(h->h16.d_ovf, 0, sizeof(v), st));
-  *count = (int32_t)std::min<uint32_t>(v, 0x7fffffffu);
+  for (int i = 0; i < 2; ++i)
+    if (src[i] && v[i] != 0) CU_CHECK(cudaMemsetAsync(src[i], 0, sizeof(uint32_t), st));
+  *count = (int32_t)std::min<uint64_t>((uint64_t)v[0] + v[1], 0x7fffffffu);
   return GMPC_OK;
 }
 
@@ -721,7 +739,7 @@ extern "C" int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float*
   if (J_all_host)
     CU_CHECK(cudaMemcpyAsync(J_all_host, d_Ja, f_Ja * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_CHECK(cudaStreamSynchronize(st));
-  if (h->last_path == GMPC_PATH_TC16 || h->last_path == GMPC_PATH_TC16S) {
+  if (h->last_path == GMPC_PATH_TC16 || h->last_path == GMPC_PATH_TC16S || h->last_path == GMPC_PATH_T128) {
     int32_t clamped = 0;
     rc = gmpc_range_overflow(h, &clamped, stream);
     if (rc) return rc;
@@ -731,7 +749,7 @@ extern "C" int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float*
       // (still the GPU; there is no CPU path)
       if (!h->auto_retry)
         return fail(GMPC_E_UNSUPPORTED, "gmpc_plan_host: operand magnitude above 65000 on the fp16-split path; "
-                                        "use GMPC_PATH_AUTO, GMPC_PATH_TC16S, GMPC_PATH_FFMA or GMPC_PATH_TC");
+                                        "use GMPC_PATH_AUTO, GMPC_PATH_T128, GMPC_PATH_TC16S or GMPC_PATH_FFMA");
       const int retry = h->last_path == GMPC_PATH_TC16 ? GMPC_PATH_TC16S : GMPC_PATH_FFMA;
       h->path = retry;
       h->in_retry = true;
@@ -1064,53 +1082,31 @@ extern "C" int gmpc_measure_fp32_peak(int device, float* tflops_out) {
   return GMPC_OK;
 }
 
-extern "C" int gmpc_tc_probe(int device, int K, int NB, int a_major, uint32_t a_lbo, uint32_t a_sbo,
-                             uint32_t a_s1, uint32_t a_s2, uint32_t a_kstep, uint32_t b_lbo,
-                             uint32_t b_sbo, uint32_t b_s1, uint32_t b_s2, uint32_t a_bytes,
-                             uint32_t smem_bytes, const float* A_host, const float* B_host,
-                             float* D_host) {
-  if (!A_host || !B_host || !D_host || K < 8 || K % 8 || NB < 16 || NB % 16 || NB > 256 ||
-      smem_bytes > 200 * 1024 || a_bytes > smem_bytes)
-    return fail(GMPC_E_ARG, "gmpc_tc_probe: bad argument");
+// Dense kind::f16 tcgen05 peak (TFLOP/s) of `device`: the tensor pipe the planner kernels run on, measured
+// with operands resident in shared memory (roofline context beside the cuBLAS figure of MEASURED_PEAKS.json).
+extern "C" int gmpc_measure_f16_mma_peak(int device, float* tflops_out) {
+  if (!tflops_out) return fail(GMPC_E_ARG, "gmpc_measure_f16_mma_peak: null argument");
   CU_CHECK(cudaSetDevice(device));
-  float *dA = nullptr, *dB = nullptr, *dD = nullptr;
-  const size_t a_floats = (a_major & 2) ? a_bytes / 4 : (size_t)128 * K;
-  CU_CHECK(cudaMalloc(&dA, sizeof(float) * a_floats));
-  CU_CHECK(cudaMalloc(&dB, sizeof(float) * NB * K));
-  CU_CHECK(cudaMalloc(&dD, sizeof(float) * 128 * NB));
-  CU_CHECK(cudaMemcpy(dA, A_host, sizeof(float) * a_floats, cudaMemcpyHostToDevice));
-  CU_CHECK(cudaMemcpy(dB, B_host, sizeof(float) * NB * K, cudaMemcpyHostToDevice));
-  CU_CHECK(cudaMemset(dD, 0, sizeof(float) * 128 * NB));
-  CU_CHECK(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  tc_probe_kernel<<<1, 128, smem_bytes>>>(dA, dB, dD, K, NB, a_major, a_lbo, a_sbo, a_s1, a_s2,
-                                          a_kstep, b_lbo, b_sbo, b_s1, b_s2, a_bytes);
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpy(D_host, dD, sizeof(float) * 128 * NB, cudaMemcpyDeviceToHost);
-  cudaFree(dA); cudaFree(dB); cudaFree(dD);
-  if (e != cudaSuccess) return fail(GMPC_E_CUDA, std::string("gmpc_tc_probe: ") + cudaGetErrorString(e));
-  return GMPC_OK;
-}
-
-extern "C" int gmpc_tc_mma_bench(int device, int grid, int N, int ksteps, int reps, uint32_t a_lbo,
-                                 uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo,
-                                 uint32_t b_kstep, uint32_t layout_type, int two_mma,
-                                 double* cycles_per_mma) {
-  if (!cycles_per_mma || grid < 1 || grid > 1024 || N < 16 || N > 256 || N % 16 || ksteps < 1 || reps < 1)
-    return fail(GMPC_E_ARG, "gmpc_tc_mma_bench: bad argument");
-  CU_CHECK(cudaSetDevice(device));
-  long long* d = nullptr;
-  CU_CHECK(cudaMalloc(&d, sizeof(long long) * grid));
-  CU_CHECK(cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  for (int rep = 0; rep < 2; ++rep)
-    tc_mma_bench_kernel<<<grid, 128, 200 * 1024>>>(d, N, ksteps, reps, a_lbo, a_sbo, a_kstep, b_lbo,
-                                                   b_sbo, b_kstep, layout_type, two_mma);
-  cudaError_t e = cudaDeviceSynchronize();
-  std::vector<long long> h(grid);
-  if (e == cudaSuccess) e = cudaMemcpy(h.data(), d, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
-  cudaFree(d);
-  if (e != cudaSuccess) return fail(GMPC_E_CUDA, std::string("gmpc_tc_mma_bench: ") + cudaGetErrorString(e));
-  long long mx = 0;
-  for (long long v : h) mx = std::max(mx, v);
-  *cycles_per_mma = (double)mx / ((double)reps * ksteps * (two_mma == 1 ? 2 : 1));
+  int sms = 0;
+  CU_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  CU_CHECK(cudaFuncSetAttribute(f16_mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+  cudaEvent_t e0, e1;
+  CU_CHECK(cudaEventCreate(&e0));
+  CU_CHECK(cudaEventCreate(&e1));
+  const int mmas = 200000;
+  float best = 0.f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU_CHECK(cudaEventRecord(e0));
+    f16_mma_peak_kernel<<<sms, 128, 48 * 1024>>>(mmas);
+    CU_CHECK(cudaEventRecord(e1));
+    CU_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 128 * 256 * 16 * (double)mmas * sms;
+    if (rep > 0) best = fmaxf(best, (float)(flops / (ms * 1e-3) / 1e12));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops_out = best;
   return GMPC_OK;
 }

@@ -87,4 +87,13 @@ __device__ __forceinline__ float pow2_recip(float s) {
   return __uint_as_float(0x7F000000u - __float_as_uint(s));
 }
 
+// max |W| of one layer -> absmax[0] (float bits compare as unsigned for non-negative values)
+__global__ void h16_absmax_kernel(const float* __restrict__ W, int count, uint32_t* absmax) {
+  float mx = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    mx = fmaxf(mx, fabsf(W[i]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+  if ((threadIdx.x & 31) == 0 && isfinite(mx)) atomicMax(absmax, __float_as_uint(mx));
+}
+
 }  // namespace gmpc

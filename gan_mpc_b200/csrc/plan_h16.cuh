@@ -8,7 +8,7 @@
 // with the WEIGHTS as the A operand (128 output features per block, <= 2 blocks) and the
 // trajectories as the N dimension, so B = 4096 start states fill 128 SMs with full-height MMAs.
 //
-// What is different from plan_tc.cuh (3xTF32), each justified by tools/mma_rate.cu on B200:
+// What is different from the first, 3xTF32 formulation (tools/legacy/plan_tc.cuh), each justified by tools/mma_rate.cu on B200:
 //  * an M=128 MMA with a small N is bound by the 4 KB read of A from shared memory (>= 40
 //    cycles), not by the tensor pipe: fp16 operands cover K = 16 per MMA instead of 8, halving the
 //    MMA count and the streamed weight bytes for the same 22-bit effective mantissa;
@@ -36,9 +36,10 @@
 #include "../../include/gmpc.h"
 #include "common.cuh"
 #include "h16_common.cuh"
-#include "plan_tc.cuh"  // tc_pass_kind, TcParams-independent helpers (rup)
 
 namespace gmpc {
+
+inline int rup(int v, int a) { return (v + a - 1) / a * a; }
 
 constexpr int H_THREADS = 384;  // producer, issuer, 8 compute warps, second producer, second issuer
 constexpr int H_PRODUCER2 = 10; // warp index of the second producer
@@ -1162,15 +1163,6 @@ __global__ void __launch_bounds__(H_THREADS, 1) plan_h16_kernel(const __grid_con
   }
 }
 
-// max |W| of one layer -> absmax[0] (float bits compare as unsigned for non-negative values)
-__global__ void h16_absmax_kernel(const float* __restrict__ W, int count, uint32_t* absmax) {
-  float mx = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
-    mx = fmaxf(mx, fabsf(W[i]));
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-  if ((threadIdx.x & 31) == 0 && isfinite(mx)) atomicMax(absmax, __float_as_uint(mx));
-}
-
 // Pack one Dense kernel W[K][N] (flax layout) into the block-major unit stream of one direction,
 // scaled by the power of two that puts max |W| in [2^10, 2^11).
 //   transposed == 0 (forward):  A rows r = output feature n, reduction kk = input feature k.
@@ -1235,6 +1227,7 @@ struct H16State {
   size_t smem_bytes = 0;
   int num_sms = 0;
   int n = 0, m = 0, fout = 0;
+  uint32_t exp_ = 0;  // GMPC_H16_EXP, read once at create (timing experiments of the TIMED build)
   int cluster = 1;  // B200: multicast did not pay for this stream (12.6 ms vs 13.0 ms on C2)
   int max_clusters[5] = {0, 0, 0, 0, 0};
   int last_cluster = 1;
@@ -1377,6 +1370,7 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
   }
   cudaGetLastError();
   if (const char* env = getenv("GMPC_TC_CLUSTER")) S.cluster = atoi(env);
+  if (const char* env = getenv("GMPC_H16_EXP")) S.exp_ = (uint32_t)atoi(env);
   if (S.cluster != 1 && S.cluster != 2 && S.cluster != 4) S.cluster = 1;
   while (S.cluster > 1 && S.max_clusters[S.cluster] <= 0) S.cluster >>= 1;
   if (getenv("GMPC_DEBUG")) {
@@ -1456,7 +1450,7 @@ inline int h16_launch(H16State& S, const PlanParams& P, bool fscale, cudaStream_
   Q.wide = S.wide;
   Q.hb_bytes = S.hb_bytes;
   for (int d = 0; d < 4; ++d) { Q.gtab[d] = S.d_gtab + S.gtab_off[d]; Q.ngroups[d] = S.ngroups[d]; }
-  if (const char* env = getenv("GMPC_H16_EXP")) Q.exp_ = (uint32_t)atoi(env);
+  Q.exp_ = S.exp_;
   Q.NQ = P.NQ;
   Q.ntiles = (int)((P.NQ + H_NB - 1) / H_NB);
   Q.lr = P.lr; Q.b1 = P.b1; Q.b2 = P.b2; Q.eps = P.eps;

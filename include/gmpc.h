@@ -38,12 +38,16 @@ extern "C" {
 #define GMPC_MAX_LAYERS 8
 
 /* kernel family used for the MLP contractions */
-#define GMPC_PATH_AUTO 0 /* tcgen05 when the tile is a real dense contraction, else FFMA */
+#define GMPC_PATH_AUTO 0 /* tcgen05 (T128, else TC16S) when the tile is a real dense contraction (>= 64 trajectories,
+                            hidden >= 64), else FFMA */
 #define GMPC_PATH_FFMA 1 /* fp32 CUDA-core path (exact fp32 FMA arithmetic) */
-#define GMPC_PATH_TC 2   /* tcgen05 3xTF32 tensor-core path (error if shape unsupported) */
+#define GMPC_PATH_TC 2   /* (retired) the first, 3xTF32 tensor-core kernel: gmpc_set_path answers GMPC_E_UNSUPPORTED */
 #define GMPC_PATH_TC16 3 /* tcgen05 fp16-split (hi/lo, 3 products, fp32 accumulate) path, pipelined */
 #define GMPC_PATH_TC16S 4 /* same, with per-trajectory power-of-two scaling of the forward operands too
                             (states of any magnitude; ~6 % slower).  Hidden widths above 256 always use it. */
+#define GMPC_PATH_T128 5  /* tcgen05 fp16-split, 128-trajectory tiles: trajectories are the M dimension, the
+                            activations live in tensor memory as the A operand, weights stream through shared
+                            memory as B; forward and adjoint operands rescaled per trajectory (hidden <= 256) */
 
 typedef struct gmpc_config {
   int32_t n;             /* state size x_size                       (dynamics/nn.py:13 x_out) */
@@ -76,7 +80,7 @@ int64_t gmpc_critic_param_count(const gmpc_handle* h);
 
 /* Select the contraction path (GMPC_PATH_*).  Default AUTO. */
 int gmpc_set_path(gmpc_handle* h, int path);
-/* Which path the last plan/objective call actually used (GMPC_PATH_FFMA, _TC or _TC16). */
+/* Which path the last plan/objective call actually used (GMPC_PATH_FFMA, _TC16, _TC16S or _T128). */
 int gmpc_last_path(const gmpc_handle* h);
 
 /* Stage model weights (copied and re-packed inside the handle; safe to free after return of
@@ -202,13 +206,15 @@ int gmpc_critic_input_grad(gmpc_handle* h, int64_t Bc, int32_t T1, const float* 
  * outer iterations and rollouts (1 + line-search trials) summed over the 32-trajectory tiles. */
 int gmpc_ilqr_stats(gmpc_handle* h, int64_t* outer_iterations, int64_t* rollouts, void* stream);
 
-/* The fp16-split tensor-core kernel (GMPC_PATH_TC16) represents operands as fp16 hi + lo parts; an
- * operand magnitude above 65000 (states, actions or hidden activations; adjoints are rescaled per
- * trajectory and cannot overflow) is clamped and counted.  This call synchronises `stream`, returns
- * the number of CTAs that clamped since the last call in *count and resets the counter.  A non-zero
- * count means the results of those calls are outside the 1e-4 parity contract: re-run them with
- * GMPC_PATH_TC16S (forward operands rescaled per trajectory), GMPC_PATH_FFMA or GMPC_PATH_TC.
- * gmpc_plan_host does this by itself when the path is AUTO (TC16 -> TC16S -> FFMA). */
+/* The fp16-split tensor-core kernels represent operands as fp16 hi + lo parts.  GMPC_PATH_T128 and
+ * GMPC_PATH_TC16S (what AUTO picks) rescale every forward and adjoint operand per trajectory by an exact
+ * power of two, so states of any magnitude are in range; the opt-in GMPC_PATH_TC16 does not rescale the
+ * forward operands.  A scaled operand above 65000 (only hidden activations ~4000 x larger than their layer's
+ * input can get there) is clamped and counted.  This call synchronises `stream`, returns the number of CTAs
+ * that clamped since the last call in *count and resets the counter.  A non-zero count means the results of
+ * those calls are outside the 1e-4 parity contract: re-run them on GMPC_PATH_FFMA.  gmpc_plan_host does this by
+ * itself when the path is AUTO; the device-pointer gmpc_plan never synchronises, so its callers check this
+ * counter themselves (the Python mirror does: _lib.Handle.plan(check_range=True), EvalMPC._plan). */
 int gmpc_range_overflow(gmpc_handle* h, int32_t* count, void* stream);
 
 /* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
@@ -297,19 +303,10 @@ int gmpc_l2_loss(gmpc_handle* h, int64_t B, const float* X, const float* desired
  * second roofline denominator bench.py reports for the CUDA-core path. */
 int gmpc_measure_fp32_peak(int device, float* tflops_out);
 
-/* Diagnostics: one tcgen05 kind::tf32 contraction D[128][NB] = A[128][K] * B[NB][K]^T with
- * caller-chosen shared-memory image strides and descriptor LBO/SBO (SWIZZLE_NONE).  HOST
- * pointers.  Pins the descriptor semantics the tensor-core planner relies on. */
-int gmpc_tc_probe(int device, int K, int NB, int a_major, uint32_t a_lbo, uint32_t a_sbo,
-                  uint32_t a_s1, uint32_t a_s2, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo,
-                  uint32_t b_s1, uint32_t b_s2, uint32_t a_bytes, uint32_t smem_bytes,
-                  const float* A_host, const float* B_host, float* D_host);
-
-/* Diagnostics: tcgen05.mma (M=128, N, K=8 tf32) cycles per instruction for a given operand
- * layout, issued the way the planner issues them (timing only). */
-int gmpc_tc_mma_bench(int device, int grid, int N, int ksteps, int reps, uint32_t a_lbo,
-                      uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo,
-                      uint32_t b_kstep, uint32_t layout_type, int two_mma, double* cycles_per_mma);
+/* Diagnostics: dense kind::f16 tcgen05 throughput of `device` in TFLOP/s (every SM issuing M=128, N=256,
+ * K=16 MMAs from shared memory): the peak of the tensor pipe the planner kernels run on.  With the
+ * three-product fp16 split (ah Wh + al Wh + ah Wl) the algorithmic ceiling is a third of it. */
+int gmpc_measure_f16_mma_peak(int device, float* tflops_out);
 
 #ifdef __cplusplus
 }

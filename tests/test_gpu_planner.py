@@ -14,7 +14,7 @@ from tests import util
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-PATHS = ["ffma", "tc", "tc16", "tc16s"]
+PATHS = ["ffma", "tc16", "tc16s", "t128"]
 
 
 def select_path(h, path):
@@ -118,7 +118,14 @@ def test_plan_c2_dims_full_horizon(method, path, built_lib):
         print(f"{method} fp32 floor {name} (oracle32 vs oracle64): median {float(fl.median()):.2e}, "
               f"max {float(fl.max()):.2e}, rows >= 1e-4: {int((fl >= 1e-4).sum())}")
         util.assert_rows_close(name, (Ub, Xb)[i], o64[i], TOL)
-    util.assert_rows_close("J", Jb[:, None], o64[2][:, None], TOL, outlier_frac=0.0, cap=TOL * 10)
+    # t128 accumulates the three split products of a layer in ONE TMEM accumulator (39 accumulate events per
+    # 208-wide layer instead of 13); the tensor core truncates on accumulation, which shows as a uniform
+    # relative shrink of ~6e-7 per step (J ~ |x|^2: twice that).  Every row must still be inside the north
+    # star's flat 1e-4 (cap = TOL, stricter than the other paths' cap), the median inside half of it.
+    if path == "t128":
+        util.assert_rows_close("J", Jb[:, None], o64[2][:, None], TOL, outlier_frac=0.0, cap=TOL, median_frac=0.5)
+    else:
+        util.assert_rows_close("J", Jb[:, None], o64[2][:, None], TOL, outlier_frac=0.0, cap=TOL * 10)
     assert torch.equal(idx.cpu(), o64[3])
 
 

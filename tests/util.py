@@ -59,7 +59,7 @@ def rel_each(a, b):
     return (a - b).norm(dim=1) / (b.norm(dim=1) + 1e-30)
 
 
-def assert_rows_close(name, k, o, tol=1e-4, outlier_frac=0.1, cap=5e-2):
+def assert_rows_close(name, k, o, tol=1e-4, outlier_frac=0.1, cap=5e-2, median_frac=0.25):
     """Row-wise (trajectory-norm-wise) parity after N planning iterations.
 
     The planner's trajectory through U-space is not continuous in the arithmetic: a hidden
@@ -72,5 +72,5 @@ def assert_rows_close(name, k, o, tol=1e-4, outlier_frac=0.1, cap=5e-2):
     nbad = int((e >= tol).sum())
     print(f"{name}: rows {len(e)}, median {float(e.median()):.2e}, max {float(e.max()):.2e}, rows >= {tol:g}: {nbad}")
     assert float(e.max()) < cap, f"{name}: max row error {float(e.max()):.3e}"
-    assert float(e.median()) < tol / 4, f"{name}: median row error {float(e.median()):.3e}"
+    assert float(e.median()) < tol * median_frac, f"{name}: median row error {float(e.median()):.3e}"
     assert nbad <= max(2, int(outlier_frac * len(e))), f"{name}: {nbad} rows above {tol}"
