@@ -41,17 +41,22 @@ namespace gmpc {
 constexpr int T_NB = 128;                          // trajectories per tile
 constexpr int T_EPI_WARPS = 16;                    // 4 per TMEM lane quarter
 constexpr int T_EPI = T_EPI_WARPS * 32;            // 512 epilogue threads
-constexpr int T_THREADS = T_EPI + 64;              // + producer warp + issuer warp
+constexpr int T_FRONT = 3;                         // producer warp + two MMA issuer warps (N-part 0 / N-part 1)
+constexpr int T_THREADS = T_EPI + 32 * T_FRONT;
 constexpr int T_MAXKS = 16;                        // k-steps of the widest operand (hidden <= 256)
-constexpr int T_MAX_SLOTS = 16;
+constexpr int T_PKS = 8;                           // k-steps one N-part of a layer defines (half of T_MAXKS)
+constexpr int T_MAX_SLOTS = 32;
 constexpr uint32_t T_D_COL = 0, T_AH_COL = 256, T_AL_COL = 384;  // TMEM columns: D | A hi | A lo
 
+// A layer's MMAs go out as two N-parts (output columns [0, n0) for every k-step, then [n0, npad)): the
+// accumulator of part 0 is complete, read out and processed while the tensor pipe works on part 1.
 struct TLayer {
-  uint32_t goff;           // byte offset of this layer's tiles in the image of its pass
+  uint32_t goff[2];        // byte offset of the tiles of N-part p in the image of the pass
+  int ncol[2];             // output columns (MMA N) of N-part p; ncol[1] == 0: single part (<= 32 columns)
+  int kpg[2];              // k-steps per ring group (one bulk copy, one slot) of part p
   int M_true;              // output features of this (possibly transposed) layer
-  int npad;                // MMA N = round_up(M_true, 16)
+  int npad;                // round_up(M_true, 16) = ncol[0] + ncol[1]
   int nks;                 // reduction k-steps (round_up(K, 16) / 16)
-  int kpg;                 // k-steps per ring group (one bulk copy, one slot)
   int bias_off;            // offset of the layer's bias in the bias table (forward layers)
   int scale_idx;           // index into the inverse weight scale table
   int pad_;
@@ -78,9 +83,38 @@ struct TParams {
   float *ws_X, *ws_G, *ws_U, *ws_M, *ws_V;   // per-CTA scratch, [..][128] trajectory-minor
   uint32_t* ws_mask;       // [grid][T (Ld-1) + (Lc-1)][2][512]
   uint32_t* ovf;           // incremented by a CTA that clamped an fp16 operand
+  long long* dbg;          // cycle counters of CTA 0 (builds with -DGMPC_T128_TIMED only)
 };
 
 // The pass schedule: iters x {T dyn fwd, [cost fwd, cost bwd], T dyn bwd}, then the final evaluation.
+#ifdef GMPC_T128_TIMED
+#define T128_TRACE(layer_no, slot) do { if (blockIdx.x == 0 && P.dbg != nullptr && (layer_no) >= 2000 && (layer_no) < 2003) \
+    P.dbg[256 + ((layer_no) - 2000) * 128 + (slot)] = clock64(); } while (0)
+#else
+#define T128_TRACE(layer_no, slot)
+#endif
+
+#ifdef GMPC_T128_TIMED
+__device__ __forceinline__ void t_wait_dbg(uint32_t bar, uint32_t parity, int tag, int layer, long long* dbg) {
+  if (mbar_try_wait_a(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (dbg != nullptr && *((volatile long long*)(dbg + 701)) > 40) return;   // the run is lost: let everybody fall through
+    if (clock64() - t0 > 20000000LL) {
+      if (dbg != nullptr) {
+        const unsigned long long i = atomicAdd((unsigned long long*)(dbg + 700), 1ULL);
+        if (i < 96) dbg[704 + i] = ((long long)tag << 40) | ((long long)(threadIdx.x >> 5) << 32) | (unsigned)layer;
+        atomicAdd((unsigned long long*)(dbg + 701), 1ULL);
+      }
+      return;
+    }
+  }
+}
+#define T_WAIT(bar, par, tag, layer) t_wait_dbg(bar, par, tag, layer, P.dbg)
+#else
+#define T_WAIT(bar, par, tag, layer) mbar_wait_a(bar, par)
+#endif
+
 struct TPassWalk {
   int pp = 0, itc = 0;
   __device__ __forceinline__ int next(const TParams& P) {
@@ -117,7 +151,7 @@ __host__ __device__ inline TSmem t_smem_layout(int nslot, uint32_t slot_bytes, i
   s.ssc = s.us + (uint32_t)m * T_NB * 4;
   s.sig = s.ssc + T_NB * 4;
   s.bars = s.sig + 2 * T_NB * 4;
-  s.total = s.bars + 8 * (2 * T_MAX_SLOTS + 2 + T_MAXKS) + 16;
+  s.total = s.bars + 8 * (2 * T_MAX_SLOTS + 5 + 2 * T_MAXKS) + 16;
   return s;
 }
 
@@ -142,7 +176,6 @@ __device__ __forceinline__ void t_st8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void t_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int MAXKS>
 __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_constant__ TParams P) {
   extern __shared__ __align__(128) uint8_t tsm[];
   const TSmem L = t_smem_layout(P.nslot, P.slot_bytes, P.nbias, P.nscale, P.n, P.m);
@@ -155,10 +188,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
   float* sig_s = reinterpret_cast<float*>(tsm + L.sig);   // [2][128] adjoint operand scale, by step parity
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tsm + L.bars);
   uint64_t* empty_bar = full_bar + T_MAX_SLOTS;
-  uint64_t* acc_bar = empty_bar + T_MAX_SLOTS;   // all MMAs of a layer are complete
-  uint64_t* dr_bar = acc_bar + 1;                // every epilogue warp has read the accumulator out
-  uint64_t* act_bar = dr_bar + 1;                // [MAXKS] k-step j of the next operand is in TMEM
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(act_bar + T_MAXKS);
+  uint64_t* acc_bar = empty_bar + T_MAX_SLOTS;   // [2] all MMAs of N-part p of a layer are complete
+  uint64_t* dr_bar = acc_bar + 2;                // [2] every epilogue warp has read part p of the accumulator out
+  uint64_t* act_bar = dr_bar + 2;                // [MAXKS] k-step j of the next operand is in TMEM (4 arrivals: its owner warps)
+  uint64_t* rel_bar = act_bar + T_MAXKS;         // [MAXKS] the layer's last MMAs that read k-step j of the current operand are complete
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(rel_bar + T_MAXKS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = P.n, m = P.m, T = P.T, NS = P.nslot;
@@ -171,9 +205,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_bar, 1);
-    mbar_init(dr_bar, T_EPI_WARPS);
-    for (int j = 0; j < T_MAXKS; ++j) mbar_init(&act_bar[j], T_EPI_WARPS);
+    mbar_init(&acc_bar[0], 1);
+    mbar_init(&acc_bar[1], 1);
+    mbar_init(&dr_bar[0], T_EPI_WARPS);
+    mbar_init(&dr_bar[1], T_EPI_WARPS);
+    for (int j = 0; j < T_MAXKS; ++j) {
+      mbar_init(&act_bar[j], 4);
+      mbar_init(&rel_bar[j], 1);
+    }
     mbar_fence_init();
   }
   __syncwarp();
@@ -200,35 +239,52 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
           const TDir& D = P.dir[kind];
           for (int l = 0; l < D.L; ++l) {
             const TLayer& Y = D.layer[l];
-            const uint32_t kb = (uint32_t)Y.npad * 64u;
-            uint32_t off = Y.goff;
-            for (int j = 0; j < Y.nks; j += Y.kpg) {
-              const uint32_t bytes = (uint32_t)min(Y.kpg, Y.nks - j) * kb;
-              if ((gc & 3u) == (uint32_t)lane) {
-                mbar_wait_a(empty_a + slot * 8, ph ^ 1);
-                const uint32_t bar = full_a + slot * 8;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                    ::"r"(ring_a + slot * P.slot_bytes), "l"(D.gsrc + off), "r"(bytes), "r"(bar) : "memory");
+            for (int pt = 0; pt < 2; ++pt) {
+              if (Y.ncol[pt] == 0) continue;
+              const uint32_t kb = (uint32_t)Y.ncol[pt] * 64u;
+              uint32_t off = Y.goff[pt];
+              for (int j = 0; j < Y.nks; j += Y.kpg[pt]) {
+                const uint32_t bytes = (uint32_t)min(Y.kpg[pt], Y.nks - j) * kb;
+                if ((gc & 3u) == (uint32_t)lane) {
+                  T_WAIT(empty_a + slot * 8, ph ^ 1, 30, (int)gc);
+                  const uint32_t bar = full_a + slot * 8;
+                  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                  asm volatile(
+                      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                      ::"r"(ring_a + slot * P.slot_bytes), "l"(D.gsrc + off), "r"(bytes), "r"(bar) : "memory");
+                }
+                off += bytes;
+                ++gc;
+                if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
               }
-              off += bytes;
-              ++gc;
-              if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
             }
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ================================================================== MMA issuer (one thread)
+  } else if (warp == 1 || warp == 2) {
+    // ================================================================== MMA issuers (one thread each)
+    // A single thread issues dependent instructions ~5 cycles apart: with descriptor arithmetic, R2UR moves
+    // and mbarrier probes one tcgen05.mma costs it 40-130 cycles, a split MMA only 40-64 tensor cycles.
+    // Issuer 0 therefore issues N-part 0 of every layer (and the whole of a single-part layer), issuer 1
+    // N-part 1, concurrently: both wait for the operand k-step by k-step (act_bar), accumulator columns of the
+    // two parts are disjoint and every other ordering is carried by the mbarriers, so the two instruction
+    // streams may interleave freely on the tensor pipe.
+    const int which = warp - 1;
     if (elect_one()) {
       const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), ring_a = smem_u32(tsm + L.ring);
-      const uint32_t acc_a = smem_u32(acc_bar), dr_a = smem_u32(dr_bar), act_a = smem_u32(act_bar);
+      const uint32_t acc_a = smem_u32(acc_bar) + 8 * which, dr_a = smem_u32(dr_bar), act_a = smem_u32(act_bar);
+      const uint32_t rel_a = smem_u32(rel_bar);
       const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 0, 128) >> 32);
       const uint32_t d_t = tmem_base + T_D_COL, ah_t = tmem_base + T_AH_COL, al_t = tmem_base + T_AL_COL;
+      const uint32_t slot16 = P.slot_bytes >> 4, ring16 = ring_a >> 4;
       uint32_t slot = 0, ph = 0, act_par = 0, dr_par = 0;
+      int lno = -1;
+      auto skip_slots = [&](int ng) {
+        slot += (uint32_t)ng;
+        while (slot >= (uint32_t)NS) { slot -= (uint32_t)NS; ph ^= 1; }
+      };
       for (int ti = 0; ti < my_tiles; ++ti) {
         TPassWalk walk;
         for (;;) {
@@ -237,29 +293,67 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
           const TDir& D = P.dir[kind];
           for (int l = 0; l < D.L; ++l) {
             const TLayer& Y = D.layer[l];
-            const uint32_t idesc = t_idesc(Y.npad);
-            const uint32_t tile16 = ((uint32_t)Y.npad * 32u) >> 4;           // one (hi or lo) tile, in 16-byte units
-            const uint32_t lbo_f = (((uint32_t)Y.npad * 16u) >> 4) << 16;    // LBO field of the descriptor
-            int j = 0;
-            while (j < Y.nks) {
-              const int nk = min(Y.kpg, Y.nks - j);
-              uint32_t b_lo = ((ring_a + slot * P.slot_bytes) >> 4) | lbo_f;
-              for (int jj = 0; jj < nk; ++jj, ++j, b_lo += 2 * tile16) {
-                mbar_wait_a(act_a + 8 * j, (act_par >> j) & 1u);
-                act_par ^= 1u << j;
-                if (j == 0) { mbar_wait_a(dr_a, dr_par); dr_par ^= 1; }
-                if (jj == 0) mbar_wait_a(full_a + slot * 8, ph);
+            const int nks = Y.nks, n0 = Y.ncol[0], n1 = Y.ncol[1];
+            const int ng0 = (nks + Y.kpg[0] - 1) / Y.kpg[0], ng1 = n1 ? (nks + Y.kpg[1] - 1) / Y.kpg[1] : 0;
+            const bool single = (n1 == 0);
+            const uint32_t lay_mask = (1u << nks) - 1u;
+            ++lno;
+            T128_TRACE(lno, which * 40 + 0);
+            if (which == 1) skip_slots(ng0);
+            // Every epilogue warp has read the previous layer's accumulator out (both parts).  Besides the
+            // write-after-read hazard on the accumulator columns this keeps every mbarrier at most ONE phase
+            // ahead of its slowest waiter: a warp arrives here only after it has passed both acc_bar waits of the
+            // previous layer, and nothing of this layer is committed before all sixteen have.
+            T_WAIT(dr_a, dr_par, 1 + 10 * which, lno);
+            T_WAIT(dr_a + 8, dr_par, 2 + 10 * which, lno);
+            dr_par ^= 1;
+            T128_TRACE(lno, which * 40 + 1);
+            if (which == 1 && single) {
+              // nothing to issue, but every phase of every barrier must be OBSERVED: a waiter that only flipped its
+              // parity bits could run two phases ahead and then pass a parity wait on a stale phase
+              for (int j = 0; j < nks; ++j) T_WAIT(act_a + 8 * j, (act_par >> j) & 1u, 15, lno * 16 + j);
+              act_par ^= lay_mask;
+              continue;
+            }
+            const int ncol = which ? n1 : n0, kpg = Y.kpg[which];
+            const uint32_t idesc = t_idesc(ncol);
+            const uint32_t tile16 = ((uint32_t)ncol * 32u) >> 4;          // one (hi or lo) tile, in 16-byte units
+            const uint32_t lbo_f = (((uint32_t)ncol * 16u) >> 4) << 16;   // LBO field of the descriptor
+            const uint32_t d_p = d_t + (which ? (uint32_t)n0 : 0u);
+            const bool commit_rel = which == 1 || single;
+            uint32_t a_off = 0;           // 8 j: TMEM column offset of k-step j of the operand, byte offset of its barriers
+            uint32_t par = act_par;       // bit 0 = parity of the barrier of the k-step about to be issued
+            int left = nks;
+            while (left > 0) {
+              const int nk = left < kpg ? left : kpg;
+              left -= nk;
+              T_WAIT(full_a + slot * 8, ph, 3 + 10 * which, lno);
+              uint32_t b_lo = (ring16 + slot * slot16) | lbo_f;
+#pragma unroll 1
+              for (int jj = 0; jj < nk; ++jj) {
+                T_WAIT(act_a + a_off, par & 1u, 4 + 10 * which, lno * 16 + (int)(a_off >> 3));
+                par >>= 1;
                 tc_fence_after();
                 const uint64_t bh = ((uint64_t)desc_hi << 32) | b_lo;
                 const uint64_t bl = ((uint64_t)desc_hi << 32) | (b_lo + tile16);
-                t_mma(d_t, ah_t + 8 * j, bh, idesc, j > 0 ? 1u : 0u);
-                t_mma(d_t, al_t + 8 * j, bh, idesc, 1u);
-                t_mma(d_t, ah_t + 8 * j, bl, idesc, 1u);
+                t_mma(d_p, ah_t + a_off, bh, idesc, a_off);          // accumulate = (j > 0)
+                t_mma(d_p, al_t + a_off, bh, idesc, 1u);
+                t_mma(d_p, ah_t + a_off, bl, idesc, 1u);
+                // the layer's last read of k-step j of the operand: the epilogue may overwrite it from here on
+                if (commit_rel) umma_commit_a(rel_a + a_off);
+                T128_TRACE(lno, which * 40 + 2 + (int)(a_off >> 3));
+                a_off += 8;
+                b_lo += 2 * tile16;
               }
               umma_commit_a(empty_a + slot * 8);
               if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
             }
+            act_par ^= lay_mask;
             umma_commit_a(acc_a);
+            if (which == 0) {
+              if (single) umma_commit_a(acc_a + 8);          // both accumulator phases complete together
+              skip_slots(ng1);
+            }
           }
         }
       }
@@ -267,15 +361,18 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
     __syncwarp();
   } else {
     // ================================================================== epilogue / per-trajectory work
-    const int ew = warp - 2;               // 0..15
+    const int ew = warp - T_FRONT;         // 0..15
     const int q = warp & 3;                // TMEM lane quarter this warp may access
     const int sub = ew >> 2;               // which 4 of every 16 features; sub 0 also owns the trajectory's state,
                                            // sub 1 its action update
     const int r = q * 32 + lane;           // trajectory (TMEM lane) in the tile
     const int et = ew * 32 + lane;         // 0..511
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t acc_a = smem_u32(acc_bar), dr_a = smem_u32(dr_bar), act_a = smem_u32(act_bar);
-    uint32_t acc_ph = 0;
+    const uint32_t acc_a = smem_u32(acc_bar), dr_a = smem_u32(dr_bar), act_a = smem_u32(act_bar), rel_a = smem_u32(rel_bar);
+    uint32_t acc_ph = 0, rel_par = 0;
+    int cur_kind = 0, elno = -1, elno2 = 0;
+    const bool tr_on = (q == 0 && lane == 0);
+    const int tr_base = 80 + sub * 12;
     const bool cost_mode = (P.mode == MODE_PLAN || P.mode == MODE_OBJGRAD);
     float w0 = 0.f, w1 = 0.f, w2 = 0.f;
     if (cost_mode) {
@@ -305,19 +402,48 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
     const int nk_costb = P.use_cost ? P.dir[DIR_COST_B].layer[0].nks : 0;
     float opmax = 0.f;  // largest operand magnitude this thread has written (fp16 range check)
 
+#ifdef GMPC_T128_TIMED
+    long long e_acc = 0, e_hid = 0, e_bnd = 0, e_ld = 0, e_alu0 = 0, e_acc1 = 0, e_pub0 = 0, e_p1 = 0, eq, eh, ex;
+    long long e_last = clock64(), e_lay[32];
+    int e_prev = -1;
+    for (int i = 0; i < 32; ++i) e_lay[i] = 0;
+    auto lay_mark = [&](int id) {
+      const long long now = clock64();
+      if (e_prev >= 0) e_lay[e_prev] += now - e_last;
+      e_last = now;
+      e_prev = id;
+    };
+    const long long e_begin = clock64();
+#define T128_E0(v) v = clock64()
+#define T128_E1(acc, v) acc += clock64() - v
+#else
+#define T128_E0(v)
+#define T128_E1(acc, v)
+#endif
+    // all MMAs of the layer (both N-parts) are complete
     auto wait_acc = [&]() {
-      mbar_wait_a(acc_a, acc_ph);
+      T128_E0(eq);
+      T_WAIT(acc_a, acc_ph, 20, elno2);
+      T_WAIT(acc_a + 8, acc_ph, 21, elno2);
+      ++elno2;
+      T128_E1(e_acc, eq);
+#ifdef GMPC_T128_TIMED
+      lay_mark(cur_kind * 8 + 7);
+      ++elno;
+      if (tr_on) T128_TRACE(elno, tr_base + 0);
+#endif
       acc_ph ^= 1;
       tc_fence_after();
     };
-    // "my reads of the accumulator are complete" (after tcgen05.wait::ld)
+    // "my reads of the accumulator (both parts) are complete" (after tcgen05.wait::ld)
     auto arrive_drained = [&]() {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(dr_a);
+      if (lane == 0) { mbar_arrive_a(dr_a); mbar_arrive_a(dr_a + 8); }
     };
-    // "k-steps [0, nk) of the next operand: my part is in TMEM" (after tcgen05.wait::st)
+    // sub 0 (the four warps that wrote it): "k-steps [0, nk) of the next operand are in TMEM" (after tcgen05.wait::st)
     auto arrive_act_range = [&](int nk) {
+      if (sub != 0) return;
       tc_fence_before();
       __syncwarp();
       if (lane == 0)
@@ -433,6 +559,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
         const TDir& D = P.dir[kind];
         const bool last = (it == P.iters);
         const bool fwd = (kind == DIR_DYN_F || kind == DIR_COST_F);
+        cur_kind = kind;
         if (kind == DIR_DYN_F && tf == 0) {
           // ------------------------------------------------------------ start of a forward sweep
           named_bar_sync(1, T_EPI);  // the previous sweep's updates of U are visible
@@ -466,65 +593,120 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
           else maskp = wsMask + ((size_t)tb * (Ld - 1) + (D.L - 2 - l)) * MSTR;
           // accumulator -> (+bias, ReLU, mask bit) or (mask gate) -> hi/lo -> next A operand.  The forward pass
           // runs in scaled units a' = a s (ReLU is positively homogeneous): the bias enters as b s.
-          const int nko = Y.npad >> 4;
-          uint32_t m0 = 0, m1 = 0;
-          if (!fwd) { m0 = maskp[0]; m1 = maskp[T_EPI]; }
+          // k-step j of the next operand (features [16 j, 16 j + 16)) belongs to sub j % 4.  Part 0 (k-steps
+          // [0, nk0)) is read out, processed AND stored while the tensor pipe works on part 1: k-step j of the
+          // operand in flight may be overwritten as soon as part 1's MMAs of k-step j are complete (rel_bar[j]).
+          const int nk0 = Y.ncol[0] >> 4, nk1 = Y.ncol[1] >> 4;
           const float inv = inv_s[Y.scale_idx];
-          const float* bp = bias_s + Y.bias_off + 4 * sub;
-          wait_acc();
-          const float s = fwd ? ssc_s[r] : 1.f;
-          uint32_t d[MAXKS][4];
+          const float* bp = bias_s + Y.bias_off;
+          float s = 1.f;
+          // 16 accumulator values (one k-step of the next operand) of this thread's trajectory -> packed hi / lo halfs
+          auto process16 = [&](const uint32_t (&raw)[16], int jg, uint32_t& mw, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+            float z[16];
+            if (fwd) {
 #pragma unroll
-          for (int j = 0; j < MAXKS; ++j)
-            if (j < nko) t_ld4(tl + T_D_COL + 16 * j + 4 * sub, d[j]);
-          tmem_ld_wait();
-          arrive_drained();
-#pragma unroll
-          for (int j = 0; j < MAXKS; ++j) {
-            if (j < nko) {
-              float z[4];
-              if (fwd) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bp + 16 * j);
-                z[0] = fmaf(__uint_as_float(d[j][0]), inv, b4.x * s);
-                z[1] = fmaf(__uint_as_float(d[j][1]), inv, b4.y * s);
-                z[2] = fmaf(__uint_as_float(d[j][2]), inv, b4.z * s);
-                z[3] = fmaf(__uint_as_float(d[j][3]), inv, b4.w * s);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  // bit = (z > 0): 0 - z is negative exactly then (and +0 for z == 0)
-                  if (j < 8) m0 = __funnelshift_l(__float_as_uint(0.f - z[c]), m0, 1);
-                  else       m1 = __funnelshift_l(__float_as_uint(0.f - z[c]), m1, 1);
-                  z[c] = fmaxf(z[c], 0.f);
-                }
-              } else {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const float v = __uint_as_float(d[j][c]) * inv;
-                  if (j < 8) { z[c] = ((int)m0 < 0) ? v : 0.f; m0 <<= 1; }
-                  else       { z[c] = ((int)m1 < 0) ? v : 0.f; m1 <<= 1; }
-                }
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bp + 16 * jg + 4 * c4);
+                z[4 * c4 + 0] = fmaf(__uint_as_float(raw[4 * c4 + 0]), inv, b4.x * s);
+                z[4 * c4 + 1] = fmaf(__uint_as_float(raw[4 * c4 + 1]), inv, b4.y * s);
+                z[4 * c4 + 2] = fmaf(__uint_as_float(raw[4 * c4 + 2]), inv, b4.z * s);
+                z[4 * c4 + 3] = fmaf(__uint_as_float(raw[4 * c4 + 3]), inv, b4.w * s);
               }
-              opmax = fmaxf(opmax, fmaxf(fmaxf(fabsf(z[0]), fabsf(z[1])), fmaxf(fabsf(z[2]), fabsf(z[3]))));
-              uint32_t h0, l0, h1, l1;
-              split_h2(z[0], z[1], h0, l0);
-              split_h2(z[2], z[3], h1, l1);
-              t_st2(tl + T_AH_COL + 8 * j + 2 * sub, h0, h1);
-              t_st2(tl + T_AL_COL + 8 * j + 2 * sub, l0, l1);
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                mw = __funnelshift_l(__float_as_uint(z[c]), mw, 1);   // collects the SIGN bits (complemented below)
+                z[c] = fmaxf(z[c], 0.f);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float v = __uint_as_float(raw[c]) * inv;
+                z[c] = ((int)mw < 0) ? v : 0.f;
+                mw <<= 1;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c += 4)
+              opmax = fmaxf(opmax, fmaxf(fmaxf(fabsf(z[c]), fabsf(z[c + 1])), fmaxf(fabsf(z[c + 2]), fabsf(z[c + 3]))));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) split_h2(z[2 * k], z[2 * k + 1], hi[k], lo[k]);
+          };
+          T128_E0(eh);
+#pragma unroll 1
+          for (int pt = 0; pt < 2; ++pt) {
+            // part 0 runs under the MMAs of part 1, part 1 after the layer's last MMA
+            T128_E0(eq);
+            T_WAIT(acc_a + 8 * pt, acc_ph, 22 + pt, elno2);
+            if (pt == 1) ++elno2;
+            T128_E1(e_acc, eq);
+#ifdef GMPC_T128_TIMED
+            if (pt == 0) { lay_mark(kind * 8 + l); ++elno; }
+            if (tr_on) T128_TRACE(elno, tr_base + pt * 6 + 0);
+#endif
+            tc_fence_after();
+            if (pt == 0 && fwd) s = ssc_s[r];
+            const int jbeg = pt ? nk0 : 0, jend = pt ? nk0 + nk1 : nk0, dcol = pt ? Y.ncol[0] : 0;
+            const bool need_rel = (pt == 0 && nk1 > 0);
+            uint32_t mw = fwd ? 0u : maskp[pt * T_EPI];
+            int nb = 0;
+            const int jfirst = jbeg + ((sub - jbeg) & 3);   // my first k-step of this part (k-step j belongs to sub j % 4)
+            if (jfirst >= jend) {                           // none: nothing of this part to read
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_a(dr_a + 8 * pt);
+            }
+            uint32_t raw[16];
+            if (jfirst < jend) {
+              tmem_ld16_issue(tl + T_D_COL + dcol + 16 * (jfirst - jbeg), raw);
+              tmem_ld_wait();
+            }
+#pragma unroll 1
+            for (int j = jfirst; j < jend; j += 4) {
+              uint32_t nxt[16], hi[8], lo[8];
+              const bool more = j + 4 < jend;
+              // the read of my next k-step is in flight under the arithmetic of this one (16 warps reading at once
+              // are bound by the ~64 B/clk TMEM read path)
+              if (more) tmem_ld16_issue(tl + T_D_COL + dcol + 16 * (j + 4 - jbeg), nxt);
+              else {   // my last read of this part of the accumulator is complete
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(dr_a + 8 * pt);
+              }
+              if (tr_on) T128_TRACE(elno, tr_base + pt * 6 + 1 + 2 * ((j - jfirst) >> 2));
+              T128_E0(ex);
+              process16(raw, j, mw, hi, lo);
+              nb += 16;
+              T128_E1(e_alu0, ex);
+              T128_E0(ex);
+              if (need_rel && j < Y.nks) T_WAIT(rel_a + 8 * j, (rel_par >> j) & 1u, 24, elno2 * 16 + j);
+              T128_E1(e_acc1, ex);
+              T128_E0(ex);
+              t_st8(tl + T_AH_COL + 8 * j, hi);
+              t_st8(tl + T_AL_COL + 8 * j, lo);
               t_st_wait();
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive_a(act_a + 8 * j);
+              T128_E1(e_pub0, ex);
+              if (more) {
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) raw[c] = nxt[c];
+              }
             }
+            // sign bits -> (z >= +0) bits, first element at bit 31 (the adjoint sweep shifts them out in order)
+            if (fwd) maskp[pt * T_EPI] = nb == 0 ? 0u : (~mw) << (32 - nb);
           }
-          if (fwd) {  // first element's bit at bit 31 (the adjoint sweep shifts them out in the same order)
-            const int nb0 = 4 * min(nko, 8), nb1 = 4 * max(nko - 8, 0);
-            maskp[0] = nb0 < 32 ? m0 << (32 - nb0) : m0;
-            maskp[T_EPI] = nb1 == 0 ? 0u : (nb1 < 32 ? m1 << (32 - nb1) : m1);
-          }
+          acc_ph ^= 1;
+          rel_par ^= (1u << Y.nks) - 1u;
+          T128_E1(e_p1, ex);
+          T128_E1(e_hid, eh);
         }
+        T128_E0(eh);
         // -------------------------------------------------------------- last layer of the pass (<= 32 outputs)
         const TLayer& Yf = D.layer[D.L - 1];
         const float invf = inv_s[Yf.scale_idx];
+        rel_par ^= (1u << Yf.nks) - 1u;   // (the last layer's epilogues below start after all of its MMAs)
         if (kind == DIR_DYN_F) {
           // step boundary: x_{t+1} = x_t + Dense(h); sub 0 writes the next operand [x_{t+1} ; u_{t+1}] s_{t+1}
           const int t = tf;
@@ -770,6 +952,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
             __threadfence_block();  // this sweep's updates of U are read by sub 0 in the next sweep
           }
         }
+        T128_E1(e_bnd, eh);
       }
       __threadfence_block();
       named_bar_sync(1, T_EPI);
@@ -797,6 +980,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
       }
     }
     if (!(opmax <= 65000.f) && P.ovf != nullptr) atomicAdd(P.ovf, 1u);
+#ifdef GMPC_T128_TIMED
+    if (blockIdx.x == 0 && P.dbg != nullptr && lane == 0 && (ew == 0 || ew == 4)) {
+      long long* o = P.dbg + 8 + (ew >> 2) * 8;   // sub 0 and sub 1 of one lane quarter
+      o[0] = clock64() - e_begin; o[1] = e_acc; o[2] = e_hid; o[3] = e_bnd; o[4] = e_ld;
+      if (ew == 0) for (int i = 0; i < 32; ++i) P.dbg[64 + i] = e_lay[i];
+      P.dbg[24 + (ew >> 2) * 8 + 0] = e_alu0; P.dbg[24 + (ew >> 2) * 8 + 1] = e_acc1; P.dbg[24 + (ew >> 2) * 8 + 2] = e_pub0; P.dbg[24 + (ew >> 2) * 8 + 3] = e_p1;
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -810,10 +1001,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
 // by the power of two that puts max |W| in [2^10, 2^11) (same rule as h16_pack_kernel).
 //   transposed == 0 (forward):  operand row = output feature n, reduction index = input feature k.
 //   transposed == 1 (adjoint):  operand row = input feature k,  reduction index = output feature n.
-// Image: per k-step [hi tile | lo tile], tile = [2 k-chunks][npad rows][8 halfs]
-// (K-major SWIZZLE_NONE core matrices: LBO = npad * 16, SBO = 128; pinned by tools/t128_probe.cu).
-__global__ void t128_pack_kernel(const float* __restrict__ W, int K, int N, int transposed, uint8_t* dst, int npad,
-                                 const uint32_t* absmax, float* inv_scale) {
+// Image of a layer: N-part 0 (operand rows [0, n0)), then N-part 1 (rows [n0, n0 + n1)); per part, per k-step:
+// [hi tile | lo tile], tile = [2 k-chunks][rows of the part][8 halfs]
+// (K-major SWIZZLE_NONE core matrices: LBO = rows * 16, SBO = 128; pinned by tools/t128_probe.cu).
+__global__ void t128_pack_kernel(const float* __restrict__ W, int K, int N, int transposed, uint8_t* dst, int n0, int n1,
+                                 int nks, const uint32_t* absmax, float* inv_scale) {
   const float mx = __uint_as_float(*absmax);
   float sc = 1.f;
   if (mx > 0.f) {
@@ -826,12 +1018,16 @@ __global__ void t128_pack_kernel(const float* __restrict__ W, int K, int N, int 
   if (idx == 0 && inv_scale != nullptr) *inv_scale = 1.f / sc;
   if (idx >= K * N) return;
   const int k = idx / N, o = idx - k * N;
-  const int row = transposed ? k : o, kk = transposed ? o : k;
+  int row = transposed ? k : o;
+  const int kk = transposed ? o : k;
   __half hi, lo;
   split_h1(W[idx] * sc, hi, lo);
-  const size_t tile_b = (size_t)npad * 32;
+  const int part = row >= n0 ? 1 : 0;
+  const int rows = part ? n1 : n0;
+  if (part) { row -= n0; dst += (size_t)nks * n0 * 64; }
+  const size_t tile_b = (size_t)rows * 32;
   const int j = kk >> 4, k16 = kk & 15;
-  uint8_t* p = dst + (size_t)j * 2 * tile_b + (size_t)(k16 >> 3) * npad * 16 + (row >> 3) * 128 + (row & 7) * 16 + (k16 & 7) * 2;
+  uint8_t* p = dst + (size_t)j * 2 * tile_b + (size_t)(k16 >> 3) * rows * 16 + (row >> 3) * 128 + (row & 7) * 16 + (k16 & 7) * 2;
   *reinterpret_cast<__half*>(p) = hi;
   *reinterpret_cast<__half*>(p + tile_b) = lo;
 }
@@ -854,10 +1050,11 @@ struct T128State {
   int nbias = 0, nscale = 0, nslot = 0, maxks = 13;
   uint32_t slot_bytes = 0;
   size_t smem_bytes = 0;
+  long long* d_dbg = nullptr;  // tools/t128_bench.cu with -DGMPC_T128_TIMED
 };
 
 using T128Kernel = void (*)(const TParams);
-inline T128Kernel t128_kernel_ptr(int maxks) { return maxks <= 13 ? plan_t128_kernel<13> : plan_t128_kernel<16>; }
+inline T128Kernel t128_kernel_ptr(int) { return plan_t128_kernel; }
 
 inline int t_rup(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -882,27 +1079,51 @@ inline int t128_create(T128State& S, const gmpc_config& c, const int* dyn_dims, 
   if (S.Ld < 2) { S.why = "dynamics MLP has no hidden layer"; return GMPC_OK; }
   if (hmax > 256) { S.why = "hidden width > 256 (accumulator + split operand exceed the 512 TMEM columns)"; return GMPC_OK; }
   if (c.n + c.m > 32 || c.cost_fout > 32) { S.why = "n+m or fout > 32"; return GMPC_OK; }
-  S.maxks = t_rup(hmax, 16) / 16 <= 13 ? 13 : 16;
-  S.slot_bytes = (uint32_t)t_rup(hmax, 16) * 64u;  // one k-step of the widest layer
-  // geometry: biases, scales, images
+  S.maxks = 13;
+  // geometry: N-parts, biases, scales, images.  A layer with more than 32 output columns is issued as two
+  // N-parts (k-steps of the next operand split ceil/floor), the narrow last layer of a pass as one.
+  auto parts = [&](TLayer& Y) {
+    const int nko = Y.npad / 16;
+    if (Y.npad <= 32) { Y.ncol[0] = Y.npad; Y.ncol[1] = 0; }
+    else { Y.ncol[0] = 16 * ((nko + 1) / 2); Y.ncol[1] = Y.npad - Y.ncol[0]; }
+  };
+  uint32_t slot = 0;
+  auto widest = [&](const int* dims, int Ln) {
+    for (int l = 0; l < Ln; ++l)
+      for (int side = 0; side < 2; ++side) {
+        TLayer Y;
+        Y.npad = t_rup(dims[l + (side ? 0 : 1)], 16);
+        parts(Y);
+        slot = std::max(slot, (uint32_t)Y.ncol[0] * 64u);
+      }
+  };
+  widest(S.dyn_dims, S.Ld);
+  widest(S.cost_dims, S.Lc);
+  S.slot_bytes = std::max(slot, 16384u);  // ring group: >= one k-step of the widest N-part, 16 KB when it is smaller
   int nbias = 0, nscale = 0;
+  auto one_layer = [&](TLayer& Y, int M_true, int red, size_t& off) {
+    Y.M_true = M_true; Y.npad = t_rup(M_true, 16); Y.nks = t_rup(red, 16) / 16;
+    parts(Y);
+    for (int pt = 0; pt < 2; ++pt) {
+      Y.kpg[pt] = Y.ncol[pt] ? std::max(1, (int)(S.slot_bytes / (Y.ncol[pt] * 64))) : 1;
+      Y.goff[pt] = (uint32_t)off;
+      off += (size_t)Y.nks * Y.ncol[pt] * 64;
+    }
+    Y.pad_ = 0;
+  };
   auto geom = [&](const int* dims, int Ln, TDir& F, TDir& Bw, size_t& off_f, size_t& off_b) {
     F.L = Bw.L = Ln; F.pad_ = Bw.pad_ = 0;
     for (int l = 0; l < Ln; ++l) {
       TLayer& Y = F.layer[l];
-      Y.M_true = dims[l + 1]; Y.npad = t_rup(dims[l + 1], 16); Y.nks = t_rup(dims[l], 16) / 16;
-      Y.kpg = std::max(1, (int)(S.slot_bytes / (Y.npad * 64)));
+      one_layer(Y, dims[l + 1], dims[l], off_f);
       Y.bias_off = nbias; nbias += Y.npad;
-      Y.scale_idx = nscale + l; Y.pad_ = 0;
-      Y.goff = (uint32_t)off_f; off_f += (size_t)Y.nks * Y.npad * 64;
+      Y.scale_idx = nscale + l;
     }
     for (int i = 0; i < Ln; ++i) {
       const int lt = Ln - 1 - i;  // the adjoint pass visits the transposed layers L-1 .. 0
       TLayer& Y = Bw.layer[i];
-      Y.M_true = dims[lt]; Y.npad = t_rup(dims[lt], 16); Y.nks = t_rup(dims[lt + 1], 16) / 16;
-      Y.kpg = std::max(1, (int)(S.slot_bytes / (Y.npad * 64)));
-      Y.bias_off = 0; Y.scale_idx = nscale + lt; Y.pad_ = 0;
-      Y.goff = (uint32_t)off_b; off_b += (size_t)Y.nks * Y.npad * 64;
+      one_layer(Y, dims[lt], dims[lt + 1], off_b);
+      Y.bias_off = 0; Y.scale_idx = nscale + lt;
     }
     nscale += Ln;
   };
@@ -957,10 +1178,10 @@ inline int t128_set_weights(T128State& S, const float* const* dyn_W, const float
       const TLayer& f = F.layer[l];
       const TLayer& rv = Bw.layer[Ln - 1 - l];
       h16_absmax_kernel<<<std::min(blocks, 64), 256, 0, st>>>(W[l], K * N, S.d_absmax + sbase + l);
-      t128_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 0, const_cast<uint8_t*>(F.gsrc) + f.goff, f.npad,
-                                               S.d_absmax + sbase + l, S.d_scale + sbase + l);
-      t128_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 1, const_cast<uint8_t*>(Bw.gsrc) + rv.goff, rv.npad,
-                                               S.d_absmax + sbase + l, nullptr);
+      t128_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 0, const_cast<uint8_t*>(F.gsrc) + f.goff[0], f.ncol[0], f.ncol[1],
+                                               f.nks, S.d_absmax + sbase + l, S.d_scale + sbase + l);
+      t128_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 1, const_cast<uint8_t*>(Bw.gsrc) + rv.goff[0], rv.ncol[0],
+                                               rv.ncol[1], rv.nks, S.d_absmax + sbase + l, nullptr);
       *launches += 3;
       cudaMemcpyAsync(S.d_bias + f.bias_off, b[l], sizeof(float) * N, cudaMemcpyDeviceToDevice, st);
     }
@@ -988,6 +1209,7 @@ inline int t128_launch(T128State& S, const PlanParams& P, cudaStream_t st, int64
   Q.ws_X = S.ws_X; Q.ws_G = S.ws_G; Q.ws_U = S.ws_U; Q.ws_M = S.ws_M; Q.ws_V = S.ws_V;
   Q.ws_mask = S.ws_mask;
   Q.ovf = S.d_ovf;
+  Q.dbg = S.d_dbg;
   if (Q.ntiles <= 0) return GMPC_OK;
   const int grid = std::min(Q.ntiles, S.num_sms);
   t128_kernel_ptr(S.maxks)<<<grid, T_THREADS, S.smem_bytes, st>>>(Q);
