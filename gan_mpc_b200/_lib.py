@@ -144,6 +144,7 @@ class Handle:
         self._h = C.c_void_p()
         _check(self.lib.gmpc_create(C.byref(self.cfg), C.byref(self._h)))
         self.n, self.m, self.T = n, m, T
+        self._path = PATH_AUTO
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -158,7 +159,9 @@ class Handle:
 
     # ---------------------------------------------------------------- configuration
     def set_path(self, path):
-        _check(self.lib.gmpc_set_path(self._h, PATHS[path] if isinstance(path, str) else path))
+        code = PATHS[path] if isinstance(path, str) else int(path)
+        _check(self.lib.gmpc_set_path(self._h, code))
+        self._path = code
 
     @property
     def last_path(self):
@@ -228,18 +231,37 @@ class Handle:
         return loss, dU, X
 
     def plan(self, x0, U0, goal, method="adam", iters=20, lr=1e-2, b1=0.9, b2=0.999, eps=1e-8,
-             want_J_all=True, out=None):
-        """x0 [B,n], U0 [B,K,T,m], goal [B,T+1,n] -> (U_best, X_best, J_best, idx, J_all)."""
+             want_J_all=True, out=None, check_range=True):
+        """x0 [B,n], U0 [B,K,T,m], goal [B,T+1,n] -> (U_best, X_best, J_best, idx, J_all).
+
+        gmpc_plan itself never synchronises.  With check_range (default) the fp16 operand-range counter of
+        the tensor-core kernels is read after the call (one 4-byte D2H copy, synchronises the stream): if
+        an operand was clamped the plan is outside the parity contract and is re-done on the fp32 CUDA-core
+        kernel when the path is AUTO, or GmpcError is raised when a tensor-core path was forced.  A caller
+        that keeps the stream asynchronous passes check_range=False and calls range_overflow() itself."""
         dev = self.device
         B, K = U0.shape[0], U0.shape[1]
         if out is None:
             out = self.alloc_plan_outputs(B, K, want_J_all)
         U_best, X_best, J_best, idx, J_all = out
-        _check(self.lib.gmpc_plan(
-            self._h, B, K, _ptr(x0, device=dev, name="x0"), _ptr(U0, device=dev, name="U0"),
-            _ptr(goal, device=dev, name="goal"), METHODS[method], iters, lr, b1, b2, eps,
-            _ptr(U_best), _ptr(X_best), _ptr(J_best), _ptr(idx, dtype=torch.int32), _ptr(J_all),
-            _stream(dev)))
+
+        def launch():
+            _check(self.lib.gmpc_plan(
+                self._h, B, K, _ptr(x0, device=dev, name="x0"), _ptr(U0, device=dev, name="U0"),
+                _ptr(goal, device=dev, name="goal"), METHODS[method], iters, lr, b1, b2, eps,
+                _ptr(U_best), _ptr(X_best), _ptr(J_best), _ptr(idx, dtype=torch.int32), _ptr(J_all),
+                _stream(dev)))
+
+        launch()
+        if check_range and B > 0 and self.last_path != "ffma" and self.range_overflow() > 0:
+            if self._path != PATH_AUTO:
+                raise GmpcError(f"plan: an operand left the fp16 hi/lo range on the forced path "
+                                f"{self.last_path!r}; use path 'auto' or 'ffma'")
+            self.set_path(PATH_FFMA)
+            try:
+                launch()
+            finally:
+                self.set_path(PATH_AUTO)
         return out
 
     def alloc_plan_outputs(self, B, K, want_J_all=True, device=None, pin=False):

@@ -337,12 +337,16 @@ extern "C" int gmpc_set_weights(gmpc_handle* h, const float* const* dyn_W,
 // real dense contraction (batch tile >= 64, hidden >= 64: the north star's rule), else the fp32
 // CUDA-core kernel.  Both tensor-core defaults rescale the forward operands per trajectory: states
 // of any magnitude stay inside the fp16 hi/lo range (the un-scaled GMPC_PATH_TC16 is opt-in only).
+// Measured on B200 (C2 dims): the 32-trajectory kernel finishes a wave of 32 x SMs trajectories in 11.9 ms
+// whatever the batch, the 128-trajectory kernel a wave of 128 x SMs in 26.5 ms: the latency tile serves
+// batches of up to two of its waves, the throughput tile everything larger (1.55 x the trajectories per second).
 static int pick_path(gmpc_handle* h, int64_t NQ) {
   if (h->path != GMPC_PATH_AUTO) return h->path;
   if (h->h16.supported && h16_worthwhile(h->h16, NQ)) {
-    if (h->t128.supported) return GMPC_PATH_T128;
+    if (h->t128.supported && NQ > (int64_t)2 * H_NB * h->num_sms) return GMPC_PATH_T128;
     return GMPC_PATH_TC16S;
   }
+  if (h->t128.supported && NQ > (int64_t)2 * H_NB * h->num_sms) return GMPC_PATH_T128;
   return GMPC_PATH_FFMA;
 }
 

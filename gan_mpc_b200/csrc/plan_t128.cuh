@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
       const uint32_t d_t = tmem_base + T_D_COL, ah_t = tmem_base + T_AH_COL, al_t = tmem_base + T_AL_COL;
       const uint32_t slot16 = P.slot_bytes >> 4, ring16 = ring_a >> 4;
       uint32_t slot = 0, ph = 0, act_par = 0, dr_par = 0;
-      int lno = -1;
+      int lno = -1, prev_n0 = 0x7fffffff;   // prev_n0: accumulator columns the previous layer's part 0 covers
       auto skip_slots = [&](int ng) {
         slot += (uint32_t)ng;
         while (slot >= (uint32_t)NS) { slot -= (uint32_t)NS; ph ^= 1; }
@@ -304,11 +304,16 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
             // write-after-read hazard on the accumulator columns this keeps every mbarrier at most ONE phase
             // ahead of its slowest waiter: a warp arrives here only after it has passed both acc_bar waits of the
             // previous layer, and nothing of this layer is committed before all sixteen have.
+            // Issuer 0 needs part 1 of the previous layer drained only when it writes those columns (its part 0
+            // reaches past the previous part 0) or commits acc_bar[1] itself (single-part layer); otherwise it
+            // observes that phase after issuing, so part 0 starts while part 1 is still being read out.
+            const bool dr1_first = which == 1 || single || n0 > prev_n0;
+            prev_n0 = single ? 0x7fffffff : n0;
             T_WAIT(dr_a, dr_par, 1 + 10 * which, lno);
-            T_WAIT(dr_a + 8, dr_par, 2 + 10 * which, lno);
-            dr_par ^= 1;
+            if (dr1_first) T_WAIT(dr_a + 8, dr_par, 2 + 10 * which, lno);
             T128_TRACE(lno, which * 40 + 1);
             if (which == 1 && single) {
+              dr_par ^= 1;
               // nothing to issue, but every phase of every barrier must be OBSERVED: a waiter that only flipped its
               // parity bits could run two phases ahead and then pass a parity wait on a stale phase
               for (int j = 0; j < nks; ++j) T_WAIT(act_a + 8 * j, (act_par >> j) & 1u, 15, lno * 16 + j);
@@ -349,6 +354,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
               if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
             }
             act_par ^= lay_mask;
+            if (!dr1_first) T_WAIT(dr_a + 8, dr_par, 5, lno);
+            dr_par ^= 1;
             umma_commit_a(acc_a);
             if (which == 0) {
               if (single) umma_commit_a(acc_a + 8);          // both accumulator phases complete together

@@ -6,14 +6,16 @@ from gan_mpc_b200 import _lib
 from gan_mpc_b200.dynamics.nn import dense_stack_lists
 from gan_mpc_b200.policy import optimizers as opt
 
-# policy/eval.py:10-20 -- honoured by planner method "ilqr" (gmpc_ilqr); the first-order planner
-# (methods "adam" / "grad", the north-star default) ignores them
+# policy/eval.py:10-20 -- honoured by planner method "ilqr" (gmpc_ilqr), the default: the policy then plans
+# exactly like the reference (trajax iLQR), which is also what BaseMPC's bilevel gradient assumes (a
+# stationary U*).  The first-order planner of the north star (methods "adam" / "grad") is an explicit opt-in
+# (planner_kwargs / YAML mpc.planner.method); it ignores these options and says so once.
 TRAJAX_iLQR_KWARGS = {
     "maxiter": 100, "grad_norm_threshold": 1e-4, "relative_grad_norm_threshold": 0.0,
     "obj_step_threshold": 0.0, "inputs_step_threshold": 0.0, "make_psd": False, "psd_delta": 0.0,
     "alpha_0": 1.0, "alpha_min": 0.00005,
 }
-PLANNER_KWARGS = {"method": "adam", "iters": 20, "learning_rate": 1e-2, "num_candidates": 1,
+PLANNER_KWARGS = {"method": "ilqr", "iters": 20, "learning_rate": 1e-2, "num_candidates": 1,
                   "b1": 0.9, "b2": 0.999, "eps": 1e-8, "path": "auto", "return_gradient": True}
 COST_ARGS_NAME = ("goal_state",)
 
@@ -68,16 +70,22 @@ class EvalMPC:
         return self._handles[key]
 
     def _stage(self, h, params):
-        """(re)stage the weights when any of the tensors was replaced or modified in place."""
+        """(re)stage the weights when any of the tensors was replaced or modified in place.
+
+        The staged tensors are kept alive and compared by identity (`is`) plus their in-place version
+        counter: a freshly built pytree (another checkpoint, a Polyak average, a tree_map result) can never
+        be mistaken for the staged one, even when the caching allocator hands it the same addresses."""
         dW, db = dense_stack_lists(params["dynamics_params"])
         cW, cb = dense_stack_lists(params["cost_params"])
         ts = dW + db + cW + cb + [params["mpc_weights"]]
-        sig = tuple((t.data_ptr(), t._version) for t in ts)
-        if self._staged.get(id(h)) != sig:
+        prev = self._staged.get(id(h))
+        same = (prev is not None and len(prev) == len(ts)
+                and all(a is t and v == t._version for (a, v), t in zip(prev, ts)))
+        if not same:
             h.set_weights([t.contiguous() for t in dW], [t.contiguous() for t in db],
                           [t.contiguous() for t in cW], [t.contiguous() for t in cb],
                           params["mpc_weights"].contiguous())
-            self._staged[id(h)] = sig
+            self._staged[id(h)] = [(t, t._version) for t in ts]
 
     def _prep(self, x0, U, goal):
         """normalise (unbatched | batched) inputs to x0 [B,n], U [B,K,T,m], goal [B,T+1,n]."""
@@ -109,9 +117,17 @@ class EvalMPC:
                 out = tuple(None if o is None else (tuple(a[0] for a in o) if isinstance(o, tuple) else o[0])
                             for o in out)
             return out
+        if not getattr(self, "_warned_first_order", False):
+            import warnings
+            warnings.warn(f"planner method {pk['method']!r}: the first-order planner of the north star, not the "
+                          "reference's trajax iLQR (trajax_ilqr_kwargs are ignored; loss_and_grad still "
+                          "differentiates through iLQR plans)", stacklevel=3)
+            self._warned_first_order = True
+        # Handle.plan reads the fp16 operand-range counter after the call and re-plans on the fp32 kernel (path
+        # 'auto') or raises (forced tensor-core path): a clamped plan never leaves this function
         Ubest, X, J, idx, J_all = h.plan(x0b, Ub, gb, method=pk["method"], iters=pk["iters"],
                                          lr=pk["learning_rate"], b1=pk["b1"], b2=pk["b2"],
-                                         eps=pk["eps"])
+                                         eps=pk["eps"], check_range=True)
         grad = lam = None
         if pk["return_gradient"]:
             _, grad, _, lam = h.objective_grad(x0b, Ubest, gb, want_X=False, want_lam=True)

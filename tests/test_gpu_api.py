@@ -41,12 +41,18 @@ def test_l2_policy_plan_and_act(built_lib):
     config = cfg("l2_hyperparameters.yaml")
     x_size, u_size = 3, 1
     train_policy, eval_policy, _ = norm_runner.get_policy(config, x_size, u_size)
+    # the YAML default is the reference's planner (trajax iLQR, test_policy_with_trajax_ilqr_method and
+    # test_default_planner_is_the_reference_ilqr); this test exercises the north star's first-order planner
+    assert eval_policy.planner_kwargs["method"] == "ilqr"
+    for pol in (train_policy, eval_policy):
+        pol.planner_kwargs["method"] = "adam"
     params = norm_runner.get_params(train_policy, config, x_size, u_size)
     assert set(params) == {"mpc_weights", "cost_params", "dynamics_params", "expert_params"}
     assert params["dynamics_params"]["params"]["Dense_0"]["kernel"].shape == (4, 200)
     history_x = torch.randn(2, x_size, generator=torch.Generator().manual_seed(0)).cuda()
     history_u = torch.zeros(1, u_size).cuda()
-    X, U, obj, gradient, adjoints, lqr, iteration = eval_policy.get_optimal_values(params, history_x, history_u)
+    with pytest.warns(UserWarning, match="first-order planner"):
+        X, U, obj, gradient, adjoints, lqr, iteration = eval_policy.get_optimal_values(params, history_x, history_u)
     T = config.mpc.horizon
     assert X.shape == (T + 1, x_size) and U.shape == (T, u_size) and obj.shape == ()
     assert gradient.shape == (T, u_size) and adjoints.shape == (T + 1, x_size) and lqr is None
@@ -66,10 +72,75 @@ def test_l2_policy_plan_and_act(built_lib):
     assert torch.equal(U2, U) and torch.equal(X2, X)
 
 
+def test_default_planner_is_the_reference_ilqr(built_lib):
+    """Defaults: the policy plans with trajax iLQR like the reference (and like BaseMPC's bilevel gradient
+    assumes); two different same-shape parameter pytrees staged back to back are never confused."""
+    config = cfg("l2_hyperparameters.yaml")
+    policy, eval_policy, _ = norm_runner.get_policy(config, 3, 1)
+    assert policy.planner_kwargs["method"] == "ilqr" and eval_policy.planner_kwargs["method"] == "ilqr"
+    params = norm_runner.get_params(policy, config, 3, 1)
+    hx = torch.randn(4, 2, 3, generator=torch.Generator().manual_seed(5)).cuda()
+    X, U, obj, grad, lam, lqr, it = policy.get_optimal_values(params, hx)
+    assert policy.last_plan_info["path"] == "ilqr" and it.dtype == torch.int32 and int(it.max()) <= 100
+    # a functionally created replacement pytree (every leaf a NEW tensor, version 0, quite possibly at the
+    # addresses of the old leaves once those are freed) must be re-staged
+    import copy
+
+    def scaled(tree, f):
+        return {k: scaled(v, f) for k, v in tree.items()} if isinstance(tree, dict) else tree * f
+    params2 = dict(params)
+    params2["cost_params"] = scaled(params["cost_params"], 1.5)
+    obj2 = policy.get_optimal_values(params2, hx)[2].clone()
+    del params
+    params3 = dict(params2)
+    params3["cost_params"] = scaled(params2["cost_params"], 1.0 / 1.5)
+    obj3 = policy.get_optimal_values(params3, hx)[2]
+    assert not torch.allclose(obj2, obj) and torch.allclose(obj3, obj, rtol=1e-4)
+
+
+def test_model_entry_points_are_callable(built_lib):
+    """DynamicsModel.predict (dynamics/dynamics_model.py:45-48), MujocoBasedModel.get_cost
+    (cost/cost_model.py:33-42: staging cost, terminal cost at t == horizon) and CriticModel.predict
+    (critic/critic_model.py:15-16) evaluate one step / one trajectory through the kernels, vs the oracle."""
+    from oracle import critic as ocritic
+    config = cfg("gan_hyperparameters.yaml")
+    n, m, B = 3, 1, 9
+    policy, _, _ = gan_runner.get_policy(config, n, m)
+    params = gan_runner.get_params(policy, config, n, m)
+    T = config.mpc.horizon
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(B, n, generator=gen).cuda()
+    u = torch.tanh(torch.randn(B, m, generator=gen)).cuda()
+    goal = torch.randn(B, T + 1, n, generator=gen).cuda()
+    op = oracle_params(params)
+    d = lambda t_: t_.cpu().double()
+    # one dynamics step, batched and unbatched
+    xn = policy.dynamics_model.predict(x, u, 0, params["dynamics_params"])
+    oxn = oracle.dynamics_mlp(d(x), d(u), op["dyn_W"], op["dyn_b"])
+    assert util.rel_rows(xn, oxn) < TOL
+    assert torch.equal(policy.dynamics(x[2], u[2], 0, params), xn[2])
+    # one step cost: staging (t < horizon) and terminal (t == horizon), through policy.cost as the reference calls it
+    for t in (0, 2, T):
+        c = policy.cost(x, u, t, params, goal)
+        oc = torch.stack([oracle.step_cost(d(x[b]), d(u[b]), t, T, op, d(goal[b])) for b in range(B)])
+        assert util.rel_rows(c[:, None], oc[:, None]) < TOL, t
+    assert abs(float(policy.cost(x[1], u[1], T, params, goal[1])) - float(oc[1])) < TOL * abs(float(oc[1]))
+    # critic score
+    cm = policy.critic_model
+    xs = torch.randn(B, T + 1, n, generator=gen).cuda()
+    s = cm.predict(xs, params["critic_params"])
+    c_ = cm.model
+    os_ = ocritic.critic_logit(d(xs), d(c_.flatten(params["critic_params"])), n, c_.lstm_features, c_.num_layers,
+                               c_.num_hidden_units)
+    assert s.shape == (B, 1) and util.rel_rows(s, os_.reshape(B, 1)) < TOL
+    assert cm.predict(xs[3], params["critic_params"]).shape == (1,)
+
+
 def test_batched_policy_and_optimizer_functions(built_lib):
     config = cfg("l2_hyperparameters.yaml")
     x_size, u_size, B = 3, 1, 70
     policy, _, _ = norm_runner.get_policy(config, x_size, u_size)
+    policy.planner_kwargs["method"] = "adam"      # first-order planner (the default is "ilqr")
     params = norm_runner.get_params(policy, config, x_size, u_size)
     hx = torch.randn(B, 2, x_size, generator=torch.Generator().manual_seed(1)).cuda()
     X, U, obj, grad, lam, _, it = policy.get_optimal_values(params, hx)

@@ -268,10 +268,12 @@ def test_tc16_range_check_and_auto_fallback(built_lib):
     oU, oX, oJ, oidx, _ = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), op, "grad", 2, 1e-3)
     # device call on the forced tc16 path: the counter fires
     h.set_path("tc16")
-    h.plan(dev(x0), dev(U0), dev(goal), method="grad", iters=2, lr=1e-3)
+    h.plan(dev(x0), dev(U0), dev(goal), method="grad", iters=2, lr=1e-3, check_range=False)
     assert h.range_overflow() > 0
     assert h.range_overflow() == 0          # reading resets it
-    with pytest.raises(_lib.GmpcError):     # forced path: the host call refuses rather than return clamped plans
+    with pytest.raises(_lib.GmpcError):     # forced path, checked device call: refuses rather than return clamped plans
+        h.plan(dev(x0), dev(U0), dev(goal), method="grad", iters=2, lr=1e-3)
+    with pytest.raises(_lib.GmpcError):     # forced path: the host call refuses as well
         h.plan_host(torch.from_numpy(x0), torch.from_numpy(U0), torch.from_numpy(goal),
                     method="grad", iters=2, lr=1e-3)
     # AUTO: transparently re-planned (rescaled variant first, fp32 kernel if that clamps too)
@@ -281,10 +283,14 @@ def test_tc16_range_check_and_auto_fallback(built_lib):
     assert h.last_path == "ffma"
     ok = torch.ones(96, dtype=torch.bool)
     assert util.rel_rows(Xb[ok], oX[ok]) < TOL and util.rel_rows(Ub[ok], oU[ok]) < TOL
+    # AUTO through the device-pointer call (what EvalMPC uses): re-planned on the fp32 kernel as well
+    Ud, Xd, Jd, _, _ = h.plan(dev(x0), dev(U0), dev(goal), method="grad", iters=2, lr=1e-3)
+    assert h.last_path == "ffma"
+    assert util.rel_rows(Xd.cpu(), oX) < TOL and util.rel_rows(Ud.cpu(), oU) < TOL
     # in-range inputs never trip it
     p2, x2, U2, g2 = util.case(cfg, 6, B=96, K=1)
-    h.plan(dev(x2), dev(U2), dev(g2), method="adam", iters=2, lr=1e-2)
-    assert h.last_path == "tc16" and h.range_overflow() == 0
+    h.plan(dev(x2), dev(U2), dev(g2), method="adam", iters=2, lr=1e-2, check_range=False)
+    assert h.last_path == "tc16s" and h.range_overflow() == 0
 
 
 @pytest.mark.parametrize("slots", [4, 5, 7, 8])

@@ -20,7 +20,7 @@ REF = "/root/reference/config"
 def test_yaml_matches_reference_values(name):
     """Our hyper-parameter files carry the reference's keys and values (+ the mpc.planner block)."""
     ours = yaml.safe_load(open(os.path.join(load_config.CONFIG_DIR, name)))
-    assert ours["mpc"]["planner"]["method"] in ("adam", "grad")
+    assert ours["mpc"]["planner"]["method"] == "ilqr"   # the reference's planner is the default
     if not os.path.exists(os.path.join(REF, name)):
         pytest.skip("reference tree not mounted")
     ref = yaml.safe_load(open(os.path.join(REF, name)))
