@@ -5,20 +5,30 @@
 // with the TRAJECTORIES as the M dimension of the MMA (TMEM lane = trajectory), the activations as
 // the A operand IN TENSOR MEMORY and the weights streamed from L2 through a shared-memory ring as
 // the B operand.  Measured on B200 (tools/t128_probe.cu, profiles/r2_t128_probe.txt): with A in TMEM
-// an M=128 x N=208 x K=16 kind::f16 MMA costs N/2 = 104 cycles, the full tensor rate, and the three
-// products of the fp16 hi/lo split (ah Wh + al Wh + ah Wl, one fp32 accumulator) of one k-step run
-// in 312 cycles with all 148 SMs streaming their weights from L2 at the same time (10 ring slots);
-// cta_group::2 brings nothing on top (336 cycles at N = 224).  plan_h16.cuh (weights as the A
-// operand from shared memory, 32 trajectories as N) pays 88 cycles per block-k-step for a quarter of
-// the trajectories: this kernel does 4 x the trajectories per SM in 1.5 x the tensor time.
+// an M=128 x N x K=16 kind::f16 MMA costs max(16, N/2) cycles, the full tensor rate, and the three
+// products of the fp16 hi/lo split (ah Wh + al Wh + ah Wl, one fp32 accumulator) of one 208-column
+// k-step run in 312 cycles with all 148 SMs streaming their weights from L2 at the same time.
 //
-// Nothing but the weights ever touches shared memory: an epilogue thread owns ONE trajectory (its
-// TMEM lane) and 4 of every 16 features: tcgen05.ld -> scale / bias / ReLU / mask bit -> fp16 hi/lo
-// split -> tcgen05.st straight into the A operand of the next layer.  Per-trajectory quantities
-// (forward and adjoint power-of-two scales, staging costs, Adam moments) are per-thread scalars.
-// The next layer's MMAs start as soon as the first 16 features of its operand are written
-// (one mbarrier per k-step), so the epilogue of layer l runs under the MMAs of layer l+1; the
-// accumulator is read out completely into registers first, which frees it for those MMAs.
+// Nothing but the weights ever touches shared memory.  Tensor memory holds two 240-column regions that
+// swap roles every layer, and a 32-column region for the narrow last layer of a pass:
+//     layer l :  A operand = region c,  accumulator = region c^1
+//     epilogue:  a thread reads 16 accumulator columns of ITS trajectory (tcgen05.ld), applies
+//                scale / bias / ReLU / mask bit, splits into fp16 hi/lo and writes the 8 + 8 packed
+//                columns back IN PLACE (tcgen05.st): the accumulator region turns, 16 columns at a
+//                time, into the A operand of layer l+1 (feature block j: hi in columns [16 j, 16 j + 8),
+//                lo in [16 j + 8, 16 j + 16)).  No thread ever touches a column another thread reads.
+//     layer l+1: A operand = region c^1, accumulator = region c (all of layer l's MMAs are complete).
+// Issue: a single thread sustains one MMA per ~80 cycles (descriptor moves to uniform registers), an N = 64
+// MMA takes 32 tensor cycles: the accumulator columns of a layer are therefore split into up to three N-PARTS
+// (four feature blocks each, the last part takes the remainder), one issuer warp per part, all walking the
+// k-steps concurrently.  Pipelining across layers is by K-STEP: feature block j of the next operand belongs to
+// epilogue sub-group j % 4 (4 warps, one per TMEM lane quarter) and has its own mbarrier; the issuers start
+// k-step j of layer l+1 as soon as block j is stored, so the MMAs of layer l+1 run under the epilogue of
+// layer l and only the first block's latency is exposed.
+// Synchronisation: one mbarrier per N-part ("all MMAs of this part of the layer are complete",
+// tcgen05.commit), one per feature block ("stored", 4 warp arrivals), the weight ring's full / empty pairs,
+// and one for the narrow accumulator's second reader.  Write-after-read on the regions needs nothing else:
+// block j's arrival follows its owners' reads, and a layer completes only after every block has arrived.
 //
 // Restates the same reference lines as plan_ffma.cuh / plan_h16.cuh (dynamics/nn.py:27-34,
 // cost/nn.py:23-29, cost/cost_model.py:20-42, policy/optimizers.py:24-31 and :78-83; optax adam of
@@ -41,29 +51,30 @@ namespace gmpc {
 constexpr int T_NB = 128;                          // trajectories per tile
 constexpr int T_EPI_WARPS = 16;                    // 4 per TMEM lane quarter
 constexpr int T_EPI = T_EPI_WARPS * 32;            // 512 epilogue threads
-constexpr int T_FRONT = 3;                         // producer warp + two MMA issuer warps (N-part 0 / N-part 1)
-constexpr int T_THREADS = T_EPI + 32 * T_FRONT;
-constexpr int T_MAXKS = 16;                        // k-steps of the widest operand (hidden <= 256)
-constexpr int T_PKS = 8;                           // k-steps one N-part of a layer defines (half of T_MAXKS)
+constexpr int T_ISSUERS = 1;                       // MMA issuer warps = N-parts per layer (measured: 1, 2 and 3 parts run
+                                                   // at the same speed, the k-step pace is set by the epilogue rounds)
+constexpr int T_THREADS = T_EPI + 32 * (1 + T_ISSUERS);   // epilogue warps 0..15, producer warp 16, issuer warps 17..
+constexpr int T_MAXP = T_ISSUERS;                  // N-parts per layer
+constexpr int T_MAXKS = 16;                        // k-steps of the widest operand
+constexpr int T_MAXH = 240;                        // widest operand / accumulator (hidden width, padded to 16)
 constexpr int T_MAX_SLOTS = 32;
-constexpr uint32_t T_D_COL = 0, T_AH_COL = 256, T_AL_COL = 384;  // TMEM columns: D | A hi | A lo
+constexpr uint32_t T_R0 = 0, T_R1 = 240, T_RC = 480;  // TMEM columns: region 0 | region 1 | narrow accumulator
 
-// A layer's MMAs go out as two N-parts (output columns [0, n0) for every k-step, then [n0, npad)): the
-// accumulator of part 0 is complete, read out and processed while the tensor pipe works on part 1.
 struct TLayer {
-  uint32_t goff[2];        // byte offset of the tiles of N-part p in the image of the pass
-  int ncol[2];             // output columns (MMA N) of N-part p; ncol[1] == 0: single part (<= 32 columns)
-  int kpg[2];              // k-steps per ring group (one bulk copy, one slot) of part p
+  uint32_t goff;           // byte offset of the layer's image in the image of the pass
+  int kpg;                 // k-steps per ring group (one bulk copy, one slot)
+  int ncol[T_MAXP];        // output columns (MMA N) of N-part p
+  int c0[T_MAXP];          // first output column of N-part p
+  int np;                  // N-parts
   int M_true;              // output features of this (possibly transposed) layer
-  int npad;                // round_up(M_true, 16) = ncol[0] + ncol[1]
+  int npad;                // round_up(M_true, 16) = sum of ncol
   int nks;                 // reduction k-steps (round_up(K, 16) / 16)
   int bias_off;            // offset of the layer's bias in the bias table (forward layers)
   int scale_idx;           // index into the inverse weight scale table
-  int pad_;
 };
 struct TDir {
   TLayer layer[MAXL];
-  const uint8_t* gsrc;     // image of the pass: per layer, per k-step: [hi tile | lo tile]
+  const uint8_t* gsrc;     // image of the pass: per layer, per k-step, per N-part: [hi tile | lo tile]
   int L;
   int pad_;
 };
@@ -86,15 +97,8 @@ struct TParams {
   long long* dbg;          // cycle counters of CTA 0 (builds with -DGMPC_T128_TIMED only)
 };
 
-// The pass schedule: iters x {T dyn fwd, [cost fwd, cost bwd], T dyn bwd}, then the final evaluation.
 #ifdef GMPC_T128_TIMED
-#define T128_TRACE(layer_no, slot) do { if (blockIdx.x == 0 && P.dbg != nullptr && (layer_no) >= 2000 && (layer_no) < 2003) \
-    P.dbg[256 + ((layer_no) - 2000) * 128 + (slot)] = clock64(); } while (0)
-#else
-#define T128_TRACE(layer_no, slot)
-#endif
-
-#ifdef GMPC_T128_TIMED
+// A wait that gives up after 20 M cycles and records (tag, warp, layer) instead of hanging: the development build.
 __device__ __forceinline__ void t_wait_dbg(uint32_t bar, uint32_t parity, int tag, int layer, long long* dbg) {
   if (mbar_try_wait_a(bar, parity)) return;
   const long long t0 = clock64();
@@ -104,6 +108,7 @@ __device__ __forceinline__ void t_wait_dbg(uint32_t bar, uint32_t parity, int ta
       if (dbg != nullptr) {
         const unsigned long long i = atomicAdd((unsigned long long*)(dbg + 700), 1ULL);
         if (i < 96) dbg[704 + i] = ((long long)tag << 40) | ((long long)(threadIdx.x >> 5) << 32) | (unsigned)layer;
+        if (i == 0) for (int w = 0; w < 24; ++w) dbg[840 + w] = ((volatile long long*)dbg)[800 + w];   // snapshot of the positions
         atomicAdd((unsigned long long*)(dbg + 701), 1ULL);
       }
       return;
@@ -111,10 +116,26 @@ __device__ __forceinline__ void t_wait_dbg(uint32_t bar, uint32_t parity, int ta
   }
 }
 #define T_WAIT(bar, par, tag, layer) t_wait_dbg(bar, par, tag, layer, P.dbg)
+// last position of every warp of CTA 0 (layer << 8 | code), for the post-mortem of a lost run
+#define T128_POS(layer, code) do { if (blockIdx.x == 0 && P.dbg != nullptr && (threadIdx.x & 31) == 0) \
+    ((volatile long long*)P.dbg)[800 + (threadIdx.x >> 5)] = ((long long)(layer) << 8) | (code); } while (0)
+#define T128_E0(v) v = clock64()
+#define T128_E1(acc, v) acc += clock64() - v
+// event trace of four consecutive layers of CTA 0 (T128_TRACE_L0 ..): cycle stamps into dbg[256 ..)
+#ifndef T128_TRACE_L0
+#define T128_TRACE_L0 545
+#endif
+#define T128_TR(layer, slot) do { if (blockIdx.x == 0 && P.dbg != nullptr && (layer) >= T128_TRACE_L0 && (layer) < T128_TRACE_L0 + 4) \
+    P.dbg[(slot)] = clock64(); } while (0)
 #else
+#define T128_TR(layer, slot)
 #define T_WAIT(bar, par, tag, layer) mbar_wait_a(bar, par)
+#define T128_POS(layer, code)
+#define T128_E0(v)
+#define T128_E1(acc, v)
 #endif
 
+// The pass schedule: iters x {T dyn fwd, [cost fwd, cost bwd], T dyn bwd}, then the final evaluation.
 struct TPassWalk {
   int pp = 0, itc = 0;
   __device__ __forceinline__ int next(const TParams& P) {
@@ -151,7 +172,7 @@ __host__ __device__ inline TSmem t_smem_layout(int nslot, uint32_t slot_bytes, i
   s.ssc = s.us + (uint32_t)m * T_NB * 4;
   s.sig = s.ssc + T_NB * 4;
   s.bars = s.sig + 2 * T_NB * 4;
-  s.total = s.bars + 8 * (2 * T_MAX_SLOTS + 5 + 2 * T_MAXKS) + 16;
+  s.total = s.bars + 8 * (2 * T_MAX_SLOTS + T_MAXP + T_MAXKS + 1) + 16;
   return s;
 }
 
@@ -163,18 +184,18 @@ __device__ __forceinline__ void t_mma(uint32_t d, uint32_t a_tmem, uint64_t bdes
                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(bdesc),
                "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void t_ld4(uint32_t taddr, uint32_t (&r)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void t_st2(uint32_t taddr, uint32_t a, uint32_t b) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
-}
 __device__ __forceinline__ void t_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void t_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t t_region(uint32_t c) { return c ? T_R1 : T_R0; }
+// 0xFFFF in every 16-bit half of x whose top bit is set (prmt with sign replication; __byte_perm drops that bit)
+__device__ __forceinline__ uint32_t t_half_signs(uint32_t x) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xBB99u));
+  return d;
+}
 
 __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_constant__ TParams P) {
   extern __shared__ __align__(128) uint8_t tsm[];
@@ -188,11 +209,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
   float* sig_s = reinterpret_cast<float*>(tsm + L.sig);   // [2][128] adjoint operand scale, by step parity
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tsm + L.bars);
   uint64_t* empty_bar = full_bar + T_MAX_SLOTS;
-  uint64_t* acc_bar = empty_bar + T_MAX_SLOTS;   // [2] all MMAs of N-part p of a layer are complete
-  uint64_t* dr_bar = acc_bar + 2;                // [2] every epilogue warp has read part p of the accumulator out
-  uint64_t* act_bar = dr_bar + 2;                // [MAXKS] k-step j of the next operand is in TMEM (4 arrivals: its owner warps)
-  uint64_t* rel_bar = act_bar + T_MAXKS;         // [MAXKS] the layer's last MMAs that read k-step j of the current operand are complete
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(rel_bar + T_MAXKS);
+  uint64_t* acc_bar = empty_bar + T_MAX_SLOTS;   // all MMAs of the layer are complete (one commit per issuer)
+  uint64_t* rnd_bar = acc_bar + T_MAXP;          // [4] feature blocks [4 r, 4 r + 4) of the next operand are stored; ALL 16
+                                                 // epilogue warps arrive, with or without a block in the round
+  uint64_t* rc_bar = rnd_bar + T_MAXKS;          // sub 1 has read the u columns of the narrow accumulator (4 warp arrivals)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(rc_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = P.n, m = P.m, T = P.T, NS = P.nslot;
@@ -203,16 +224,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&acc_bar[0], 1);
-    mbar_init(&acc_bar[1], 1);
-    mbar_init(&dr_bar[0], T_EPI_WARPS);
-    mbar_init(&dr_bar[1], T_EPI_WARPS);
-    for (int j = 0; j < T_MAXKS; ++j) {
-      mbar_init(&act_bar[j], 4);
-      mbar_init(&rel_bar[j], 1);
-    }
+    mbar_init(acc_bar, T_MAXP);
+    for (int j = 0; j < 4; ++j) mbar_init(&rnd_bar[j], T_EPI_WARPS);
+    mbar_init(rc_bar, 4);
+    for (int s = 0; s < NS; ++s) mbar_init(&empty_bar[s], T_MAXP);
     mbar_fence_init();
   }
   __syncwarp();
@@ -223,10 +239,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0) {
+  if (warp == T_EPI_WARPS) {
     // ================================================================== weight-stream producer
-    // One ring slot = one group = kpg k-steps of one layer ([hi tile | lo tile] each), one bulk copy.
-    // tools/bulk_copy_rate.cu: a cp.async.bulk holds its issuing lane ~460 cycles, so four lanes take
+    // One ring slot = one group = kpg k-steps of one layer (all N-parts, [hi tile | lo tile] each), one bulk
+    // copy.  tools/bulk_copy_rate.cu: a cp.async.bulk holds its issuing lane ~460 cycles, so four lanes take
     // every fourth group; all lanes walk the same schedule.
     if (lane < 4) {
       const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), ring_a = smem_u32(tsm + L.ring);
@@ -239,52 +255,47 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
           const TDir& D = P.dir[kind];
           for (int l = 0; l < D.L; ++l) {
             const TLayer& Y = D.layer[l];
-            for (int pt = 0; pt < 2; ++pt) {
-              if (Y.ncol[pt] == 0) continue;
-              const uint32_t kb = (uint32_t)Y.ncol[pt] * 64u;
-              uint32_t off = Y.goff[pt];
-              for (int j = 0; j < Y.nks; j += Y.kpg[pt]) {
-                const uint32_t bytes = (uint32_t)min(Y.kpg[pt], Y.nks - j) * kb;
-                if ((gc & 3u) == (uint32_t)lane) {
-                  T_WAIT(empty_a + slot * 8, ph ^ 1, 30, (int)gc);
-                  const uint32_t bar = full_a + slot * 8;
-                  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-                  asm volatile(
-                      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                      ::"r"(ring_a + slot * P.slot_bytes), "l"(D.gsrc + off), "r"(bytes), "r"(bar) : "memory");
-                }
-                off += bytes;
-                ++gc;
-                if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
+            const uint32_t kb = (uint32_t)Y.npad * 64u;
+            uint32_t off = Y.goff;
+            for (int j = 0; j < Y.nks; j += Y.kpg) {
+              const uint32_t bytes = (uint32_t)min(Y.kpg, Y.nks - j) * kb;
+              if ((gc & 3u) == (uint32_t)lane) {
+                T_WAIT(empty_a + slot * 8, ph ^ 1, 30, (int)gc);
+                const uint32_t bar = full_a + slot * 8;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                    ::"r"(ring_a + slot * P.slot_bytes), "l"(D.gsrc + off), "r"(bytes), "r"(bar) : "memory");
               }
+              off += bytes;
+              ++gc;
+              if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
             }
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp > T_EPI_WARPS) {
     // ================================================================== MMA issuers (one thread each)
-    // A single thread issues dependent instructions ~5 cycles apart: with descriptor arithmetic, R2UR moves
-    // and mbarrier probes one tcgen05.mma costs it 40-130 cycles, a split MMA only 40-64 tensor cycles.
-    // Issuer 0 therefore issues N-part 0 of every layer (and the whole of a single-part layer), issuer 1
-    // N-part 1, concurrently: both wait for the operand k-step by k-step (act_bar), accumulator columns of the
-    // two parts are disjoint and every other ordering is carried by the mbarriers, so the two instruction
-    // streams may interleave freely on the tensor pipe.
-    const int which = warp - 1;
+    // Issuer p issues N-part p of every layer, k-step by k-step as the feature blocks of the operand arrive.
+    // Accumulator columns of different parts are disjoint, a part's completion is tracked by the commit of the
+    // thread that issued it, so the three instruction streams may interleave freely on the tensor pipe.  Every
+    // issuer observes every phase of every block barrier, also in layers in which it issues nothing (a waiter
+    // that only flipped its parity bit could run two phases ahead and pass a parity wait on a stale phase).
+    const int which = warp - T_EPI_WARPS - 1;
     if (elect_one()) {
       const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), ring_a = smem_u32(tsm + L.ring);
-      const uint32_t acc_a = smem_u32(acc_bar) + 8 * which, dr_a = smem_u32(dr_bar), act_a = smem_u32(act_bar);
-      const uint32_t rel_a = smem_u32(rel_bar);
+      const uint32_t acc_a = smem_u32(acc_bar), rnd_a = smem_u32(rnd_bar), rc_a = smem_u32(rc_bar);
       const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 0, 128) >> 32);
-      const uint32_t d_t = tmem_base + T_D_COL, ah_t = tmem_base + T_AH_COL, al_t = tmem_base + T_AL_COL;
       const uint32_t slot16 = P.slot_bytes >> 4, ring16 = ring_a >> 4;
-      uint32_t slot = 0, ph = 0, act_par = 0, dr_par = 0;
-      int lno = -1, prev_n0 = 0x7fffffff;   // prev_n0: accumulator columns the previous layer's part 0 covers
-      auto skip_slots = [&](int ng) {
-        slot += (uint32_t)ng;
-        while (slot >= (uint32_t)NS) { slot -= (uint32_t)NS; ph ^= 1; }
-      };
+      uint32_t slot = 0, ph = 0, rpar = 0, rc_par = 0, cur = 0;
+      int lno = -1;
+#ifdef GMPC_T128_TIMED
+      long long i_kst = 0, i_full = 0, i_first = 0, iq;
+      long long il_first[4] = {0, 0, 0, 0}, il_rest[4] = {0, 0, 0, 0}, il_t0 = 0;   // dyn fwd, by layer
+      const long long i_begin = clock64();
+#endif
       for (int ti = 0; ti < my_tiles; ++ti) {
         TPassWalk walk;
         for (;;) {
@@ -293,93 +304,103 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
           const TDir& D = P.dir[kind];
           for (int l = 0; l < D.L; ++l) {
             const TLayer& Y = D.layer[l];
-            const int nks = Y.nks, n0 = Y.ncol[0], n1 = Y.ncol[1];
-            const int ng0 = (nks + Y.kpg[0] - 1) / Y.kpg[0], ng1 = n1 ? (nks + Y.kpg[1] - 1) / Y.kpg[1] : 0;
-            const bool single = (n1 == 0);
-            const uint32_t lay_mask = (1u << nks) - 1u;
+            const int nks = Y.nks, kpg = Y.kpg;
+            const bool narrow = (l == D.L - 1);
             ++lno;
-            T128_TRACE(lno, which * 40 + 0);
-            if (which == 1) skip_slots(ng0);
-            // Every epilogue warp has read the previous layer's accumulator out (both parts).  Besides the
-            // write-after-read hazard on the accumulator columns this keeps every mbarrier at most ONE phase
-            // ahead of its slowest waiter: a warp arrives here only after it has passed both acc_bar waits of the
-            // previous layer, and nothing of this layer is committed before all sixteen have.
-            // Issuer 0 needs part 1 of the previous layer drained only when it writes those columns (its part 0
-            // reaches past the previous part 0) or commits acc_bar[1] itself (single-part layer); otherwise it
-            // observes that phase after issuing, so part 0 starts while part 1 is still being read out.
-            const bool dr1_first = which == 1 || single || n0 > prev_n0;
-            prev_n0 = single ? 0x7fffffff : n0;
-            T_WAIT(dr_a, dr_par, 1 + 10 * which, lno);
-            if (dr1_first) T_WAIT(dr_a + 8, dr_par, 2 + 10 * which, lno);
-            T128_TRACE(lno, which * 40 + 1);
-            if (which == 1 && single) {
-              dr_par ^= 1;
-              // nothing to issue, but every phase of every barrier must be OBSERVED: a waiter that only flipped its
-              // parity bits could run two phases ahead and then pass a parity wait on a stale phase
-              for (int j = 0; j < nks; ++j) T_WAIT(act_a + 8 * j, (act_par >> j) & 1u, 15, lno * 16 + j);
-              act_par ^= lay_mask;
-              continue;
+#ifdef GMPC_T128_TIMED
+            il_t0 = clock64();
+#endif
+            const uint32_t a_t = tmem_base + t_region(cur);
+            const uint32_t d_t = tmem_base + (narrow ? T_RC : t_region(cur ^ 1u));
+            cur ^= 1u;
+            const bool mine = which < Y.np;
+            // the u columns of the previous adjoint boundary's narrow accumulator have been read (sub 1)
+            if (which == 0 && narrow && kind == DIR_DYN_B) {
+              T_WAIT(rc_a, rc_par, 2, lno);
+              rc_par ^= 1;
             }
-            const int ncol = which ? n1 : n0, kpg = Y.kpg[which];
+            const int ncol = mine ? Y.ncol[which] : 16;
             const uint32_t idesc = t_idesc(ncol);
             const uint32_t tile16 = ((uint32_t)ncol * 32u) >> 4;          // one (hi or lo) tile, in 16-byte units
             const uint32_t lbo_f = (((uint32_t)ncol * 16u) >> 4) << 16;   // LBO field of the descriptor
-            const uint32_t d_p = d_t + (which ? (uint32_t)n0 : 0u);
-            const bool commit_rel = which == 1 || single;
-            uint32_t a_off = 0;           // 8 j: TMEM column offset of k-step j of the operand, byte offset of its barriers
-            uint32_t par = act_par;       // bit 0 = parity of the barrier of the k-step about to be issued
-            int left = nks;
-            while (left > 0) {
-              const int nk = left < kpg ? left : kpg;
-              left -= nk;
-              T_WAIT(full_a + slot * 8, ph, 3 + 10 * which, lno);
-              uint32_t b_lo = (ring16 + slot * slot16) | lbo_f;
+            const uint32_t kst16 = ((uint32_t)Y.npad * 64u) >> 4;         // one k-step of the layer (all parts)
+            const uint32_t part16 = mine ? ((uint32_t)Y.c0[which] * 64u) >> 4 : 0u;
+            const uint32_t d_p = d_t + (mine ? (uint32_t)Y.c0[which] : 0u);
+            const int extra = which == 0 ? T_MAXP - Y.np : 0;   // issuer 0 releases the slot for the absent parts too
+            uint32_t a_off = 0;           // 16 j: TMEM column offset of k-step j of the operand
+            uint32_t b_lo = 0;
+            int in_group = 0;             // k-steps left in the ring group in flight
 #pragma unroll 1
-              for (int jj = 0; jj < nk; ++jj) {
-                T_WAIT(act_a + a_off, par & 1u, 4 + 10 * which, lno * 16 + (int)(a_off >> 3));
-                par >>= 1;
+            for (int j = 0; j < nks; ++j) {
+              if ((j & 3) == 0) {         // feature blocks [j, j + 4) of the operand are stored
+                T128_E0(iq);
+                T128_POS(lno, 64 + j);
+                T_WAIT(rnd_a + 2 * j, (rpar >> (j >> 2)) & 1u, 4 + 10 * which, lno * 16 + j);
+                T128_TR(lno, 256 + (lno - T128_TRACE_L0) * 64 + which * 16 + j);
+#ifdef GMPC_T128_TIMED
+                if (j == 0) {
+                  i_first += clock64() - iq;
+                  if (kind == DIR_DYN_F && l < 4) { il_first[l] += clock64() - il_t0; il_t0 = clock64(); }
+                } else i_kst += clock64() - iq;
+#endif
                 tc_fence_after();
+              }
+              if (in_group == 0) {
+                in_group = nks - j < kpg ? nks - j : kpg;
+                T128_E0(iq);
+                if (mine) T_WAIT(full_a + slot * 8, ph, 3 + 10 * which, lno);
+                T128_E1(i_full, iq);
+                b_lo = (ring16 + slot * slot16 + part16) | lbo_f;
+              }
+              if (mine) {
                 const uint64_t bh = ((uint64_t)desc_hi << 32) | b_lo;
                 const uint64_t bl = ((uint64_t)desc_hi << 32) | (b_lo + tile16);
-                t_mma(d_p, ah_t + a_off, bh, idesc, a_off);          // accumulate = (j > 0)
-                t_mma(d_p, al_t + a_off, bh, idesc, 1u);
-                t_mma(d_p, ah_t + a_off, bl, idesc, 1u);
-                // the layer's last read of k-step j of the operand: the epilogue may overwrite it from here on
-                if (commit_rel) umma_commit_a(rel_a + a_off);
-                T128_TRACE(lno, which * 40 + 2 + (int)(a_off >> 3));
-                a_off += 8;
-                b_lo += 2 * tile16;
+                t_mma(d_p, a_t + a_off, bh, idesc, a_off);          // accumulate = (j > 0)
+                t_mma(d_p, a_t + a_off + 8u, bh, idesc, 1u);
+                t_mma(d_p, a_t + a_off, bl, idesc, 1u);
               }
-              umma_commit_a(empty_a + slot * 8);
-              if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
+              a_off += 16;
+              b_lo += kst16;
+              if (--in_group == 0) {
+                if (mine) {
+                  umma_commit_a(empty_a + slot * 8);
+                  for (int x = 0; x < extra; ++x) umma_commit_a(empty_a + slot * 8);
+                }
+                if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1; }
+              }
             }
-            act_par ^= lay_mask;
-            if (!dr1_first) T_WAIT(dr_a + 8, dr_par, 5, lno);
-            dr_par ^= 1;
+            rpar ^= (1u << ((nks + 3) >> 2)) - 1u;
+            // Every issuer commits, also with nothing issued: the epilogue passes a layer only after EVERY issuer has
+            // walked it, and every epilogue warp arrives on the round barriers of every layer, so no barrier can get
+            // two phases ahead of any of its waiters.
             umma_commit_a(acc_a);
-            if (which == 0) {
-              if (single) umma_commit_a(acc_a + 8);          // both accumulator phases complete together
-              skip_slots(ng1);
-            }
+#ifdef GMPC_T128_TIMED
+            if (kind == DIR_DYN_F && l < 4) il_rest[l] += clock64() - il_t0;
+#endif
           }
         }
       }
+#ifdef GMPC_T128_TIMED
+      if (blockIdx.x == 0 && P.dbg != nullptr) {
+        long long* o = P.dbg + 40 + which * 8;
+        o[0] = clock64() - i_begin; o[1] = i_first; o[2] = i_kst; o[3] = i_full;
+        if (which == 0) for (int i = 0; i < 4; ++i) { P.dbg[100 + i] = il_first[i]; P.dbg[104 + i] = il_rest[i]; }
+      }
+#endif
     }
     __syncwarp();
   } else {
     // ================================================================== epilogue / per-trajectory work
-    const int ew = warp - T_FRONT;         // 0..15
+    const int ew = warp;                   // 0..15
     const int q = warp & 3;                // TMEM lane quarter this warp may access
-    const int sub = ew >> 2;               // which 4 of every 16 features; sub 0 also owns the trajectory's state,
+    const int sub = ew >> 2;               // feature blocks j % 4 == sub; sub 0 also owns the trajectory's state,
                                            // sub 1 its action update
     const int r = q * 32 + lane;           // trajectory (TMEM lane) in the tile
     const int et = ew * 32 + lane;         // 0..511
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t acc_a = smem_u32(acc_bar), dr_a = smem_u32(dr_bar), act_a = smem_u32(act_bar), rel_a = smem_u32(rel_bar);
-    uint32_t acc_ph = 0, rel_par = 0;
-    int cur_kind = 0, elno = -1, elno2 = 0;
-    const bool tr_on = (q == 0 && lane == 0);
-    const int tr_base = 80 + sub * 12;
+    const uint32_t acc_a = smem_u32(acc_bar), rnd_a = smem_u32(rnd_bar), rc_a = smem_u32(rc_bar);
+    uint32_t acc_par = 0, cur = 0;         // cur: region of the operand of the layer in flight
+    int elno = 0;
     const bool cost_mode = (P.mode == MODE_PLAN || P.mode == MODE_OBJGRAD);
     float w0 = 0.f, w1 = 0.f, w2 = 0.f;
     if (cost_mode) {
@@ -399,7 +420,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
     float* xs = xs_s + r;     // this trajectory's column of the shared per-trajectory arrays
     float* lam = lam_s + r;
     float* us = us_s + r;
-    constexpr int MSTR = 2 * T_EPI;  // mask words per (step, layer)
+    constexpr int MSTR = 2 * T_EPI;  // mask words per (step, layer): 4 feature blocks x 16 bits per thread
     uint32_t* wsMask = P.ws_mask + (size_t)blockIdx.x * ((size_t)T * (Ld - 1) + (Lc - 1)) * MSTR + et;
     uint32_t* costMask = wsMask + (size_t)T * (Ld - 1) * MSTR;
     const bool adam = (P.mode == MODE_PLAN && P.method == 1);
@@ -408,73 +429,52 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
     const int nk_costf = P.use_cost ? P.dir[DIR_COST_F].layer[0].nks : 0;
     const int nk_costb = P.use_cost ? P.dir[DIR_COST_B].layer[0].nks : 0;
     float opmax = 0.f;  // largest operand magnitude this thread has written (fp16 range check)
+    __half2 opmax2 = __float2half2_rn(0.f);   // the same for the packed hidden operands (NaN-propagating maximum)
 
 #ifdef GMPC_T128_TIMED
-    long long e_acc = 0, e_hid = 0, e_bnd = 0, e_ld = 0, e_alu0 = 0, e_acc1 = 0, e_pub0 = 0, e_p1 = 0, eq, eh, ex;
-    long long e_last = clock64(), e_lay[32];
-    int e_prev = -1;
-    for (int i = 0; i < 32; ++i) e_lay[i] = 0;
-    auto lay_mark = [&](int id) {
-      const long long now = clock64();
-      if (e_prev >= 0) e_lay[e_prev] += now - e_last;
-      e_last = now;
-      e_prev = id;
-    };
+    long long e_acc = 0, e_hid = 0, e_bnd = 0, e_ld = 0, e_alu = 0, e_st = 0, e_fin = 0, eq, eh, ex;
     const long long e_begin = clock64();
-#define T128_E0(v) v = clock64()
-#define T128_E1(acc, v) acc += clock64() - v
-#else
-#define T128_E0(v)
-#define T128_E1(acc, v)
 #endif
-    // all MMAs of the layer (both N-parts) are complete
+    // all MMAs of the layer are complete (every issuer has committed, with or without a part in this layer)
     auto wait_acc = [&]() {
+      T128_POS(elno, 1);
       T128_E0(eq);
-      T_WAIT(acc_a, acc_ph, 20, elno2);
-      T_WAIT(acc_a + 8, acc_ph, 21, elno2);
-      ++elno2;
+      T_WAIT(acc_a, acc_par, 20, elno);
       T128_E1(e_acc, eq);
-#ifdef GMPC_T128_TIMED
-      lay_mark(cur_kind * 8 + 7);
+      T128_POS(elno, 2);
+      if (q == 0 && lane == 0) T128_TR(elno, 520 + (elno - T128_TRACE_L0) * 20 + sub * 5);
       ++elno;
-      if (tr_on) T128_TRACE(elno, tr_base + 0);
-#endif
-      acc_ph ^= 1;
+      acc_par ^= 1u;
       tc_fence_after();
     };
-    // "my reads of the accumulator (both parts) are complete" (after tcgen05.wait::ld)
-    auto arrive_drained = [&]() {
+    // "my share of feature blocks [4 r, 4 r + 4) of the next operand is stored" (after tcgen05.wait::st), or "I have
+    // none in this round": every warp arrives on every round barrier of every layer
+    auto arrive_round = [&](int rnd) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive_a(dr_a); mbar_arrive_a(dr_a + 8); }
+      if (lane == 0) mbar_arrive_a(rnd_a + 8 * rnd);
     };
-    // sub 0 (the four warps that wrote it): "k-steps [0, nk) of the next operand are in TMEM" (after tcgen05.wait::st)
-    auto arrive_act_range = [&](int nk) {
-      if (sub != 0) return;
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0)
-        for (int j = 0; j < nk; ++j) mbar_arrive_a(act_a + 8 * j);
-    };
-    // sub 0: features [16 ks, 16 ks + 16) of a small operand, already scaled -> k-step ks of the A operand
-    auto store_kstep = [&](int ks, const float (&v)[16]) {
+    // sub 0: features [16 ks, 16 ks + 16) of a small operand, already scaled -> feature block ks of region `opn`
+    auto store_kstep = [&](uint32_t opn, int ks, const float (&v)[16]) {
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         opmax = fmaxf(opmax, fmaxf(fabsf(v[2 * k]), fabsf(v[2 * k + 1])));
         split_h2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
       }
-      t_st8(tl + T_AH_COL + 8 * ks, hi);
-      t_st8(tl + T_AL_COL + 8 * ks, lo);
+      t_st8(opn + 16 * ks, hi);
+      t_st8(opn + 16 * ks + 8, lo);
     };
-    auto load16 = [&](int half, float (&o)[16]) {
+    auto load16 = [&](int half, float (&o)[16]) {   // 16 columns of the narrow accumulator
       uint32_t d0[16];
-      tmem_ld16_issue(tl + T_D_COL + 16 * half, d0);
+      tmem_ld16_issue(tl + T_RC + 16 * half, d0);
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 16; ++c) o[c] = __uint_as_float(d0[c]);
     };
 
+    // the first adjoint boundary layer has no predecessor whose narrow accumulator is still being read
+    if (sub == 1 && lane == 0) mbar_arrive_a(rc_a);
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
       const long long q0 = (long long)tile * T_NB;
@@ -517,8 +517,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
       float Jr = 0.f;
       float sg = 1.f;           // sub 0: scale of the adjoint operand in flight
       float bc1 = 1.f, bc2 = 1.f;
-      // staging cost of step t for this thread's trajectory (sub 0): x from shared memory, u / goal from scratch
+      // staging cost of step t for this thread's trajectory (sub 0): x from shared memory, u / goal from scratch.
+      // Only the sweep whose J is reported needs it (the final evaluation, or the only sweep of a call without one).
+      bool want_J = false;
       auto stage_cost = [&](int t) {
+        if (!want_J) return;
         float dd = 0.f, uu = 0.f;
         if (need_goal)
           for (int i = 0; i < n; ++i) {
@@ -535,8 +538,9 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
           Jr += dd;
         }
       };
-      // sub 0: the <= 32-feature operand [xs ; us] * sc (us: nu features after the n state features) -> k-steps [0, nk)
-      auto publish_state_operand = [&](const float* xcol, int nu, float sc, int nk) {
+      // sub 0: the <= 32-feature operand [xs ; us] * sc (us: nu features after the n state features) -> feature
+      // blocks [0, nk) of region `opn`
+      auto publish_state_operand = [&](uint32_t opn, const float* xcol, int nu, float sc, int nk) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h < nk) {
@@ -549,14 +553,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
               else if (i < n + nu) x = us[(i - n) * T_NB];
               v[c] = x * sc;
             }
-            store_kstep(h, v);
+            store_kstep(opn, h, v);
           }
         }
         t_st_wait();
       };
-      // every layer's first MMA waits for "accumulator drained" by the epilogue of the layer before it (also
-      // across tiles); only the very first layer of the kernel has no predecessor
-      if (ti == 0) arrive_drained();
 
       TPassWalk walk;
       int it = 0, tf = 0, tb = T - 1;
@@ -566,7 +567,6 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
         const TDir& D = P.dir[kind];
         const bool last = (it == P.iters);
         const bool fwd = (kind == DIR_DYN_F || kind == DIR_COST_F);
-        cur_kind = kind;
         if (kind == DIR_DYN_F && tf == 0) {
           // ------------------------------------------------------------ start of a forward sweep
           named_bar_sync(1, T_EPI);  // the previous sweep's updates of U are visible
@@ -580,10 +580,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
             for (int j = 0; j < m; ++j) us[j * T_NB] = wsU[j * T_NB];
             const float s0 = pow2_scale_to_8(mx);
             ssc_s[r] = s0;
-            publish_state_operand(xs, m, s0, nk_dynf);
+            publish_state_operand(tl + t_region(cur), xs, m, s0, nk_dynf);
           }
-          arrive_act_range(nk_dynf);
+          arrive_round(0);
           Jr = 0.f;
+          want_J = last || !P.final_fwd;
           if (sub == 0) stage_cost(0);
           if (adam && sub == 1) {
             bc1 = (float)(1.0 - pow((double)P.b1, (double)(it + 1)));
@@ -598,122 +599,104 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
           else if (kind == DIR_COST_F) maskp = costMask + (size_t)l * MSTR;
           else if (kind == DIR_COST_B) maskp = costMask + (size_t)(D.L - 2 - l) * MSTR;
           else maskp = wsMask + ((size_t)tb * (Ld - 1) + (D.L - 2 - l)) * MSTR;
-          // accumulator -> (+bias, ReLU, mask bit) or (mask gate) -> hi/lo -> next A operand.  The forward pass
-          // runs in scaled units a' = a s (ReLU is positively homogeneous): the bias enters as b s.
-          // k-step j of the next operand (features [16 j, 16 j + 16)) belongs to sub j % 4.  Part 0 (k-steps
-          // [0, nk0)) is read out, processed AND stored while the tensor pipe works on part 1: k-step j of the
-          // operand in flight may be overwritten as soon as part 1's MMAs of k-step j are complete (rel_bar[j]).
-          const int nk0 = Y.ncol[0] >> 4, nk1 = Y.ncol[1] >> 4;
+          // accumulator -> (+bias, ReLU, mask bit) or (mask gate) -> hi/lo -> A operand of the next layer, in place.
+          // The forward pass runs in scaled units a' = a s (ReLU is positively homogeneous): the bias enters as b s.
+          const uint32_t dreg = tl + t_region(cur ^ 1u);
           const float inv = inv_s[Y.scale_idx];
           const float* bp = bias_s + Y.bias_off;
           float s = 1.f;
-          // 16 accumulator values (one k-step of the next operand) of this thread's trajectory -> packed hi / lo halfs
-          auto process16 = [&](const uint32_t (&raw)[16], int jg, uint32_t& mw, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
-            float z[16];
-            if (fwd) {
+          // ReLU bits of my feature blocks: block j -> 16 bits of word (j >> 3), at bits [0, 8) (even elements) and
+          // [16, 24) (odd elements), shifted left by 8 when (j & 4); a set bit = pre-activation >= +0
+          uint32_t mw0 = 0u, mw1 = 0u;
+          if (!fwd) { mw0 = maskp[0]; mw1 = maskp[T_EPI]; }
+          // 16 accumulator values (one feature block) of this thread's trajectory -> packed hi / lo halfs, two elements
+          // at a time in the packed domain: hr = fp16x2(z); negative halves are cleared with a byte-permute sign mask
+          // (forward: ReLU; the adjoint clears the halves whose stored bit is 0); lo = fp16x2(z - hi) through the
+          // mixed-precision fma (fp16 x fp16 + fp32), cleared with the same mask.
+          // gbits: forward: returns the NEGATIVE bits of the block; adjoint: takes the block's stored bits.
+          auto process16 = [&](const uint32_t (&raw)[16], int jg, uint32_t& gbits, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+            uint32_t neg = 0u;
 #pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bp + 16 * jg + 4 * c4);
-                z[4 * c4 + 0] = fmaf(__uint_as_float(raw[4 * c4 + 0]), inv, b4.x * s);
-                z[4 * c4 + 1] = fmaf(__uint_as_float(raw[4 * c4 + 1]), inv, b4.y * s);
-                z[4 * c4 + 2] = fmaf(__uint_as_float(raw[4 * c4 + 2]), inv, b4.z * s);
-                z[4 * c4 + 3] = fmaf(__uint_as_float(raw[4 * c4 + 3]), inv, b4.w * s);
+            for (int k = 0; k < 8; ++k) {
+              float z0, z1;
+              if (fwd) {
+                const float2 b2 = *reinterpret_cast<const float2*>(bp + 16 * jg + 2 * k);
+                z0 = fmaf(__uint_as_float(raw[2 * k]), inv, b2.x * s);
+                z1 = fmaf(__uint_as_float(raw[2 * k + 1]), inv, b2.y * s);
+              } else {
+                z0 = __uint_as_float(raw[2 * k]) * inv;
+                z1 = __uint_as_float(raw[2 * k + 1]) * inv;
               }
-#pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                mw = __funnelshift_l(__float_as_uint(z[c]), mw, 1);   // collects the SIGN bits (complemented below)
-                z[c] = fmaxf(z[c], 0.f);
+              uint32_t hr, clr;
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hr) : "f"(z1), "f"(z0));
+              if (fwd) {
+                clr = t_half_signs(hr);                              // 0xFFFF in every negative half
+                neg |= clr & (0x00010001u << k);
+              } else {
+                clr = ~t_half_signs(gbits << (15 - k));              // 0xFFFF in every half whose stored bit is 0
               }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const float v = __uint_as_float(raw[c]) * inv;
-                z[c] = ((int)mw < 0) ? v : 0.f;
-                mw <<= 1;
-              }
+              const uint32_t h = hr & ~clr;
+              float d0, d1;
+              asm("{\n\t.reg .f16 l, u, m1;\n\tmov.b32 {l, u}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
+                  "fma.rn.f32.f16 %0, l, m1, %3;\n\tfma.rn.f32.f16 %1, u, m1, %4;\n\t}"
+                  : "=f"(d0), "=f"(d1) : "r"(h), "f"(z0), "f"(z1));
+              uint32_t lr;
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lr) : "f"(d1), "f"(d0));
+              hi[k] = h;
+              lo[k] = lr & ~clr;
+              const __half2 h2 = *reinterpret_cast<const __half2*>(&h);
+              opmax2 = __hmax2_nan(opmax2, fwd ? h2 : __habs2(h2));
             }
-#pragma unroll
-            for (int c = 0; c < 16; c += 4)
-              opmax = fmaxf(opmax, fmaxf(fmaxf(fabsf(z[c]), fabsf(z[c + 1])), fmaxf(fabsf(z[c + 2]), fabsf(z[c + 3]))));
-#pragma unroll
-            for (int k = 0; k < 8; ++k) split_h2(z[2 * k], z[2 * k + 1], hi[k], lo[k]);
+            if (fwd) gbits = neg;
           };
           T128_E0(eh);
+          wait_acc();
+          if (fwd) s = ssc_s[r];
+          const int nko = Y.npad >> 4;
+          // one round: block j (if it exists) -> operand, then the round's arrival.  (Reading the block of the next
+          // round ahead of the arithmetic needs 16 more registers than the 96 a 5-warp scheduler partition allows.)
 #pragma unroll 1
-          for (int pt = 0; pt < 2; ++pt) {
-            // part 0 runs under the MMAs of part 1, part 1 after the layer's last MMA
-            T128_E0(eq);
-            T_WAIT(acc_a + 8 * pt, acc_ph, 22 + pt, elno2);
-            if (pt == 1) ++elno2;
-            T128_E1(e_acc, eq);
-#ifdef GMPC_T128_TIMED
-            if (pt == 0) { lay_mark(kind * 8 + l); ++elno; }
-            if (tr_on) T128_TRACE(elno, tr_base + pt * 6 + 0);
-#endif
-            tc_fence_after();
-            if (pt == 0 && fwd) s = ssc_s[r];
-            const int jbeg = pt ? nk0 : 0, jend = pt ? nk0 + nk1 : nk0, dcol = pt ? Y.ncol[0] : 0;
-            const bool need_rel = (pt == 0 && nk1 > 0);
-            uint32_t mw = fwd ? 0u : maskp[pt * T_EPI];
-            int nb = 0;
-            const int jfirst = jbeg + ((sub - jbeg) & 3);   // my first k-step of this part (k-step j belongs to sub j % 4)
-            if (jfirst >= jend) {                           // none: nothing of this part to read
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive_a(dr_a + 8 * pt);
-            }
-            uint32_t raw[16];
-            if (jfirst < jend) {
-              tmem_ld16_issue(tl + T_D_COL + dcol + 16 * (jfirst - jbeg), raw);
+          for (int j = 3 - sub; j < ((nko + 3) & ~3); j += 4) {   // the first blocks come from the subs without boundary duties
+            if (j < nko) {
+              uint32_t raw[16], hi[8], lo[8];
+              T128_E0(ex);
+              tmem_ld16_issue(dreg + 16 * j, raw);
               tmem_ld_wait();
-            }
-#pragma unroll 1
-            for (int j = jfirst; j < jend; j += 4) {
-              uint32_t nxt[16], hi[8], lo[8];
-              const bool more = j + 4 < jend;
-              // the read of my next k-step is in flight under the arithmetic of this one (16 warps reading at once
-              // are bound by the ~64 B/clk TMEM read path)
-              if (more) tmem_ld16_issue(tl + T_D_COL + dcol + 16 * (j + 4 - jbeg), nxt);
-              else {   // my last read of this part of the accumulator is complete
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_a(dr_a + 8 * pt);
+              T128_E1(e_ld, ex);
+              T128_E0(ex);
+              const int sh = (j & 4) << 1;            // 0 or 8: position of block j's bits in its mask word
+              uint32_t gb = 0u;
+              if (!fwd) gb = ((j & 8) ? mw1 : mw0) >> sh;
+              process16(raw, j, gb, hi, lo);
+              if (fwd) {
+                const uint32_t act = (~gb & 0x00FF00FFu) << sh;   // negative bits -> (z >= +0) bits
+                if (j & 8) mw1 |= act; else mw0 |= act;
               }
-              if (tr_on) T128_TRACE(elno, tr_base + pt * 6 + 1 + 2 * ((j - jfirst) >> 2));
+              T128_E1(e_alu, ex);
               T128_E0(ex);
-              process16(raw, j, mw, hi, lo);
-              nb += 16;
-              T128_E1(e_alu0, ex);
-              T128_E0(ex);
-              if (need_rel && j < Y.nks) T_WAIT(rel_a + 8 * j, (rel_par >> j) & 1u, 24, elno2 * 16 + j);
-              T128_E1(e_acc1, ex);
-              T128_E0(ex);
-              t_st8(tl + T_AH_COL + 8 * j, hi);
-              t_st8(tl + T_AL_COL + 8 * j, lo);
+              t_st8(dreg + 16 * j, hi);
+              t_st8(dreg + 16 * j + 8, lo);
               t_st_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive_a(act_a + 8 * j);
-              T128_E1(e_pub0, ex);
-              if (more) {
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 16; ++c) raw[c] = nxt[c];
-              }
+              T128_E1(e_st, ex);
             }
-            // sign bits -> (z >= +0) bits, first element at bit 31 (the adjoint sweep shifts them out in order)
-            if (fwd) maskp[pt * T_EPI] = nb == 0 ? 0u : (~mw) << (32 - nb);
+            arrive_round(j >> 2);
+            T128_POS(elno, 32 + j);
+            if (q == 0 && lane == 0) T128_TR(elno - 1, 520 + (elno - 1 - T128_TRACE_L0) * 20 + sub * 5 + 1 + (j >> 2));
           }
-          acc_ph ^= 1;
-          rel_par ^= (1u << Y.nks) - 1u;
-          T128_E1(e_p1, ex);
+          T128_E0(ex);
+          if (fwd) { maskp[0] = mw0; maskp[T_EPI] = mw1; }
+          cur ^= 1u;
+          T128_E1(e_fin, ex);
           T128_E1(e_hid, eh);
         }
         T128_E0(eh);
         // -------------------------------------------------------------- last layer of the pass (<= 32 outputs)
+        // accumulator in the narrow region; the next operand (if a layer follows) goes to the region the
+        // layer's own operand does NOT occupy
         const TLayer& Yf = D.layer[D.L - 1];
         const float invf = inv_s[Yf.scale_idx];
-        rel_par ^= (1u << Yf.nks) - 1u;   // (the last layer's epilogues below start after all of its MMAs)
+        const uint32_t opn = tl + t_region(cur ^ 1u);
+        cur ^= 1u;
         if (kind == DIR_DYN_F) {
           // step boundary: x_{t+1} = x_t + Dense(h); sub 0 writes the next operand [x_{t+1} ; u_{t+1}] s_{t+1}
           const int t = tf;
@@ -743,16 +726,13 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
                 }
               }
             }
-            arrive_drained();
             if (more) {
               const float sn = pow2_scale_to_8(mx);
               ssc_s[r] = sn;
-              publish_state_operand(xs, with_u ? m : 0, sn, nk_next);
+              publish_state_operand(opn, xs, with_u ? m : 0, sn, nk_next);
             }
-          } else {
-            arrive_drained();
           }
-          if (more) arrive_act_range(nk_next);
+          if (more) arrive_round(0);
           if (sub == 0) {  // off the critical path: keep x_{t+1} for the adjoint sweep, its staging cost
             for (int i = 0; i < n; ++i) wsX[((size_t)(t + 1) * n + i) * T_NB] = xs[i * T_NB];
             if (t + 1 < T) stage_cost(t + 1);
@@ -779,9 +759,9 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
                   }
                   sg = pow2_scale_to_8(mx);
                   sig_s[((T - 1) & 1) * T_NB + r] = sg;
-                  publish_state_operand(lam, 0, sg, nk_dynb);
+                  publish_state_operand(opn, lam, 0, sg, nk_dynb);
                 }
-                arrive_act_range(nk_dynb);
+                arrive_round(0);
               }
             }
           }
@@ -796,7 +776,6 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
             float y0[16], y1[16];
             load16(0, y0);
             if (P.fout > 16) load16(1, y1);
-            arrive_drained();
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               float ya = 0.f, yb = 0.f;
@@ -812,14 +791,12 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
               sg = pow2_scale_to_8(mx);
 #pragma unroll
               for (int c = 0; c < 16; ++c) { y0[c] *= sg; y1[c] *= sg; }
-              store_kstep(0, y0);
-              if (nk_costb > 1) store_kstep(1, y1);
+              store_kstep(opn, 0, y0);
+              if (nk_costb > 1) store_kstep(opn, 1, y1);
               t_st_wait();
             }
-          } else {
-            arrive_drained();
           }
-          if (!last) arrive_act_range(nk_costb);
+          if (!last) arrive_round(0);
         } else if (kind == DIR_COST_B) {
           // ------------------------------------------------------------ lambda_T = d(terminal cost)/dx_T
           wait_acc();
@@ -842,14 +819,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
                 }
               }
             }
-            arrive_drained();
             sg = pow2_scale_to_8(mx);
             sig_s[((T - 1) & 1) * T_NB + r] = sg;
-            publish_state_operand(lam, 0, sg, nk_dynb);
-          } else {
-            arrive_drained();
+            publish_state_operand(opn, lam, 0, sg, nk_dynb);
           }
-          arrive_act_range(nk_dynb);
+          arrive_round(0);
           if (sub == 0 && P.lam_out != nullptr && rvalid)
             for (int i = 0; i < n; ++i) P.lam_out[(qr * (T + 1) + T) * n + i] = lam[i * T_NB];
         } else {
@@ -899,41 +873,45 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
                 }
               }
             }
-            arrive_drained();
             if (t > 0) {
               sg = pow2_scale_to_8(mx);
               sig_s[((t - 1) & 1) * T_NB + r] = sg;
-              publish_state_operand(lam, 0, sg, nk_next);
-              arrive_act_range(nk_next);
+              publish_state_operand(opn, lam, 0, sg, nk_next);
+              arrive_round(0);
             }
             if (P.lam_out != nullptr && rvalid)
               for (int i = 0; i < n; ++i) P.lam_out[(qr * (T + 1) + t) * n + i] = lam[i * T_NB];
           } else if (sub == 1) {
             const float c0 = invf * pow2_recip(sig_s[(t & 1) * T_NB + r]);
+            // the u features are columns [n, n + m) of the narrow accumulator: read them, then the update is off the
+            // critical path
+            float o0[16], o1[16];
+            const bool need0 = n < 16, need1 = n + m > 16;
+            if (need0) load16(0, o0);
+            if (need1) load16(1, o1);
+            tc_fence_before();     // the narrow accumulator may be overwritten by the next adjoint boundary layer
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(rc_a);
+            if (t > 0) arrive_round(0);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              if (16 * h < n + m && 16 * h + 16 > n) {
-                float o[16];
-                load16(h, o);
-                if (h == 1 || n + m <= 16) {  // the accumulator is read out: free it, the update is off the critical path
-                  arrive_drained();
-                  if (t > 0) arrive_act_range(nk_next);
-                }
+              if (h == 0 ? need0 : need1) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                   const int i = 16 * h + c;
                   if (i >= n && i < n + m) {
                     const int j = i - n;
                     const size_t ix = ((size_t)t * m + j) * T_NB;
-                    float u = wsU[ix];
-                    float g = o[c] * c0;
+                    float u = wsU[ix], m_old = 0.f, v_old = 0.f;
+                    if (adam) { m_old = wsM[ix]; v_old = wsV[ix]; }
+                    float g = (h == 0 ? o0[c] : o1[c]) * c0;
                     if (cost_mode) g = (w0 * u) / su + g;
                     if (P.mode == MODE_PLAN) {
                       if (P.method == 0) {
                         u = u - P.lr * g;
                       } else {
-                        const float mo = P.b1 * wsM[ix] + (1.f - P.b1) * g;
-                        const float ve = P.b2 * wsV[ix] + (1.f - P.b2) * g * g;
+                        const float mo = P.b1 * m_old + (1.f - P.b1) * g;
+                        const float ve = P.b2 * v_old + (1.f - P.b2) * g * g;
                         wsM[ix] = mo;
                         wsV[ix] = ve;
                         u = u - P.lr * (mo / bc1) / (sqrtf(ve / bc2) + P.eps);
@@ -944,14 +922,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
                     }
                   }
                 }
-              } else if (h == 1 && n + m > 16) {   // (unreachable for n + m > 16: the second half always holds u features)
-                arrive_drained();
-                if (t > 0) arrive_act_range(nk_next);
               }
             }
           } else {
-            arrive_drained();
-            if (t > 0) arrive_act_range(nk_next);
+            if (t > 0) arrive_round(0);
           }
           if (--tb < 0) {
             tb = T - 1;
@@ -986,13 +960,13 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
         }
       }
     }
+    opmax = fmaxf(opmax, 0.f);
+    if (!(fmaxf(__low2float(opmax2), __high2float(opmax2)) <= 65000.f)) opmax = __int_as_float(0x7fc00000);
     if (!(opmax <= 65000.f) && P.ovf != nullptr) atomicAdd(P.ovf, 1u);
 #ifdef GMPC_T128_TIMED
-    if (blockIdx.x == 0 && P.dbg != nullptr && lane == 0 && (ew == 0 || ew == 4)) {
-      long long* o = P.dbg + 8 + (ew >> 2) * 8;   // sub 0 and sub 1 of one lane quarter
-      o[0] = clock64() - e_begin; o[1] = e_acc; o[2] = e_hid; o[3] = e_bnd; o[4] = e_ld;
-      if (ew == 0) for (int i = 0; i < 32; ++i) P.dbg[64 + i] = e_lay[i];
-      P.dbg[24 + (ew >> 2) * 8 + 0] = e_alu0; P.dbg[24 + (ew >> 2) * 8 + 1] = e_acc1; P.dbg[24 + (ew >> 2) * 8 + 2] = e_pub0; P.dbg[24 + (ew >> 2) * 8 + 3] = e_p1;
+    if (blockIdx.x == 0 && P.dbg != nullptr && lane == 0 && (ew & 3) == 0) {
+      long long* o = P.dbg + 8 + sub * 8;   // the four subs of lane quarter 0
+      o[0] = clock64() - e_begin; o[1] = e_acc; o[2] = e_hid; o[3] = e_bnd; o[4] = e_ld; o[5] = e_alu; o[6] = e_st; o[7] = e_fin;
     }
 #endif
   }
@@ -1008,10 +982,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
 // by the power of two that puts max |W| in [2^10, 2^11) (same rule as h16_pack_kernel).
 //   transposed == 0 (forward):  operand row = output feature n, reduction index = input feature k.
 //   transposed == 1 (adjoint):  operand row = input feature k,  reduction index = output feature n.
-// Image of a layer: N-part 0 (operand rows [0, n0)), then N-part 1 (rows [n0, n0 + n1)); per part, per k-step:
-// [hi tile | lo tile], tile = [2 k-chunks][rows of the part][8 halfs]
+// Image of a layer: per k-step, per N-part p (operand rows [c0[p], c0[p+1])): [hi tile | lo tile],
+// tile = [2 k-chunks][rows of the part][8 halfs]
 // (K-major SWIZZLE_NONE core matrices: LBO = rows * 16, SBO = 128; pinned by tools/t128_probe.cu).
-__global__ void t128_pack_kernel(const float* __restrict__ W, int K, int N, int transposed, uint8_t* dst, int n0, int n1,
+struct TParts {
+  int np;
+  int c0[T_MAXP + 1];   // first row of part p; c0[np] = padded row count
+};
+__global__ void t128_pack_kernel(const float* __restrict__ W, int K, int N, int transposed, uint8_t* dst, TParts pp,
                                  int nks, const uint32_t* absmax, float* inv_scale) {
   const float mx = __uint_as_float(*absmax);
   float sc = 1.f;
@@ -1029,12 +1007,16 @@ __global__ void t128_pack_kernel(const float* __restrict__ W, int K, int N, int 
   const int kk = transposed ? o : k;
   __half hi, lo;
   split_h1(W[idx] * sc, hi, lo);
-  const int part = row >= n0 ? 1 : 0;
-  const int rows = part ? n1 : n0;
-  if (part) { row -= n0; dst += (size_t)nks * n0 * 64; }
+  int part = 0;
+  while (part + 1 < pp.np && row >= pp.c0[part + 1]) ++part;
+  const int rows = pp.c0[part + 1] - pp.c0[part];
+  const int npad = pp.c0[pp.np];
+  row -= pp.c0[part];
   const size_t tile_b = (size_t)rows * 32;
   const int j = kk >> 4, k16 = kk & 15;
-  uint8_t* p = dst + (size_t)j * 2 * tile_b + (size_t)(k16 >> 3) * rows * 16 + (row >> 3) * 128 + (row & 7) * 16 + (k16 & 7) * 2;
+  (void)nks;
+  uint8_t* p = dst + ((size_t)j * npad + pp.c0[part]) * 64 + (size_t)(k16 >> 3) * rows * 16 + (row >> 3) * 128 + (row & 7) * 16 +
+               (k16 & 7) * 2;
   *reinterpret_cast<__half*>(p) = hi;
   *reinterpret_cast<__half*>(p + tile_b) = lo;
 }
@@ -1054,14 +1036,11 @@ struct T128State {
   uint32_t* d_ovf = nullptr;
   float *ws_X = nullptr, *ws_G = nullptr, *ws_U = nullptr, *ws_M = nullptr, *ws_V = nullptr;
   uint32_t* ws_mask = nullptr;
-  int nbias = 0, nscale = 0, nslot = 0, maxks = 13;
+  int nbias = 0, nscale = 0, nslot = 0;
   uint32_t slot_bytes = 0;
   size_t smem_bytes = 0;
   long long* d_dbg = nullptr;  // tools/t128_bench.cu with -DGMPC_T128_TIMED
 };
-
-using T128Kernel = void (*)(const TParams);
-inline T128Kernel t128_kernel_ptr(int) { return plan_t128_kernel; }
 
 inline int t_rup(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -1071,6 +1050,22 @@ inline void t128_destroy(T128State& S) {
   S.d_stream = nullptr; S.d_bias = S.d_scale = nullptr; S.d_absmax = S.d_ovf = nullptr;
   S.ws_X = S.ws_G = S.ws_U = S.ws_M = S.ws_V = nullptr; S.ws_mask = nullptr;
   S.supported = false;
+}
+
+// N-parts of a layer with npad output columns: parts of `bpp` feature blocks (16 columns each), the last part
+// takes the remainder; a layer of fewer than bpp blocks (and the narrow last layer of a pass) is one part.
+inline void t128_parts(TLayer& Y, int bpp) {
+  const int nko = Y.npad / 16;
+  const int np = std::min(T_MAXP, std::max(1, nko / bpp));
+  const int per = (nko / bpp > T_MAXP) ? nko / np : bpp;
+  Y.np = np;
+  int c = 0;
+  for (int p = 0; p < T_MAXP; ++p) {
+    const int nb = p >= np ? 0 : (p == np - 1 ? nko - per * (np - 1) : per);
+    Y.c0[p] = c;
+    Y.ncol[p] = 16 * nb;
+    c += 16 * nb;
+  }
 }
 
 inline int t128_create(T128State& S, const gmpc_config& c, const int* dyn_dims, const int* cost_dims,
@@ -1084,59 +1079,49 @@ inline int t128_create(T128State& S, const gmpc_config& c, const int* dyn_dims, 
   for (int i = 1; i < S.Ld; ++i) hmax = std::max(hmax, dyn_dims[i]);
   for (int i = 1; i < S.Lc; ++i) hmax = std::max(hmax, cost_dims[i]);
   if (S.Ld < 2) { S.why = "dynamics MLP has no hidden layer"; return GMPC_OK; }
-  if (hmax > 256) { S.why = "hidden width > 256 (accumulator + split operand exceed the 512 TMEM columns)"; return GMPC_OK; }
+  int hmin = 1 << 30;
+  for (int i = 1; i < S.Ld; ++i) hmin = std::min(hmin, dyn_dims[i]);
+  for (int i = 1; i < S.Lc; ++i) hmin = std::min(hmin, cost_dims[i]);
+  if (hmin < 17) { S.why = "hidden width < 17 (every epilogue sub-group pair must own a feature block)"; return GMPC_OK; }
+  if (hmax > T_MAXH) { S.why = "hidden width > 240 (two operand / accumulator regions exceed the 512 TMEM columns)"; return GMPC_OK; }
   if (c.n + c.m > 32 || c.cost_fout > 32) { S.why = "n+m or fout > 32"; return GMPC_OK; }
-  S.maxks = 13;
-  // geometry: N-parts, biases, scales, images.  A layer with more than 32 output columns is issued as two
-  // N-parts (k-steps of the next operand split ceil/floor), the narrow last layer of a pass as one.
-  auto parts = [&](TLayer& Y) {
-    const int nko = Y.npad / 16;
-    if (Y.npad <= 32) { Y.ncol[0] = Y.npad; Y.ncol[1] = 0; }
-    else { Y.ncol[0] = 16 * ((nko + 1) / 2); Y.ncol[1] = Y.npad - Y.ncol[0]; }
-  };
-  uint32_t slot = 0;
-  auto widest = [&](const int* dims, int Ln) {
-    for (int l = 0; l < Ln; ++l)
-      for (int side = 0; side < 2; ++side) {
-        TLayer Y;
-        Y.npad = t_rup(dims[l + (side ? 0 : 1)], 16);
-        parts(Y);
-        slot = std::max(slot, (uint32_t)Y.ncol[0] * 64u);
-      }
-  };
-  widest(S.dyn_dims, S.Ld);
-  widest(S.cost_dims, S.Lc);
-  S.slot_bytes = std::max(slot, 16384u);  // ring group: >= one k-step of the widest N-part, 16 KB when it is smaller
+  int bpp = 4;
+  if (const char* e = getenv("GMPC_T128_PART_BLOCKS")) bpp = std::max(1, atoi(e));
   int nbias = 0, nscale = 0;
-  auto one_layer = [&](TLayer& Y, int M_true, int red, size_t& off) {
+  uint32_t slot = 0;
+  auto one_layer = [&](TLayer& Y, int M_true, int red, bool narrow) {
+    memset(&Y, 0, sizeof(Y));
     Y.M_true = M_true; Y.npad = t_rup(M_true, 16); Y.nks = t_rup(red, 16) / 16;
-    parts(Y);
-    for (int pt = 0; pt < 2; ++pt) {
-      Y.kpg[pt] = Y.ncol[pt] ? std::max(1, (int)(S.slot_bytes / (Y.ncol[pt] * 64))) : 1;
-      Y.goff[pt] = (uint32_t)off;
-      off += (size_t)Y.nks * Y.ncol[pt] * 64;
-    }
-    Y.pad_ = 0;
+    t128_parts(Y, narrow ? 1000 : bpp);
+    slot = std::max(slot, (uint32_t)Y.npad * 64u);
   };
-  auto geom = [&](const int* dims, int Ln, TDir& F, TDir& Bw, size_t& off_f, size_t& off_b) {
+  auto geom = [&](const int* dims, int Ln, TDir& F, TDir& Bw) {
     F.L = Bw.L = Ln; F.pad_ = Bw.pad_ = 0;
     for (int l = 0; l < Ln; ++l) {
       TLayer& Y = F.layer[l];
-      one_layer(Y, dims[l + 1], dims[l], off_f);
+      one_layer(Y, dims[l + 1], dims[l], l == Ln - 1);
       Y.bias_off = nbias; nbias += Y.npad;
       Y.scale_idx = nscale + l;
     }
     for (int i = 0; i < Ln; ++i) {
       const int lt = Ln - 1 - i;  // the adjoint pass visits the transposed layers L-1 .. 0
       TLayer& Y = Bw.layer[i];
-      one_layer(Y, dims[lt], dims[lt + 1], off_b);
+      one_layer(Y, dims[lt], dims[lt + 1], i == Ln - 1);
       Y.bias_off = 0; Y.scale_idx = nscale + lt;
     }
     nscale += Ln;
   };
+  geom(S.dyn_dims, S.Ld, S.dir[DIR_DYN_F], S.dir[DIR_DYN_B]);
+  geom(S.cost_dims, S.Lc, S.dir[DIR_COST_F], S.dir[DIR_COST_B]);
+  S.slot_bytes = std::max(slot, 16384u);  // ring group: >= one k-step of the widest layer, 16 KB when it is smaller
   size_t sz[4] = {0, 0, 0, 0};
-  geom(S.dyn_dims, S.Ld, S.dir[DIR_DYN_F], S.dir[DIR_DYN_B], sz[DIR_DYN_F], sz[DIR_DYN_B]);
-  geom(S.cost_dims, S.Lc, S.dir[DIR_COST_F], S.dir[DIR_COST_B], sz[DIR_COST_F], sz[DIR_COST_B]);
+  for (int d = 0; d < 4; ++d)
+    for (int l = 0; l < S.dir[d].L; ++l) {
+      TLayer& Y = S.dir[d].layer[l];
+      Y.kpg = std::max(1, (int)(S.slot_bytes / (Y.npad * 64)));
+      Y.goff = (uint32_t)sz[d];
+      sz[d] += (size_t)Y.nks * Y.npad * 64;
+    }
   S.nbias = nbias; S.nscale = nscale;
   const TSmem L0 = t_smem_layout(0, S.slot_bytes, nbias, nscale, c.n, c.m);
   int nslot = (int)((smem_optin - std::min(smem_optin, (size_t)L0.total)) / S.slot_bytes);
@@ -1166,8 +1151,7 @@ inline int t128_create(T128State& S, const gmpc_config& c, const int* dyn_dims, 
   if (cudaMalloc(&S.ws_M, G * su * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
   if (cudaMalloc(&S.ws_V, G * su * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
   if (cudaMalloc(&S.ws_mask, G * smk * sizeof(uint32_t)) != cudaSuccess) return GMPC_E_CUDA;
-  if (cudaFuncSetAttribute(t128_kernel_ptr(S.maxks), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_bytes) !=
-      cudaSuccess)
+  if (cudaFuncSetAttribute(plan_t128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_bytes) != cudaSuccess)
     return GMPC_E_CUDA;
   S.supported = true;
   S.why = "";
@@ -1179,16 +1163,23 @@ inline int t128_set_weights(T128State& S, const float* const* dyn_W, const float
   if (!S.supported) return GMPC_OK;
   cudaMemsetAsync(S.d_absmax, 0, S.nscale * sizeof(uint32_t), st);
   cudaMemsetAsync(S.d_stream, 0, S.stream_bytes, st);
+  auto parts_of = [](const TLayer& Y) {
+    TParts pp;
+    pp.np = Y.np;
+    for (int p = 0; p < T_MAXP; ++p) pp.c0[p] = Y.c0[p];
+    for (int p = Y.np; p <= T_MAXP; ++p) pp.c0[p] = Y.npad;   // c0[np] = padded row count
+    return pp;
+  };
   auto one = [&](const int* dims, int Ln, const float* const* W, const float* const* b, TDir& F, TDir& Bw, int sbase) {
     for (int l = 0; l < Ln; ++l) {
       const int K = dims[l], N = dims[l + 1], blocks = (K * N + 255) / 256;
       const TLayer& f = F.layer[l];
       const TLayer& rv = Bw.layer[Ln - 1 - l];
       h16_absmax_kernel<<<std::min(blocks, 64), 256, 0, st>>>(W[l], K * N, S.d_absmax + sbase + l);
-      t128_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 0, const_cast<uint8_t*>(F.gsrc) + f.goff[0], f.ncol[0], f.ncol[1],
-                                               f.nks, S.d_absmax + sbase + l, S.d_scale + sbase + l);
-      t128_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 1, const_cast<uint8_t*>(Bw.gsrc) + rv.goff[0], rv.ncol[0],
-                                               rv.ncol[1], rv.nks, S.d_absmax + sbase + l, nullptr);
+      t128_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 0, const_cast<uint8_t*>(F.gsrc) + f.goff, parts_of(f), f.nks,
+                                               S.d_absmax + sbase + l, S.d_scale + sbase + l);
+      t128_pack_kernel<<<blocks, 256, 0, st>>>(W[l], K, N, 1, const_cast<uint8_t*>(Bw.gsrc) + rv.goff, parts_of(rv),
+                                               rv.nks, S.d_absmax + sbase + l, nullptr);
       *launches += 3;
       cudaMemcpyAsync(S.d_bias + f.bias_off, b[l], sizeof(float) * N, cudaMemcpyDeviceToDevice, st);
     }
@@ -1219,7 +1210,7 @@ inline int t128_launch(T128State& S, const PlanParams& P, cudaStream_t st, int64
   Q.dbg = S.d_dbg;
   if (Q.ntiles <= 0) return GMPC_OK;
   const int grid = std::min(Q.ntiles, S.num_sms);
-  t128_kernel_ptr(S.maxks)<<<grid, T_THREADS, S.smem_bytes, st>>>(Q);
+  plan_t128_kernel<<<grid, T_THREADS, S.smem_bytes, st>>>(Q);
   ++*launches;
   return cudaGetLastError() == cudaSuccess ? GMPC_OK : GMPC_E_CUDA;
 }

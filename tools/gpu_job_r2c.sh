@@ -1,0 +1,10 @@
+set -x
+mkdir -p gpurun_out
+L=gpurun_out/t128_bench_r2c.log
+timeout 60 ./build/t128_bench_timed 128 4 2 200 1 > $L 2>&1
+timeout 60 ./build/t128_bench_timed 4096 32 20 200 2 >> $L 2>&1
+timeout 60 ./build/t128_bench 4096 32 20 200 3 >> $L 2>&1
+timeout 60 ./build/t128_bench 18944 32 20 200 3 >> $L 2>&1
+cat $L
+timeout 600 python -m pytest tests/test_gpu_planner.py -m gpu -q -x -k "t128" 2>&1 | tail -15 > gpurun_out/tests_r2c.log
+cat gpurun_out/tests_r2c.log

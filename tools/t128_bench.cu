@@ -32,17 +32,23 @@ int main(int argc, char** argv) {
   memset(&c, 0, sizeof(c));
   c.n = 17; c.m = 6; c.T = T; c.dyn_layers = 4; c.dyn_hidden = H; c.cost_layers = 3; c.cost_hidden = 128; c.cost_fout = 10;
   int dyn_dims[MAXL + 1] = {c.n + c.m, H, H, H, c.n}, cost_dims[MAXL + 1] = {c.n, 128, 128, 10};
+  if (getenv("T128_ODD")) {   // tests/util.py ODD: widths that are not multiples of 16, two-layer cost MLP
+    c.n = 5; c.m = 3; c.dyn_layers = 3; c.dyn_hidden = 50; c.cost_layers = 2; c.cost_hidden = 30; c.cost_fout = 7;
+    const int dd[4] = {8, 50, 50, 5}, cd[3] = {5, 30, 7};
+    for (int i = 0; i < 4; ++i) dyn_dims[i] = dd[i];
+    for (int i = 0; i < 3; ++i) cost_dims[i] = cd[i];
+  }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, 0);
   T128State S;
   int rc = t128_create(S, c, dyn_dims, cost_dims, prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
   if (rc || !S.supported) { printf("t128_create: rc %d supported %d (%s)\n", rc, (int)S.supported, S.why.c_str()); return 1; }
   const float *dW[4], *db[4], *cW[3], *cb[3];
-  for (int l = 0; l < 4; ++l) {
+  for (int l = 0; l < c.dyn_layers; ++l) {
     dW[l] = dev_rand((size_t)dyn_dims[l] * dyn_dims[l + 1], sqrtf(3.f / dyn_dims[l]), 11 + l);
     db[l] = dev_rand(dyn_dims[l + 1], 0.f, 1);
   }
-  for (int l = 0; l < 3; ++l) {
+  for (int l = 0; l < c.cost_layers; ++l) {
     cW[l] = dev_rand((size_t)cost_dims[l] * cost_dims[l + 1], sqrtf(3.f / cost_dims[l]), 21 + l);
     cb[l] = dev_rand(cost_dims[l + 1], 0.f, 1);
   }
@@ -89,49 +95,51 @@ int main(int argc, char** argv) {
   cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
   if (h[40]) {
     const double layers = (double)(iters * (2.0 * T * 4 + 6) + T * 4 + 3);
-    for (int w = 0; w < 2; ++w)
-      printf("  issuer %d: total %lld cycles (%.0f per layer) | wait act %lld  drained %lld  full %lld  hand-off %lld\n", w, h[40 + 8 * w],
-             h[40 + 8 * w] / layers, h[41 + 8 * w], h[42 + 8 * w], h[43 + 8 * w], h[44 + 8 * w]);
-    for (int s = 0; s < 2; ++s)
-      printf("  epi sub%d: total %lld | wait acc %lld  hidden epilogue %lld (of which ld+drain %lld)  boundary (incl. its acc wait) %lld\n", s,
-             h[8 + 8 * s], h[9 + 8 * s], h[10 + 8 * s], h[12 + 8 * s], h[11 + 8 * s]);
-    const double hl = (double)(iters * (2.0 * T * 3 + 4) + T * 3 + 2);
-    for (int s = 0; s < 2; ++s)
-      printf("  epi sub%d per hidden layer (its ~3.3 k-steps): tcgen05.ld+wait %.0f | arithmetic %.0f | wait rel %.0f | st+wait+arrive %.0f\n", s,
-             h[12 + 8 * s] / hl, h[24 + 8 * s] / hl, h[25 + 8 * s] / hl, h[26 + 8 * s] / hl);
+    for (int w = 0; w < 3; ++w)
+      printf("  issuer %d: total %lld (%.0f per layer) | per layer: wait first block %.0f  wait other blocks %.0f  wait ring %.0f  issue+rest %.0f\n", w,
+             h[40 + 8 * w], h[40 + 8 * w] / layers, h[41 + 8 * w] / layers, h[42 + 8 * w] / layers, h[43 + 8 * w] / layers,
+             (h[40 + 8 * w] - h[41 + 8 * w] - h[42 + 8 * w] - h[43 + 8 * w]) / layers);
   }
   if (h[40]) {
-    const char* kn[4] = {"dyn fwd", "cost fwd", "cost bwd", "dyn bwd"};
-    const double cnt[4] = {(double)T * (iters + 1), (double)iters + 1, (double)iters, (double)T * iters};
-    for (int k = 0; k < 4; ++k) {
-      printf("  %-8s cycles from 'part 0 of this layer complete' to the same event of the next layer:", kn[k]);
-      for (int l = 0; l < 8; ++l)
-        if (h[64 + 8 * k + l]) printf("  L%d %.0f", l, h[64 + 8 * k + l] / cnt[k]);
-      printf("\n");
+    const double np = (double)T * (iters + 1);
+    printf("  issuer 0, dyn fwd by layer (layer start -> first block available | -> last MMA issued):");
+    for (int i = 0; i < 4; ++i) printf("  L%d %.0f | %.0f", i, h[100 + i] / np, h[104 + i] / np);
+    printf("\n");
+  }
+  if (h[8]) {
+    const double hl = (double)(iters * (2.0 * T * 3 + 4) + T * 3 + 2);
+    for (int sb = 0; sb < 4; ++sb) {
+      const long long* o = h + 8 + 8 * sb;
+      printf("  epi sub%d: total %lld | wait acc %lld  hidden %lld  boundary %lld | per hidden layer: ld %.0f  alu %.0f  st %.0f  finish %.0f  (all %.0f)\n",
+             sb, o[0], o[1], o[2], o[3], o[4] / hl, o[5] / hl, o[6] / hl, o[7] / hl, o[2] / hl);
     }
   }
-  if (h[40]) {
-    const long long t0 = h[256];
-    for (int L = 0; L < 3; ++L) {
-      const long long* e = h + 256 + 128 * L;
-      printf("  trace layer %d (cycles since issuer 0 reached layer 2000):\n", 2000 + L);
-      for (int w = 0; w < 2; ++w) {
-        printf("    issuer %d: start %lld  waits done %lld  k-steps issued:", w, e[40 * w] - t0, e[40 * w + 1] - t0);
-        for (int j = 0; j < 13; ++j) if (e[40 * w + 2 + j]) printf(" %lld", e[40 * w + 2 + j] - t0);
+  if (h[700]) {
+    printf("  %lld waits timed out (tag: 1 operand, 3 full [+10: issuer 1]; 20 narrow acc, 22+p acc part p; 30 empty):\n", h[700]);
+    for (int i = 0; i < 96 && i < h[700]; ++i)
+      printf("    tag %lld warp %lld layer/id %lld\n", h[704 + i] >> 40, (h[704 + i] >> 32) & 255, h[704 + i] & 0xffffffffLL);
+  }
+  if (h[256 + 64]) {
+    const long long t0 = h[520 + 3 * 5];   // sub 3 passes the acc wait of the first traced layer
+    for (int L = 0; L < 4; ++L) {
+      printf("  trace layer +%d (cycles since sub 3 saw layer +0 complete)\n", L);
+      for (int w = 0; w < 3; ++w) {
+        printf("    issuer %d block available:", w);
+        for (int j = 0; j < 13; ++j) if (h[256 + L * 64 + w * 16 + j]) printf(" %lld", h[256 + L * 64 + w * 16 + j] - t0);
         printf("\n");
       }
       for (int sb = 0; sb < 4; ++sb) {
-        const long long* q = e + 80 + 12 * sb;
-        printf("    sub %d: acc0 %lld | ld %lld pub %lld | ld %lld pub %lld || acc1 %lld | ld %lld pub %lld | ld %lld pub %lld\n", sb, q[0] - t0,
-               q[1] ? q[1] - t0 : 0, q[2] ? q[2] - t0 : 0, q[3] ? q[3] - t0 : 0, q[4] ? q[4] - t0 : 0, q[6] ? q[6] - t0 : 0,
-               q[7] ? q[7] - t0 : 0, q[8] ? q[8] - t0 : 0, q[9] ? q[9] - t0 : 0, q[10] ? q[10] - t0 : 0);
+        const long long* e = h + 520 + L * 20 + sb * 5;
+        printf("    sub %d: acc seen %lld | blocks stored:", sb, e[0] ? e[0] - t0 : 0);
+        for (int i = 1; i < 5; ++i) if (e[i]) printf(" %lld", e[i] - t0);
+        printf("\n");
       }
     }
   }
   if (h[700]) {
-    printf("  %lld waits timed out (tag: 1/2 drained0/1, 3 full, 4 act [+10: issuer 1]; 20-23 acc, 24 rel):\n", h[700]);
-    for (int i = 0; i < 96 && i < h[700]; ++i)
-      printf("    tag %lld warp %lld layer/id %lld\n", h[704 + i] >> 40, (h[704 + i] >> 32) & 255, h[704 + i] & 0xffffffffLL);
+    printf("  last positions (warp: layer code; epilogue: 1 waiting acc, 2 acc passed, 16+nk boundary arrive, 32+j block j stored; issuer: 64+k waiting block k):\n   ");
+    for (int w = 0; w < 20; ++w) printf(" w%d: %lld/%lld", w, h[840 + w] >> 8, h[840 + w] & 255);
+    printf("\n");
   }
   uint32_t ovf = 0;
   cudaMemcpy(&ovf, S.d_ovf, 4, cudaMemcpyDeviceToHost);
