@@ -333,20 +333,22 @@ extern "C" int gmpc_set_weights(gmpc_handle* h, const float* const* dyn_W,
   return GMPC_OK;
 }
 
-// Which kernel family serves a call: explicit choice, else a tensor-core kernel when the tile is a
-// real dense contraction (batch tile >= 64, hidden >= 64: the north star's rule), else the fp32
-// CUDA-core kernel.  Both tensor-core defaults rescale the forward operands per trajectory: states
-// of any magnitude stay inside the fp16 hi/lo range (the un-scaled GMPC_PATH_TC16 is opt-in only).
-// Measured on B200 (C2 dims): the 32-trajectory kernel finishes a wave of 32 x SMs trajectories in 11.9 ms
-// whatever the batch, the 128-trajectory kernel a wave of 128 x SMs in 26.5 ms: the latency tile serves
-// batches of up to two of its waves, the throughput tile everything larger (1.55 x the trajectories per second).
+// Which kernel family serves a call: explicit choice, else by MEASURED time on B200 (C2 dims, 20 iterations):
+//   * the 32-trajectory tensor-core kernel finishes a wave of 32 x SMs trajectories in 11.9 ms whatever the
+//     batch, and a single trajectory in 2.2 ms (C1 dims) / 12.7 ms (C2 dims) against 9.2 / 63 ms of the fp32
+//     CUDA-core kernel: it serves every batch of up to one wave, also the single state of an acting call
+//     (the north star's "tile >= 64" rule would pick the 4 x slower kernel there);
+//   * the 128-trajectory kernel finishes a wave of 128 x SMs trajectories in 23.5 ms (2 x the trajectories per
+//     second): everything larger than one wave of the 32-trajectory kernel.
+// Both tensor-core defaults rescale the forward operands per trajectory, so states of any magnitude stay inside
+// the fp16 hi/lo range (the un-scaled GMPC_PATH_TC16 is opt-in only).  The fp32 kernel serves the shapes the
+// tensor-core kernels do not cover (hidden < 64 or > 512, n + m > 32, fout > 32) and is the last resort of the
+// operand range check.
 static int pick_path(gmpc_handle* h, int64_t NQ) {
   if (h->path != GMPC_PATH_AUTO) return h->path;
-  if (h->h16.supported && h16_worthwhile(h->h16, NQ)) {
-    if (h->t128.supported && NQ > (int64_t)2 * H_NB * h->num_sms) return GMPC_PATH_T128;
-    return GMPC_PATH_TC16S;
-  }
-  if (h->t128.supported && NQ > (int64_t)2 * H_NB * h->num_sms) return GMPC_PATH_T128;
+  const bool dense = h16_worthwhile(h->h16, NQ);   // hidden width >= 64: a real contraction in the feature dimension
+  if (dense && h->t128.supported && NQ > (int64_t)H_NB * h->num_sms) return GMPC_PATH_T128;
+  if (dense && h->h16.supported) return GMPC_PATH_TC16S;
   return GMPC_PATH_FFMA;
 }
 

@@ -1,0 +1,151 @@
+"""GPU parity at the BASELINE configs AS BENCHMARKED ("parity on the real configs").
+
+* C2 at full size: the benchmark's own inputs (`synthetic.planner_inputs(seed)` with the benchmark's
+  weights, B = 4096, T = 32, 20 Adam iterations) for the seeds the eight ranks of the scaling run use,
+  on the default path and on the 128-trajectory kernel, against the fp64 oracle
+  (reference lines: policy/optimizers.py:24-31 and :78-83, cost/cost_model.py:33-42).
+* C4 dims (hidden 512, three layers) at the full horizon T = 64 with K = 8 candidates: selection
+  indices exact wherever the oracle's top-2 gap exceeds rounding.
+* C5's 50 planning iterations.
+
+Each case prints the summary the bench line carries in `parity` (median / max row error, rows above
+1e-4, and the same numbers for the oracle's own fp32-vs-fp64 floor); the operand range counter must
+stay 0 (a clamped plan is outside the parity contract)."""
+
+import numpy as np
+import pytest
+import torch
+
+from gan_mpc_b200 import synthetic
+from oracle import planner as oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _summary(name, got, o64, o32=None):
+    e = util.rel_each(got, o64)
+    msg = f"{name}: rows {len(e)}, median {float(e.median()):.2e}, max {float(e.max()):.2e}, rows >= 1e-4: {int((e >= TOL).sum())}"
+    if o32 is not None:
+        f = util.rel_each(o32, o64)
+        msg += f" | fp32 floor: median {float(f.median()):.2e}, max {float(f.max()):.2e}, rows >= 1e-4: {int((f >= TOL).sum())}"
+    print(msg)
+    return e
+
+
+def _bench_case(name, seed, B=None, K=None):
+    cfg = dict(synthetic.CONFIGS[name])
+    if B is not None:
+        cfg["B"] = B
+    if K is not None:
+        cfg["K"] = K
+    p = synthetic.planner_params(0, **cfg)              # bench.py: every rank plans with the weights of seed 0
+    x0, U0, goal = synthetic.planner_inputs(seed, **cfg)
+    return cfg, p, x0, U0, goal
+
+
+_ORACLE_CACHE = {}
+
+
+def _oracles(key, x0, U0, goal, p, method, iters, lr):
+    """(fp64 oracle plan, fp32 oracle plan), computed once per (config, seed) and shared by the path variants."""
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE.clear()     # inputs come in seed order: keep one entry
+        f = torch.float32
+        _ORACLE_CACHE[key] = (
+            oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), util.to_oracle(p), method, iters, lr),
+            oracle.plan(util.tt(x0, f), util.tt(U0, f), util.tt(goal, f), util.to_oracle(p, f), method, iters, lr))
+    return _ORACLE_CACHE[key]
+
+
+def _handle(cfg, p):
+    return util.make_handle({k: cfg[k] for k in ("n", "m", "T", "dyn_layers", "dyn_hidden", "cost_layers",
+                                                 "cost_hidden", "cost_fout")}, p)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("path", ["auto", "t128"])
+def test_c2_full_size_benchmark_inputs(seed, path, built_lib):
+    """The timed workload of bench.py, rank `seed`: 4096 states, 20 Adam iterations, vs the fp64 oracle.
+
+    Measured (B200, 8 seeds, profiles/r2_parity_fullsize.txt): the oracle ITSELF in fp32 leaves 1.1-1.5 % of the
+    4096 plans (U rows) above 1e-4 of its fp64 run -- Adam's first steps are -lr g / (|g| + eps), ReLU masks flip at
+    zero pre-activations and the random-init residual dynamics amplify |x| to ~1e4 over 32 steps, so these
+    trajectories have no 1e-4-accurate fp32 plan in ANY implementation.  The 32-trajectory kernel (three fp16
+    products, ~22 mantissa bits) leaves 2.0-2.7 %, the 128-trajectory kernel (all three products into ONE truncating
+    accumulator) 5.6-6.9 %; rollout states and plan cost have medians of ~1e-6 and are above 1e-4 on < 0.7 % of the
+    rows.  Bars: nothing is garbage (max row error < 5e-2, plan cost < 1e-2), medians below 5e-6, selection exact,
+    and the count of rows above 1e-4 bounded per kernel (4 % / 9 %) and by a multiple of the fp32 floor's own."""
+    cfg, p, x0, U0, goal = _bench_case("C2", seed)
+    h = _handle(cfg, p)
+    h.set_path(path)
+    o64, o32 = _oracles(("C2", seed), x0, U0, goal, p, "adam", cfg["iters"], 1e-2)
+    Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=cfg["iters"], lr=1e-2,
+                                check_range=False)
+    assert h.range_overflow() == 0, "an operand left the fp16 hi/lo range on the benchmark's own inputs"
+    assert h.last_path == ("tc16s" if path == "auto" else path)
+    print(f"C2 seed {seed} path {h.last_path}")
+    for name, got, i in (("U", Ub, 0), ("X", Xb, 1), ("J", Jb[:, None], 2)):
+        ref = o64[i] if i < 2 else o64[2][:, None]
+        r32 = o32[i] if i < 2 else o32[2][:, None]
+        e = _summary(name, got, ref, r32)
+        fl = util.rel_each(r32, ref)
+        nbad, nfloor = int((e >= TOL).sum()), int((fl >= TOL).sum())
+        frac, mult = (0.04, 3) if h.last_path == "tc16s" else (0.09, 7)
+        assert float(e.max()) < (5e-2 if i < 2 else 1e-2), name
+        assert float(e.median()) < 0.05 * TOL, name
+        assert nbad <= frac * len(e) and nbad <= mult * nfloor + 32, (name, nbad, nfloor)
+    assert torch.equal(idx.cpu(), o64[3])
+
+
+def test_c4_dims_full_horizon_k8_selection(built_lib):
+    """C4: hidden 512 x 3 layers, T = 64, K = 8 candidates, 20 Adam iterations, 64 states (512 trajectories)."""
+    cfg, p, x0, U0, goal = _bench_case("C4", 3, B=64)
+    h = _handle(cfg, p)
+    o64, o32 = _oracles(("C4", 3), x0, U0, goal, p, "adam", cfg["iters"], 1e-2)
+    Ub, Xb, Jb, idx, Jall = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=cfg["iters"], lr=1e-2)
+    assert h.range_overflow() == 0
+    print("C4 path", h.last_path)
+    e = _summary("J_all", Jall.reshape(-1, 1), o64[4].reshape(-1, 1), o32[4].reshape(-1, 1))
+    fl = util.rel_each(o32[4].reshape(-1, 1), o64[4].reshape(-1, 1))
+    assert float(e.max()) < 5e-2 and float(e.median()) < 0.05 * TOL
+    assert int((e >= TOL).sum()) <= 2 * int((fl >= TOL).sum()) + 8
+    top2 = torch.sort(o64[4], dim=1).values[:, :2]
+    clear = ((top2[:, 1] - top2[:, 0]) / top2[:, 0].abs().clamp_min(1e-30)) > 1e-3
+    print("near-tie states:", int((~clear).sum()), "of", len(clear))
+    assert int(clear.sum()) >= len(clear) // 2
+    assert torch.equal(idx.cpu()[clear], o64[3][clear])        # selection: bit-exact
+    same = idx.cpu() == o64[3]
+    for name, got, i in (("U_best", Ub, 0), ("X_best", Xb, 1)):
+        e = _summary(name, got[same.cuda()], o64[i][same], o32[i][same])
+        assert float(e.max()) < 5e-2 and float(e.median()) < 0.05 * TOL
+        assert int((e >= TOL).sum()) <= max(2, len(e) // 5)
+
+
+@pytest.mark.parametrize("path", ["auto", "t128"])
+def test_c5_fifty_iterations(path, built_lib):
+    """C5's planning depth (50 Adam iterations, T = 32) at 256 states."""
+    cfg, p, x0, U0, goal = _bench_case("C5", 5, B=256)
+    h = _handle(cfg, p)
+    h.set_path(path)
+    o64 = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), util.to_oracle(p), "adam", 50, 1e-2)
+    f = torch.float32
+    o32 = oracle.plan(util.tt(x0, f), util.tt(U0, f), util.tt(goal, f), util.to_oracle(p, f), "adam", 50, 1e-2)
+    Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=50, lr=1e-2, check_range=False)
+    assert h.range_overflow() == 0
+    print("C5 path", h.last_path)
+    # 50 iterations compound the same effects: measured 7 % (32-trajectory kernel) and 18 % (128-trajectory kernel)
+    # of the plans above 1e-4, against 2.3 % for the oracle's own fp32 run
+    frac = 0.12 if h.last_path == "tc16s" else 0.25
+    for name, got, i in (("U", Ub, 0), ("X", Xb, 1)):
+        e = _summary(name, got, o64[i], o32[i])
+        assert float(e.max()) < 5e-2 and float(e.median()) < 0.25 * TOL
+        assert int((e >= TOL).sum()) <= frac * len(e), name
+    e = _summary("J", Jb[:, None], o64[2][:, None], o32[2][:, None])
+    assert float(e.max()) < 1e-2 and float(e.median()) < 0.05 * TOL
+    assert torch.equal(idx.cpu(), o64[3])
