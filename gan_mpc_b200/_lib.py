@@ -70,6 +70,10 @@ _SIGS = {
     "gmpc_dynamics_fit": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, _f, C.c_float, C.c_int32, _f,
                                     C.POINTER(_f), C.POINTER(_f), C.c_void_p]),
     "gmpc_dynamics_fit_columns": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int32]),
+    "gmpc_gemm_nt": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, _f, _f, C.c_float, C.c_int32, _f, _f,
+                               C.c_void_p]),
+    "gmpc_cost_mixed_vjp": (C.c_int, [C.c_void_p, C.c_int64, _f, _f, C.c_float, C.POINTER(_f), C.POINTER(_f),
+                                      C.c_void_p]),
     "gmpc_expert_propose": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, _f, _f, C.c_int32, C.c_int32,
                                       C.c_int32, _f, _f, C.c_void_p]),
     "gmpc_expert_param_count": (C.c_int64, [C.c_int32] * 5),
@@ -421,6 +425,31 @@ class Handle:
             _ptr(next_xseq, device=dev, name="next_xseq"), float(discount_factor), int(bool(teacher_forcing)),
             _ptr(loss), pa, pc, _stream(dev)))
         return loss, act, cot
+
+    def gemm_nt(self, A, B, alpha=1.0, want_rowsum=False):
+        """gmpc_gemm_nt: A [M,R], B [N,R] -> (alpha A B^T [M,N], alpha rowsum(B) [N] or None)."""
+        dev = self.device
+        M, R = A.shape
+        N = B.shape[0]
+        Cm = torch.empty(M, N, device=dev, dtype=torch.float32)
+        rs = torch.empty(N, device=dev, dtype=torch.float32) if want_rowsum else None
+        _check(self.lib.gmpc_gemm_nt(self._h, M, N, R, _ptr(A, device=dev, name="A"), _ptr(B, device=dev, name="B"),
+                                     float(alpha), 0, _ptr(Cm), _ptr(rs), _stream(dev)))
+        return Cm, rs
+
+    def cost_mixed_vjp(self, xT, dxT, scale, dims):
+        """gmpc_cost_mixed_vjp: x_T [B,n], dx_T [B,n] -> (gW [L x [in_l,out_l]], gb [L x [out_l]]), batch-reduced and
+        multiplied by `scale`; dims = the cost MLP's layer widths [n, H, ..., fout]."""
+        dev = self.device
+        B, L = xT.shape[0], len(dims) - 1
+        gW = [torch.empty(dims[l], dims[l + 1], device=dev, dtype=torch.float32) for l in range(L)]
+        gb = [torch.empty(dims[l + 1], device=dev, dtype=torch.float32) for l in range(L)]
+        pW, pb = (_f * L)(), (_f * L)()
+        for l in range(L):
+            pW[l], pb[l] = gW[l].data_ptr(), gb[l].data_ptr()
+        _check(self.lib.gmpc_cost_mixed_vjp(self._h, B, _ptr(xT, device=dev, name="xT"), _ptr(dxT, device=dev, name="dxT"),
+                                            float(scale), pW, pb, _stream(dev)))
+        return gW, gb
 
     def expert_propose(self, history_x, params_flat, lstm_features, num_layers, num_hidden_units):
         """gmpc_expert_propose: history_x [B,hist+1,n] -> (goal_xseq [B,T+1,n], init_useq [B,T,m])."""

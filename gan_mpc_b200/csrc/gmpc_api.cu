@@ -20,6 +20,7 @@
 #include "dynfit.cuh"
 #include "plan_h16.cuh"
 #include "plan_t128.cuh"
+#include "smallgemm.cuh"
 
 using namespace gmpc;
 
@@ -94,6 +95,8 @@ struct gmpc_handle {
   bool fit_attr = false;
   float* d_ilqr_ws = nullptr;
   size_t ilqr_ws_bytes = 0;
+  void* d_vjp_ws = nullptr;          // activations / tangents / masks / cotangents of gmpc_cost_mixed_vjp
+  size_t vjp_ws_bytes = 0;
   long long* d_ilqr_stats = nullptr;
 };
 
@@ -274,7 +277,8 @@ extern "C" int gmpc_destroy(gmpc_handle* h) {
   cudaFree(h->ws_X); cudaFree(h->ws_G); cudaFree(h->ws_U); cudaFree(h->ws_M); cudaFree(h->ws_V);
   cudaFree(h->ws_mask); cudaFree(h->d_scratch); cudaFree(h->d_stage);
   cudaFree(h->d_partial); cudaFree(h->d_losses); cudaFree(h->d_fuse);
-  cudaFree(h->d_ilqr_ws); cudaFree(h->d_ilqr_stats); cudaFree(h->d_fit_masks);
+  cudaFree(h->d_ilqr_ws);
+  cudaFree(h->d_vjp_ws); cudaFree(h->d_ilqr_stats); cudaFree(h->d_fit_masks);
   delete h;
   return GMPC_OK;
 }
@@ -764,6 +768,132 @@ extern "C" int gmpc_plan_host(gmpc_handle* h, int64_t B, int32_t K, const float*
       h->in_retry = false;
       h->path = GMPC_PATH_AUTO;
       return rc;
+    }
+  }
+  return GMPC_OK;
+}
+
+// ----------------------------------------------------------------------------------- small contractions
+// C[M,N] = alpha A B^T (+ C), A[M,R], B[N,R] row-major; rowsum_B[N] = alpha sum_r B[n,r] (nullable): the weight and
+// bias gradients of the dynamics fit from gmpc_dynamics_fit's factors (norm/dynamics_trainer.py:64-79).
+extern "C" int gmpc_gemm_nt(gmpc_handle* h, int32_t M, int32_t N, int64_t R, const float* A, const float* B, float alpha,
+                            int32_t accumulate, float* C, float* rowsum_B, void* stream) {
+  if (!h) return fail(GMPC_E_ARG, "gmpc_gemm_nt: null handle");
+  if (M < 0 || N < 0 || R < 0 || !A || !B || !C) return fail(GMPC_E_ARG, "gmpc_gemm_nt: bad argument");
+  if (M == 0 || N == 0) return GMPC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  SGemm G;
+  memset(&G, 0, sizeof(G));
+  G.A = A; G.sam = R; G.sar = 1;
+  G.B = B; G.sbr = 1; G.sbn = R;
+  G.C = C; G.ldc = N; G.M = M; G.N = N; G.R = R; G.alpha = alpha; G.accumulate = accumulate;
+  CU_CHECK(small_gemm(G, SG_EPI_NONE, st));
+  ++h->launches;
+  if (rowsum_B) {
+    strided_sum_kernel<<<(N + 7) / 8, 256, 0, st>>>(B, R, 1, N, R, alpha, rowsum_B);
+    CU_CHECK(cudaGetLastError());
+    ++h->launches;
+  }
+  return GMPC_OK;
+}
+
+// The cost-MLP part of cost_vjp (policy/optimizers.py:93-105), reduced over the batch:
+//   gW[l], gb[l] = scale * sum_b grad_theta [ w2 d/de |f(x_T[b] + e dx_T[b]; theta)|^2 ],  w2 = sigmoid(mpc_weights[2]),
+// f = the staged cost MLP (cost/nn.py:23-29).  phi = 2 f(x) . (Jf dx): the cotangent 2 w2 (Jf dx) goes back through
+// the primal network (activations a_l), the cotangent 2 w2 f(x) through the tangent network (da_l, linear, no bias):
+//   gW_l = a_l^T c_l + da_l^T d_l,  gb_l = colsum(c_l).   gW[l] is [in_l, out_l] (flax kernel layout).
+extern "C" int gmpc_cost_mixed_vjp(gmpc_handle* h, int64_t B, const float* xT, const float* dxT, float scale,
+                                   float* const* gW, float* const* gb, void* stream) {
+  int rc = check_ready(h, "gmpc_cost_mixed_vjp", B);
+  if (rc) return rc;
+  if (!gW || !gb || (B > 0 && (!xT || !dxT))) return fail(GMPC_E_ARG, "gmpc_cost_mixed_vjp: null argument");
+  if (B > (int64_t)1 << 24) return fail(GMPC_E_ARG, "gmpc_cost_mixed_vjp: batch too large");
+  const MlpPack& mp = h->cost;
+  const int L = mp.L;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {
+    for (int l = 0; l < L; ++l) {
+      CU_CHECK(cudaMemsetAsync(gW[l], 0, sizeof(float) * mp.dims[l] * mp.dims[l + 1], st));
+      CU_CHECK(cudaMemsetAsync(gb[l], 0, sizeof(float) * mp.dims[l + 1], st));
+    }
+    return GMPC_OK;
+  }
+  int dmax = 0;
+  size_t hid = 0;
+  for (int l = 0; l <= L; ++l) dmax = std::max(dmax, mp.dims[l]);
+  for (int l = 1; l < L; ++l) hid += mp.dims[l];
+  // workspace: a_l, da_l, mask_l for the hidden layers; y, dy; two pairs of cotangent buffers
+  const size_t need = sizeof(float) * (size_t)B * (3 * hid + 2 * (size_t)mp.dims[L] + 4 * (size_t)dmax);
+  rc = grow(&h->d_vjp_ws, &h->vjp_ws_bytes, need);
+  if (rc) return rc;
+  float* w = (float*)h->d_vjp_ws;
+  const float* a[MAXL + 1];
+  const float* da[MAXL + 1];
+  float* mk[MAXL + 1];
+  a[0] = xT; da[0] = dxT; mk[0] = nullptr;
+  for (int l = 1; l < L; ++l) {
+    float* al = w; w += (size_t)B * mp.dims[l];
+    float* dl = w; w += (size_t)B * mp.dims[l];
+    mk[l] = w; w += (size_t)B * mp.dims[l];
+    SGemm G;
+    memset(&G, 0, sizeof(G));
+    G.A = a[l - 1]; G.sam = mp.dims[l - 1]; G.sar = 1;
+    G.B = mp.Wf[l - 1]; G.sbr = mp.ldf[l - 1]; G.sbn = 1;
+    G.C = al; G.ldc = mp.dims[l]; G.M = (int)B; G.N = mp.dims[l]; G.R = mp.dims[l - 1]; G.alpha = 1.f;
+    G.bias = mp.bias[l - 1]; G.mask = mk[l];
+    CU_CHECK(small_gemm(G, SG_EPI_BIAS_RELU_MASK, st));
+    G.A = da[l - 1]; G.C = dl; G.bias = nullptr;
+    CU_CHECK(small_gemm(G, SG_EPI_MASK, st));
+    a[l] = al; da[l] = dl;
+    h->launches += 2;
+  }
+  float* y = w; w += (size_t)B * mp.dims[L];
+  float* dy = w; w += (size_t)B * mp.dims[L];
+  float* cbuf[2] = {w, w + (size_t)B * dmax};
+  float* dbuf[2] = {w + 2 * (size_t)B * dmax, w + 3 * (size_t)B * dmax};
+  {
+    SGemm G;
+    memset(&G, 0, sizeof(G));
+    G.A = a[L - 1]; G.sam = mp.dims[L - 1]; G.sar = 1;
+    G.B = mp.Wf[L - 1]; G.sbr = mp.ldf[L - 1]; G.sbn = 1;
+    G.C = y; G.ldc = mp.dims[L]; G.M = (int)B; G.N = mp.dims[L]; G.R = mp.dims[L - 1]; G.alpha = 1.f;
+    G.bias = mp.bias[L - 1];
+    CU_CHECK(small_gemm(G, SG_EPI_BIAS, st));
+    G.A = da[L - 1]; G.C = dy; G.bias = nullptr;
+    CU_CHECK(small_gemm(G, SG_EPI_NONE, st));
+    const long long cnt = (long long)B * mp.dims[L];
+    mixed_vjp_seed_kernel<<<(int)std::min<long long>((cnt + 255) / 256, 1024), 256, 0, st>>>(y, dy, h->d_mpcw, scale, cnt,
+                                                                                              cbuf[0], dbuf[0]);
+    CU_CHECK(cudaGetLastError());
+    h->launches += 3;
+  }
+  int cur = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const int Ki = mp.dims[l], No = mp.dims[l + 1];
+    SGemm G;
+    memset(&G, 0, sizeof(G));
+    // gW_l [Ki, No] = a_l^T c + da_l^T d   (reduction over the batch)
+    G.A = a[l]; G.sam = 1; G.sar = Ki;
+    G.B = cbuf[cur]; G.sbr = No; G.sbn = 1;
+    G.C = gW[l]; G.ldc = No; G.M = Ki; G.N = No; G.R = B; G.alpha = 1.f;
+    CU_CHECK(small_gemm(G, SG_EPI_NONE, st));
+    G.A = da[l]; G.B = dbuf[cur]; G.accumulate = 1;
+    CU_CHECK(small_gemm(G, SG_EPI_NONE, st));
+    strided_sum_kernel<<<(No + 7) / 8, 256, 0, st>>>(cbuf[cur], 1, No, No, B, 1.f, gb[l]);
+    CU_CHECK(cudaGetLastError());
+    h->launches += 3;
+    if (l > 0) {
+      // c' = (c W_l^T) * mask_l, the same for d: W_l^T(r = output, n = input) = Wb[l][r * ldb + n]
+      memset(&G, 0, sizeof(G));
+      G.A = cbuf[cur]; G.sam = No; G.sar = 1;
+      G.B = mp.Wb[l]; G.sbr = mp.ldb[l]; G.sbn = 1;
+      G.C = cbuf[cur ^ 1]; G.ldc = Ki; G.M = (int)B; G.N = Ki; G.R = No; G.alpha = 1.f;
+      G.mask = mk[l];
+      CU_CHECK(small_gemm(G, SG_EPI_MASK, st));
+      G.A = dbuf[cur]; G.C = dbuf[cur ^ 1];
+      CU_CHECK(small_gemm(G, SG_EPI_MASK, st));
+      h->launches += 2;
+      cur ^= 1;
     }
   }
   return GMPC_OK;

@@ -2,8 +2,8 @@
 
 predict_loss / train_per_update / train_params run on libgmpc: the rollout over the window, the
 discounted loss and the back-propagation through time are gmpc_dynamics_fit (csrc/dynfit.cuh); the
-contraction that is left for the weight gradient, dW_l = act_l cot_l^T, is one plain GEMM per layer
-(cuBLAS through torch.matmul); the update is optax chain(clip_by_global_norm(100), adam) on the
+contraction that is left for the weight gradient, dW_l = act_l cot_l^T (and the bias gradient, the row sums of
+cot_l), is gmpc_gemm_nt (csrc/smallgemm.cuh); the update is optax chain(clip_by_global_norm(100), adam) on the
 leaves labelled "tx" through gmpc_clip_adam_step.  `train` (:123-194) interleaves simulator
 episodes (dm_control) with train_params and is outside the B200 hot path."""
 
@@ -38,10 +38,12 @@ def loss_and_grad(policy, params, batch_x, batch_u, batch_y, discount_factor, te
     from gan_mpc_b200.policy import bilevel
     _, (loss, act, cot) = _fit(policy, params, batch_x, batch_u, batch_y, discount_factor, teacher_forcing)
     B = loss.shape[0]
+    h = policy._handle(batch_x.shape[-1], batch_u.shape[-1])
     grads = bilevel.zeros_like_tree(params)
     dp = grads["dynamics_params"]["params"]
     for l in range(len(act)):
-        dp[f"Dense_{l}"] = {"kernel": (act[l] @ cot[l].t()) / B, "bias": cot[l].sum(1) / B}
+        dW, db = h.gemm_nt(act[l], cot[l], alpha=1.0 / B, want_rowsum=True)
+        dp[f"Dense_{l}"] = {"kernel": dW, "bias": db}
     return loss.mean(), grads
 
 

@@ -69,7 +69,8 @@ class BaseMPC(eval.EvalMPC):
             _, out = self._bilevel(hx[..., -1, :], init_u, params, goal, by)
             self.last_bilevel = out
             loss_sum = out["loss"].sum()
-            grads = bilevel.high_level_grad_tree(params, out, reduce_mean="sum")
+            grads = bilevel.high_level_grad_tree(params, out, reduce_mean="sum",
+                                                 handle=self._handle(hx.shape[-1], init_u.shape[-1]))
         else:  # more ranks than samples: this rank contributes zeros
             loss_sum = torch.zeros((), device=self.device)
             grads = bilevel.zeros_like_tree(params)

@@ -59,15 +59,24 @@ def zeros_like_tree(tree, lead=()):
     return tree
 
 
-def high_level_grad_tree(params, out, reduce_mean):
+def high_level_grad_tree(params, out, reduce_mean, handle=None):
     """params-shaped pytree of d (H . grad_U J) / d params from one gmpc_bilevel_l2 result `out`
     (policy/optimizers.py:69-71).  reduce_mean: True = leaf-wise batch mean (policy/base.py:126-127),
     "sum" = batch sum (data-parallel callers divide by the global batch after the all-reduce), False =
-    every leaf keeps a leading batch axis (what vmap of bilevel_optimization returns)."""
+    every leaf keeps a leading batch axis (what vmap of bilevel_optimization returns).
+    With `handle` (a _lib.Handle whose staged weights are `params`) the batch-reduced cost-MLP part runs in
+    libgmpc (gmpc_cost_mixed_vjp): the trainers' path.  The per-sample variant (reduce_mean False, the
+    functional API of policy/optimizers.py) stays on the torch formulation above."""
     B = out["X"].shape[0]
     w2 = torch.sigmoid(params["mpc_weights"][2])
     mode = None if not reduce_mean else ("sum" if reduce_mean == "sum" else "mean")
-    gW, gb = cost_mlp_mixed_vjp(params["cost_params"], w2, out["X"][:, -1].contiguous(), out["dxT"], mode)
+    xT = out["X"][:, -1].contiguous()
+    if handle is not None and mode is not None:
+        Ws, _ = dense_stack_lists(params["cost_params"])
+        dims = [Ws[0].shape[0]] + [W.shape[1] for W in Ws]
+        gW, gb = handle.cost_mixed_vjp(xT, out["dxT"].contiguous(), 1.0 if mode == "sum" else 1.0 / B, dims)
+    else:
+        gW, gb = cost_mlp_mixed_vjp(params["cost_params"], w2, xT, out["dxT"], mode)
     red = ((lambda t: t.sum(0)) if reduce_mean == "sum" else (lambda t: t.mean(0))) if reduce_mean else (lambda t: t)
     lead = () if reduce_mean else (B,)
     tree = {k: zeros_like_tree(v, lead) for k, v in params.items()}

@@ -236,6 +236,21 @@ int gmpc_dynamics_fit(gmpc_handle* h, int64_t B, int32_t S, const float* xseq, c
                       float* loss, float* const* act, float* const* cot, void* stream);
 int64_t gmpc_dynamics_fit_columns(const gmpc_handle* h, int64_t B, int32_t S);
 
+/* The contraction gmpc_dynamics_fit leaves:  C[M,N] = alpha A B^T (+ C when accumulate != 0),  A[M,R], B[N,R] row-major,
+ * and optionally  rowsum_B[N] = alpha sum_r B[n,r]  (nullable).  With A = act[l], B = cot[l], alpha = 1/B this is
+ * value_and_grad of the batch-mean predict_loss w.r.t. Dense_l's kernel [in,out] and bias
+ * (norm/dynamics_trainer.py:64-79).  Deterministic (no split over the reduction). */
+int gmpc_gemm_nt(gmpc_handle* h, int32_t M, int32_t N, int64_t R, const float* A, const float* B, float alpha,
+                 int32_t accumulate, float* C, float* rowsum_B, void* stream);
+
+/* The cost-MLP part of cost_vjp (policy/optimizers.py:93-105, the last factor of bilevel_optimization :69-71),
+ * reduced over the batch:  gW[l] [in_l,out_l], gb[l] [out_l]  =  scale * sum_b grad_theta of
+ *   sigmoid(mpc_weights[2]) * d/de |f(x_T[b] + e dx_T[b]; theta)|^2 ,   f = the staged cost MLP (cost/nn.py:23-29),
+ * x_T[B,n] the terminal states of the plans, dx_T[B,n] their tangents along H (gmpc_bilevel_l2 / _tail outputs).
+ * scale = 1/B gives policy/base.py:126-127's batch mean, scale = 1 the sum a data-parallel caller all-reduces. */
+int gmpc_cost_mixed_vjp(gmpc_handle* h, int64_t B, const float* xT, const float* dxT, float scale,
+                        float* const* gW, float* const* gb, void* stream);
+
 /* The expert proposal network in front of the planner: EvalMPC.get_goal_states_init_actions
  * (policy/eval.py:87-107, policy/base.py:40-61) = ExpertModel.get_history_carry (LSTM carry warmed up
  * on the history rows with teacher forcing, expert/expert_model.py:60-71) followed by
