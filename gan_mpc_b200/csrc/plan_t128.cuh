@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
   uint64_t* rc_bar = rnd_bar + T_MAXKS;          // sub 1 has read the u columns of the narrow accumulator (4 warp arrivals)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(rc_bar + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // (a shuffle from lane 0 is provably warp-uniform: the role branches below are then convergent for the compiler,
+  // which lets the MMA issuer keep its loop state and descriptors in uniform registers)
+  const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
   const int n = P.n, m = P.m, T = P.T, NS = P.nslot;
   const int my_tiles = ((int)blockIdx.x < P.ntiles) ? (P.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -286,7 +289,9 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
     // issuer observes every phase of every block barrier, also in layers in which it issues nothing (a waiter
     // that only flipped its parity bit could run two phases ahead and pass a parity wait on a stale phase).
     const int which = warp - T_EPI_WARPS - 1;
-    if (elect_one()) {
+    // The whole warp walks the schedule (converged); one elected lane issues the MMAs and the commits.
+    const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
+    {
       const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), ring_a = smem_u32(tsm + L.ring);
       const uint32_t acc_a = smem_u32(acc_bar), rnd_a = smem_u32(rnd_bar), rc_a = smem_u32(rc_bar);
       const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 0, 128) >> 32);
@@ -312,8 +317,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
 #ifdef GMPC_T128_TIMED
             il_t0 = clock64();
 #endif
-            const uint32_t a_t = tmem_base + t_region(cur);
-            const uint32_t d_t = tmem_base + (narrow ? T_RC : t_region(cur ^ 1u));
+            const uint32_t a_t = tmem_u + t_region(cur);
+            const uint32_t d_t = tmem_u + (narrow ? T_RC : t_region(cur ^ 1u));
             cur ^= 1u;
             const bool mine = which < Y.np;
             // the u columns of the previous adjoint boundary's narrow accumulator have been read (sub 1)
@@ -357,14 +362,16 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
               if (mine) {
                 const uint64_t bh = ((uint64_t)desc_hi << 32) | b_lo;
                 const uint64_t bl = ((uint64_t)desc_hi << 32) | (b_lo + tile16);
-                t_mma(d_p, a_t + a_off, bh, idesc, a_off);          // accumulate = (j > 0)
-                t_mma(d_p, a_t + a_off + 8u, bh, idesc, 1u);
-                t_mma(d_p, a_t + a_off, bl, idesc, 1u);
+                if (elect_one()) {
+                  t_mma(d_p, a_t + a_off, bh, idesc, a_off);          // accumulate = (j > 0)
+                  t_mma(d_p, a_t + a_off + 8u, bh, idesc, 1u);
+                  t_mma(d_p, a_t + a_off, bl, idesc, 1u);
+                }
               }
               a_off += 16;
               b_lo += kst16;
               if (--in_group == 0) {
-                if (mine) {
+                if (mine && elect_one()) {
                   umma_commit_a(empty_a + slot * 8);
                   for (int x = 0; x < extra; ++x) umma_commit_a(empty_a + slot * 8);
                 }
@@ -375,7 +382,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
             // Every issuer commits, also with nothing issued: the epilogue passes a layer only after EVERY issuer has
             // walked it, and every epilogue warp arrives on the round barriers of every layer, so no barrier can get
             // two phases ahead of any of its waiters.
-            umma_commit_a(acc_a);
+            if (elect_one()) umma_commit_a(acc_a);
 #ifdef GMPC_T128_TIMED
             if (kind == DIR_DYN_F && l < 4) il_rest[l] += clock64() - il_t0;
 #endif
