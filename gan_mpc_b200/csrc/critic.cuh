@@ -275,7 +275,12 @@ __global__ void critic_reduce_clip_adam_kernel(const float* partial, int nparts,
     blocksq[blockIdx.x] = tot;
     __threadfence();
     atomicAdd(ticket, 1ULL);
-    while (*reinterpret_cast<volatile unsigned long long*>(ticket) < expected) {}
+    // (bounded: a launch of this scan that never ran -- its tickets were handed out on the host -- must surface as an
+    // error, not as a hang)
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned long long*>(ticket) < expected) {
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
     __threadfence();
   }
   __syncthreads();

@@ -1169,9 +1169,13 @@ extern "C" int gmpc_critic_train_scan(gmpc_handle* h, int32_t steps, int64_t Bc,
         h->d_partial, grid, d.P, grad_scratch, h->d_losses, Bc, inv_count, losses + s, params_flat, mom, vel,
         lr, max_norm, b1, b2, eps, bc1, bc2, h->d_fuse + 2, reinterpret_cast<unsigned long long*>(h->d_fuse),
         h->fuse_tickets += (unsigned long long)rb);
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
+      // the tail kernel of this step was not enqueued: take its tickets back, or the next scan would wait for them
+      h->fuse_tickets -= (unsigned long long)rb;
+      return fail(GMPC_E_CUDA, std::string("gmpc_critic_train_scan: launch failed: ") + cudaGetErrorString(e));
+    }
     h->launches += 2;
   }
-  CU_CHECK(cudaGetLastError());
   return GMPC_OK;
 }
 

@@ -343,3 +343,24 @@ def test_auto_retries_with_forward_scaling(built_lib):
                                      method="grad", iters=2, lr=1e-3)
     assert h.last_path == "tc16s"
     assert util.rel_rows(Xb, oX) < TOL and util.rel_rows(Jb[:, None], oJ[:, None]) < TOL
+
+
+@pytest.mark.parametrize("cfg,B,K", [(util.ODD, 27, 3), (util.ODD, 45, 1), (util.SMALL, 129, 1), (util.MID, 300, 1)])
+def test_t128_repeated_launches_never_stall(cfg, B, K, built_lib):
+    """The 128-trajectory kernel's barrier protocol under repetition: narrow hidden layers (ODD: some epilogue warps
+    own no feature block of a layer), more than one tile per CTA, plan / objective / rollout modes back to back.  A
+    protocol slip shows as a trapped wait (launch failure) or as results that change between identical calls."""
+    p, x0, U0, goal = util.case(cfg, 77, B=B, K=K)
+    h = util.make_handle(cfg, p)
+    select_path(h, "t128")
+    ref = None
+    for rep in range(12):
+        Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=3, lr=1e-2)
+        J, dU, X, _ = h.objective_grad(dev(x0), dev(U0[:, 0]), dev(goal))
+        Xr = h.rollout(dev(x0), dev(U0[:, 0]))
+        out = (Ub.clone(), Jb.clone(), dU.clone(), Xr.clone())
+        if ref is None:
+            ref = out
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(out, ref)), f"results changed at repetition {rep}"
+    torch.cuda.synchronize()
