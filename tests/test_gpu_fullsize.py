@@ -149,3 +149,23 @@ def test_c5_fifty_iterations(path, built_lib):
     e = _summary("J", Jb[:, None], o64[2][:, None], o32[2][:, None])
     assert float(e.max()) < 1e-2 and float(e.median()) < 0.05 * TOL
     assert torch.equal(idx.cpu(), o64[3])
+
+
+def test_c3_planner_full_size(built_lib):
+    """C3's planner: 8192 states at the GAN YAML dims (n = 3, m = 1, T = 5), 20 Adam iterations, on the path AUTO picks
+    for that batch (the 128-trajectory kernel)."""
+    cfg, p, x0, U0, goal = _bench_case("C3", 0)
+    h = _handle(cfg, p)
+    o64, o32 = _oracles(("C3", 0), x0, U0, goal, p, "adam", cfg["iters"], 1e-2)
+    Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=cfg["iters"], lr=1e-2, check_range=False)
+    assert h.range_overflow() == 0
+    assert h.last_path == "t128"
+    print("C3 path", h.last_path)
+    for name, got, i in (("U", Ub, 0), ("X", Xb, 1), ("J", Jb[:, None], 2)):
+        ref = o64[i] if i < 2 else o64[2][:, None]
+        r32 = o32[i] if i < 2 else o32[2][:, None]
+        e = _summary(name, got, ref, r32)
+        fl = util.rel_each(r32, ref)
+        assert float(e.max()) < 5e-2 and float(e.median()) < 0.05 * TOL, name
+        assert int((e >= TOL).sum()) <= 0.02 * len(e) + 4 * int((fl >= TOL).sum()), name
+    assert torch.equal(idx.cpu(), o64[3])
