@@ -1357,7 +1357,7 @@ inline int h16_create(H16State& S, const gmpc_config& c, const int* dyn_dims, co
   for (int t = 0; t < 2; ++t)
     for (int f = 0; f < 2; ++f)
       if (cudaFuncSetAttribute(h16_kernel_ptr(t, S.wide, f), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)S.smem_bytes) != cudaSuccess)
+                               (int)prop.sharedMemPerBlockOptin) != cudaSuccess)   // (per kernel, not per handle: the device maximum)
         return GMPC_E_CUDA;
   for (int C = 2; C <= 4; C *= 2) {
     cudaLaunchConfig_t cfg;

@@ -1170,7 +1170,9 @@ inline int t128_create(T128State& S, const gmpc_config& c, const int* dyn_dims, 
   if (cudaMalloc(&S.ws_M, G * su * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
   if (cudaMalloc(&S.ws_V, G * su * sizeof(float)) != cudaSuccess) return GMPC_E_CUDA;
   if (cudaMalloc(&S.ws_mask, G * smk * sizeof(uint32_t)) != cudaSuccess) return GMPC_E_CUDA;
-  if (cudaFuncSetAttribute(plan_t128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_bytes) != cudaSuccess)
+  // (the attribute belongs to the kernel, not to the handle: the device maximum, so that handles of different
+  // shapes can be alive at the same time)
+  if (cudaFuncSetAttribute(plan_t128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin) != cudaSuccess)
     return GMPC_E_CUDA;
   S.supported = true;
   S.why = "";

@@ -364,3 +364,20 @@ def test_t128_repeated_launches_never_stall(cfg, B, K, built_lib):
         else:
             assert all(torch.equal(a, b) for a, b in zip(out, ref)), f"results changed at repetition {rep}"
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("path", ["tc16s", "t128"])
+def test_handles_of_different_shapes_coexist(path, built_lib):
+    """Two live handles with different model shapes (hence different shared-memory footprints of the same kernels),
+    used alternately: the dynamic shared-memory limit belongs to the kernel, not to the handle created last."""
+    cases = []
+    for cfg, seed in ((util.MID, 3), (util.SMALL, 4), (util.ODD, 5)):
+        p, x0, U0, goal = util.case(cfg, seed, B=40, K=1)
+        h = util.make_handle(cfg, p)
+        select_path(h, path)
+        o = oracle.plan(util.tt(x0), util.tt(U0), util.tt(goal), util.to_oracle(p), "adam", 3, 1e-2)
+        cases.append((h, x0, U0, goal, o))
+    for _ in range(2):
+        for h, x0, U0, goal, o in cases:
+            Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=3, lr=1e-2)
+            assert util.rel_rows(Xb, o[1]) < TOL and util.rel_rows(Jb[:, None], o[2][:, None]) < TOL
