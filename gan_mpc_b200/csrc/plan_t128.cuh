@@ -18,17 +18,21 @@
 //                time, into the A operand of layer l+1 (feature block j: hi in columns [16 j, 16 j + 8),
 //                lo in [16 j + 8, 16 j + 16)).  No thread ever touches a column another thread reads.
 //     layer l+1: A operand = region c^1, accumulator = region c (all of layer l's MMAs are complete).
-// Issue: a single thread sustains one MMA per ~80 cycles (descriptor moves to uniform registers), an N = 64
-// MMA takes 32 tensor cycles: the accumulator columns of a layer are therefore split into up to three N-PARTS
-// (four feature blocks each, the last part takes the remainder), one issuer warp per part, all walking the
-// k-steps concurrently.  Pipelining across layers is by K-STEP: feature block j of the next operand belongs to
-// epilogue sub-group j % 4 (4 warps, one per TMEM lane quarter) and has its own mbarrier; the issuers start
-// k-step j of layer l+1 as soon as block j is stored, so the MMAs of layer l+1 run under the epilogue of
-// layer l and only the first block's latency is exposed.
-// Synchronisation: one mbarrier per N-part ("all MMAs of this part of the layer are complete",
-// tcgen05.commit), one per feature block ("stored", 4 warp arrivals), the weight ring's full / empty pairs,
-// and one for the narrow accumulator's second reader.  Write-after-read on the regions needs nothing else:
-// block j's arrival follows its owners' reads, and a layer completes only after every block has arrived.
+// Issue: ONE issuer warp walks the schedule converged, an elected lane issues; the warp-role branches are taken
+// on a shuffled (provably uniform) warp index, so the loop state and the descriptors live in uniform registers
+// and nothing but the three UTCHMMA of a k-step and a handful of uniform adds is executed per k-step.  (The
+// accumulator columns can be split into N-parts with one issuer warp each -- T_ISSUERS -- but one, two and three
+// parts run at the same speed: the k-step pace is set by the epilogue.)
+// Pipelining across layers is by ROUNDS of four feature blocks: block j of the next operand belongs to epilogue
+// sub-group 3 - j % 4 (4 warps, one per TMEM lane quarter; the sub-groups with step-boundary duties own the later
+// blocks), every epilogue warp arrives on the round's mbarrier -- with or without a block in the round -- and the
+// issuer starts k-steps 4 r .. 4 r + 3 of layer l+1 as soon as round r is stored, so the MMAs of layer l+1 run
+// under the epilogue of layer l.
+// Synchronisation: one mbarrier "all MMAs of the layer are complete" (one tcgen05.commit per issuer), one per
+// round (16 warp arrivals), the weight ring's full / empty pairs, and one for the narrow accumulator's second
+// reader.  Because all 16 warps arrive on every round of every layer no barrier can get two phases ahead of any
+// of its waiters, and write-after-read on the regions needs nothing else: a round's arrival follows its owners'
+// reads, and a layer completes only after every round has arrived.
 //
 // Restates the same reference lines as plan_ffma.cuh / plan_h16.cuh (dynamics/nn.py:27-34,
 // cost/nn.py:23-29, cost/cost_model.py:20-42, policy/optimizers.py:24-31 and :78-83; optax adam of
@@ -283,10 +287,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) plan_t128_kernel(const __grid_co
     __syncwarp();
   } else if (warp > T_EPI_WARPS) {
     // ================================================================== MMA issuers (one thread each)
-    // Issuer p issues N-part p of every layer, k-step by k-step as the feature blocks of the operand arrive.
+    // Issuer p issues N-part p of every layer, round by round as the feature blocks of the operand arrive.
     // Accumulator columns of different parts are disjoint, a part's completion is tracked by the commit of the
-    // thread that issued it, so the three instruction streams may interleave freely on the tensor pipe.  Every
-    // issuer observes every phase of every block barrier, also in layers in which it issues nothing (a waiter
+    // lane that issued it, so several instruction streams may interleave freely on the tensor pipe.  Every
+    // issuer observes every phase of every round barrier, also in layers in which it issues nothing (a waiter
     // that only flipped its parity bit could run two phases ahead and pass a parity wait on a stale phase).
     const int which = warp - T_EPI_WARPS - 1;
     // The whole warp walks the schedule (converged); one elected lane issues the MMAs and the commits.
