@@ -32,7 +32,7 @@ class Config(C.Structure):
 class IlqrOptions(C.Structure):
     """gmpc_ilqr_options: the trajax options the reference sets (policy/eval.py:10-20)."""
     _fields_ = [("maxiter", C.c_int32), ("grad_norm_threshold", C.c_float),
-                ("alpha_0", C.c_float), ("alpha_min", C.c_float)]
+                ("alpha_0", C.c_float), ("alpha_min", C.c_float), ("gradient_lag", C.c_int32)]
 
 
 _f = C.c_void_p  # device/host float*
@@ -294,7 +294,7 @@ class Handle:
         return out
 
     def ilqr(self, x0, U0, goal, maxiter=100, grad_norm_threshold=1e-4, alpha_0=1.0,
-             alpha_min=0.00005, want_lqr=False, **unsupported):
+             alpha_min=0.00005, want_lqr=False, gradient_lag=False, **unsupported):
         """trajax iLQR (the reference's ilqr_solve, policy/optimizers.py:10-21), batched:
         x0 [B,n], U0 [B,T,m], goal [B,T+1,n] ->
         (X, U, obj, gradient, adjoints, (A, B) or None, iteration).  Keyword names are those of
@@ -317,7 +317,8 @@ class Handle:
         it = torch.empty(B, device=dev, dtype=torch.int32)
         A = torch.empty(B, self.T, self.n, self.n, **f) if want_lqr else None
         Bm = torch.empty(B, self.T, self.n, self.m, **f) if want_lqr else None
-        opt = IlqrOptions(int(maxiter), float(grad_norm_threshold), float(alpha_0), float(alpha_min))
+        opt = IlqrOptions(int(maxiter), float(grad_norm_threshold), float(alpha_0), float(alpha_min),
+                          int(bool(gradient_lag)))
         _check(self.lib.gmpc_ilqr(
             self._h, B, _ptr(x0, device=dev, name="x0"), _ptr(U0, device=dev, name="U0"),
             _ptr(goal, device=dev, name="goal"), C.byref(opt), _ptr(X), _ptr(U), _ptr(obj),
@@ -325,7 +326,7 @@ class Handle:
         return X, U, obj, grad, lam, ((A, Bm) if want_lqr else None), it
 
     def ilqr_host(self, x0, U0, goal, maxiter=100, grad_norm_threshold=1e-4, alpha_0=1.0,
-                  alpha_min=0.00005):
+                  alpha_min=0.00005, gradient_lag=False):
         """gmpc_ilqr_host: HOST (cpu) tensors in and out, synchronous: (X, U, obj, gradient, adjoints,
         None, iteration)."""
         cpu = torch.device("cpu")
@@ -337,7 +338,8 @@ class Handle:
         grad = torch.empty(B, self.T, self.m, **f)
         lam = torch.empty(B, self.T + 1, self.n, **f)
         it = torch.empty(B, dtype=torch.int32)
-        opt = IlqrOptions(int(maxiter), float(grad_norm_threshold), float(alpha_0), float(alpha_min))
+        opt = IlqrOptions(int(maxiter), float(grad_norm_threshold), float(alpha_0), float(alpha_min),
+                          int(bool(gradient_lag)))
         _check(self.lib.gmpc_ilqr_host(
             self._h, B, _ptr(x0, device=cpu, name="x0"), _ptr(U0, device=cpu, name="U0"),
             _ptr(goal, device=cpu, name="goal"), C.byref(opt), _ptr(X), _ptr(U), _ptr(obj), _ptr(grad),
@@ -345,7 +347,7 @@ class Handle:
         return X, U, obj, grad, lam, None, it
 
     def bilevel_l2(self, x0, U0, goal, desired, maxiter=100, grad_norm_threshold=1e-4, alpha_0=1.0,
-                   alpha_min=0.00005, want_hessian=False, V=None, **unsupported):
+                   alpha_min=0.00005, want_hessian=False, V=None, gradient_lag=False, **unsupported):
         """bilevel_optimization (policy/optimizers.py:34-75) for the L2 loss, batched; see
         include/gmpc.h.  Returns a dict of X, U, obj, low_level_grad, iteration, loss, B, hessian,
         H, dxT, grad_mpc_weights."""
@@ -365,7 +367,8 @@ class Handle:
                  hessian=torch.empty(B, T * m, T * m, **f) if want_hessian else None,
                  H=torch.empty(B, T, m, **f), dxT=torch.empty(B, n, **f),
                  grad_mpc_weights=torch.empty(B, 3, **f))
-        opt = IlqrOptions(int(maxiter), float(grad_norm_threshold), float(alpha_0), float(alpha_min))
+        opt = IlqrOptions(int(maxiter), float(grad_norm_threshold), float(alpha_0), float(alpha_min),
+                          int(bool(gradient_lag)))
         _check(self.lib.gmpc_bilevel_l2(
             self._h, B, _ptr(x0, device=dev, name="x0"), _ptr(U0, device=dev, name="U0"),
             _ptr(goal, device=dev, name="goal"), _ptr(desired, device=dev, name="desired"), C.byref(opt),

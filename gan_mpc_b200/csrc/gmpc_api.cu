@@ -561,6 +561,7 @@ static int ilqr_launch(gmpc_handle* h, int64_t B, const float* x0, const float* 
   Q.gthr = opt->grad_norm_threshold;
   Q.alpha0 = opt->alpha_0;
   Q.alpha_min = opt->alpha_min;
+  Q.grad_lag = opt->gradient_lag ? 1 : 0;
   Q.it_out = iteration;
   Q.A_out = lqr_A;
   Q.B_out = lqr_B;
@@ -669,7 +670,7 @@ extern "C" int gmpc_bilevel_tail(gmpc_handle* h, int64_t B, const float* x0, con
   float* sX = (float*)h->d_scratch;
   float* sU = sX + (size_t)B * (c.T + 1) * c.n;
   float* sJ = sU + (size_t)B * c.T * c.m;
-  const gmpc_ilqr_options opt{0, 0.f, 1.f, 0.f};
+  const gmpc_ilqr_options opt{0, 0.f, 1.f, 0.f, 0};
   BilevelArgs bl{dLdX, nullptr, loss_grad_U, hessian, H, dxT, grad_mpc_weights, nullptr, 1};
   return ilqr_launch(h, B, x0, U, goal, &opt, sX, sU, sJ, nullptr, nullptr, nullptr, nullptr, nullptr,
                      &bl, stream);

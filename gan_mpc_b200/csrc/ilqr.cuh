@@ -34,6 +34,7 @@ struct IlqrParams {
   PlanParams pp;        // layer descriptors, sizes, x0 / U_in / goal, X_out / U_out / J_out / dU_out / lam_out
   int maxiter;
   float gthr, alpha0, alpha_min;
+  int grad_lag;         // gmpc_ilqr_options::gradient_lag: returned gradient / adjoints and the continuation test lag one iterate
   int* it_out;          // [B] iterations run per trajectory
   float* A_out;         // [B,T,n,n] nullable: dynamics Jacobians at the returned trajectory (lqr[5])
   float* B_out;         // [B,T,n,m] nullable (lqr[6])
@@ -57,7 +58,7 @@ struct IlqrParams {
 
 // per-CTA global scratch, every array is [..][RT]
 struct IlqrWs {
-  size_t X, Xn, G, lam, U, Un, k, grad, A, B, K, Jf, QT, qT, S, QS, H, rhs, total;
+  size_t X, Xn, G, lam, U, Un, k, grad, A, B, K, Jf, QT, qT, S, QS, H, rhs, lamP, gradP, gnP, total;
 };
 __host__ __device__ inline IlqrWs ilqr_ws_layout(int n, int m, int T, int fout, int bilevel) {
   IlqrWs s;
@@ -77,6 +78,9 @@ __host__ __device__ inline IlqrWs ilqr_ws_layout(int n, int m, int T, int fout, 
   s.Jf = o; o += (size_t)fout * n * RT;
   s.QT = o; o += (size_t)n * n * RT;
   s.qT = o; o += (size_t)n * RT;
+  s.lamP = o; o += sx;      // gradient_lag: adjoints / gradient / gradient norm of the iterate BEFORE the last step
+  s.gradP = o; o += su;
+  s.gnP = o; o += RT;
   s.S = s.QS = s.H = s.rhs = o;
   if (bilevel) {  // sensitivities d x_t / dU [n][Tm], Q S, the (Tm)^2 Hessian, the right-hand side
     const size_t TM = (size_t)T * m;
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
   float* wsb = Q.ws + (size_t)blockIdx.x * Q.ws_stride;
   float *wsX = wsb + WL.X, *wsXn = wsb + WL.Xn, *wsG = wsb + WL.G, *wsLam = wsb + WL.lam;
   float *wsU = wsb + WL.U, *wsUn = wsb + WL.Un, *wsk = wsb + WL.k, *wsGrad = wsb + WL.grad;
+  float *wsLamP = wsb + WL.lamP, *wsGradP = wsb + WL.gradP, *wsGnP = wsb + WL.gnP;
   float *wsA = wsb + WL.A, *wsB = wsb + WL.B, *wsK = wsb + WL.K, *wsJf = wsb + WL.Jf;
   float *wsQT = wsb + WL.QT, *wsqT = wsb + WL.qT;
   const int Ld = P.dir[DIR_DYN_F].L, Lc = P.dir[DIR_COST_F].L;
@@ -517,11 +522,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
       if (tid < RT) {  // trajax ilqr continuation_criterion, per lane
         float gn2 = 0.f;
         for (int k = 0; k < NTHREADS / 32; ++k) gn2 += gpart_s[k * RT + r];
-        const float gn = sqrtf(gn2);
+        const float gn = (gn2 != gn2) ? __int_as_float(0x7f800000) : sqrtf(gn2);   // trajax: NaN grad_norm -> inf (keeps iterating)
         if (!init && act_s[r]) it_s[r] += 1;
-        act_s[r] = (act_s[r] && it_s[r] < Q.maxiter && gn > Q.gthr && alpha_s[r] > Q.alpha_min) ? 1 : 0;
+        // gradient_lag: the test sees the gradient of the iterate BEFORE the step just taken (the initial one twice)
+        float gt = gn;
+        if (Q.grad_lag) {
+          if (init) wsGnP[r] = gn;
+          gt = wsGnP[r];
+        }
+        act_s[r] = (act_s[r] && it_s[r] < Q.maxiter && gt > Q.gthr && alpha_s[r] > Q.alpha_min) ? 1 : 0;
+        if (Q.grad_lag && act_s[r]) wsGnP[r] = gn;
       }
       const int any = __syncthreads_or(tid < RT && act_s[r]);
+      if (Q.grad_lag) {
+        // what a lane returns: the gradient / adjoints of its previous iterate -- they move on only for the lanes
+        // that go on iterating (all lanes after the initial linearisation)
+        for (int e = tid; e < T * m * RT; e += NTHREADS)
+          if (init || act_s[e & 31]) wsGradP[e] = wsGrad[e];
+        for (int e = tid; e < (T + 1) * n * RT; e += NTHREADS)
+          if (init || act_s[e & 31]) wsLamP[e] = wsLam[e];
+      }
       if (!any) break;
       ++n_outer;
 
@@ -965,8 +985,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ilqr_kernel(const __grid_constant
     }
     const bool bl = Q.desired != nullptr;
     const struct { float* dst; const float* src; int per; } outs[8] = {
-        {P.U_out, wsU, T * m},          {P.X_out, wsX, (T + 1) * n}, {P.dU_out, wsGrad, T * m},
-        {P.lam_out, wsLam, (T + 1) * n}, {Q.A_out, wsA, T * n * n},   {Q.B_out, wsB, T * n * m},
+        {P.U_out, wsU, T * m},          {P.X_out, wsX, (T + 1) * n}, {P.dU_out, Q.grad_lag ? wsGradP : wsGrad, T * m},
+        {P.lam_out, Q.grad_lag ? wsLamP : wsLam, (T + 1) * n}, {Q.A_out, wsA, T * n * n},   {Q.B_out, wsB, T * n * m},
         {bl ? Q.bl_B : nullptr, wsUn, T * m}, {bl ? Q.bl_H : nullptr, wsb + WL.rhs, T * m}};
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {

@@ -138,6 +138,12 @@ typedef struct gmpc_ilqr_options {
   float grad_norm_threshold;   /* 1e-4 */
   float alpha_0;               /* 1.0 */
   float alpha_min;             /* 0.00005 */
+  int32_t gradient_lag;        /* 0 (default): `gradient` / `adjoints` and the continuation test belong to the RETURNED
+                                * trajectory.  1: trajax's loop body as two independent recollections of the source have it
+                                * (`gradient, adjoints = adjoint(A, B, q, r)` with the lqr tuple unpacked BEFORE the step,
+                                * then `lqr = get_lqr_params(X, U)`): the returned gradient / adjoints and the
+                                * `grad_norm_threshold` test lag one iterate, so a converging solve runs one more
+                                * iteration.  trajax@c94a637 is not on disk, hence an option and not the default. */
 } gmpc_ilqr_options;
 
 /* The reference's OWN planner step: ilqr_solve (policy/optimizers.py:10-21) = trajax.optimizers.ilqr

@@ -170,28 +170,38 @@ def line_search_ddp(X, U, K, k, obj, goal_X, params, alpha_0, alpha_min, lanes):
 
 
 def ilqr(x0, U0, goal_X, params, maxiter=100, grad_norm_threshold=1e-4, alpha_0=1.0,
-         alpha_min=0.00005, **unused):
+         alpha_min=0.00005, gradient_lag=False, **unused):
     """trajax ilqr as called by policy/optimizers.py:19-21, batched (x0 [B,n], U0 [B,T,m],
     goal_X [B,T+1,n]).  Returns (X, U, obj, gradient, adjoints, lqr, iteration) like the 7-tuple
     unpacked at policy/optimizers.py:55; lqr = (Q, q, R, r, M, A, B) at the returned trajectory.
     The thresholds relative_grad_norm / obj_step / inputs_step are 0.0 in the reference
     (policy/eval.py:13-15): with strict comparisons they only stop a lane that made no progress,
-    which the alpha > alpha_min test already does."""
+    which the alpha > alpha_min test already does.
+
+    gradient_lag: trajax's loop body as recalled (source not on disk) unpacks the lqr
+    tuple BEFORE the step and calls `adjoint(A, B, q, r)` on it after the line search, before
+    `lqr = get_lqr_params(X, U)`: the returned gradient / adjoints and the grad_norm test then belong to the
+    iterate before the last step.  False (default) keeps them at the returned trajectory."""
     X, obj = pl.objective(x0, U0, goal_X, params)
     U = U0.clone()
     lqr = lqr_params(X, U, goal_X, params)
-    gradient, adjoints = adjoint(lqr[5], lqr[6], lqr[1], lqr[3])
+    gradient, adjoints = adjoint(lqr[5], lqr[6], lqr[1], lqr[3])   # at the current iterate
+    g_ret, a_ret = gradient, adjoints                                # what the loop carries when gradient_lag
     B = x0.shape[0]
     alpha = torch.full((B,), alpha_0, dtype=x0.dtype)
     iteration = torch.zeros(B, dtype=torch.int32)
 
     def cont():
-        gn = gradient.flatten(1).norm(dim=1)
+        gn = (g_ret if gradient_lag else gradient).flatten(1).norm(dim=1)
+        gn = torch.where(torch.isnan(gn), torch.full_like(gn, float("inf")), gn)   # trajax: a NaN gradient norm keeps iterating
         return (iteration < maxiter) & (gn > grad_norm_threshold) & (alpha > alpha_min)
 
     lanes = cont()
     while bool(lanes.any()):
         K, k = tvlqr(*lqr)
+        if gradient_lag:   # adjoint of the lqr tuple unpacked before the step = the gradient at the old iterate
+            g_ret = torch.where(lanes[:, None, None], gradient, g_ret)
+            a_ret = torch.where(lanes[:, None, None], adjoints, a_ret)
         X, U, obj_n, alpha_n = line_search_ddp(X, U, K, k, obj, goal_X, params, alpha_0, alpha_min, lanes)
         obj = torch.where(lanes, obj_n, obj)
         alpha = torch.where(lanes, alpha_n, alpha)
@@ -199,4 +209,6 @@ def ilqr(x0, U0, goal_X, params, maxiter=100, grad_norm_threshold=1e-4, alpha_0=
         gradient, adjoints = adjoint(lqr[5], lqr[6], lqr[1], lqr[3])
         iteration = iteration + lanes.to(torch.int32)
         lanes = lanes & cont()
+    if gradient_lag:
+        return X, U, obj, g_ret, a_ret, lqr, iteration
     return X, U, obj, gradient, adjoints, lqr, iteration

@@ -212,3 +212,46 @@ def test_ilqr_host_buffers_and_empty_batch(built_lib):
     assert o["H"].shape == (0, 5, 1)
     loss, act, cot = h.dynamics_fit(e(0, 4, 3), e(0, 4, 1), e(0, 4, 3), 0.9, True, [4, 200, 200, 200, 3])
     assert loss.shape == (0,) and act[0].shape == (4, 0)
+
+
+@pytest.mark.parametrize("cfg,B,maxiter", [(util.SMALL, 37, 1), (util.SMALL, 64, 3), (util.MID, 33, 2)])
+def test_ilqr_gradient_lag_option(cfg, B, maxiter, built_lib):
+    """gmpc_ilqr_options::gradient_lag -- trajax's loop body as recalled (`adjoint` on the lqr tuple unpacked before
+    the step): the returned gradient / adjoints are those of the iterate BEFORE the last step and the grad_norm test
+    lags with them; trajectory, objective and lqr are unchanged for lanes that stop on maxiter or alpha."""
+    h, op, x0, U0, goal = _setup(cfg, 43, B)
+    a = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=maxiter)
+    b = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=maxiter, gradient_lag=True)
+    o = oilqr.ilqr(util.tt(x0), util.tt(U0), util.tt(goal), op, maxiter=maxiter, gradient_lag=True)
+    # no lane converges on the gradient norm within these few iterations: same steps, same trajectories
+    assert torch.equal(a[6], b[6]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    same_it = (b[6].cpu() == o[6])
+    assert int(same_it.sum()) >= B - max(1, B // 16)
+    frac = 0.1 if maxiter == 1 else 0.2
+    util.assert_rows_close("gradient (lagging)", b[3], o[3], tol=TOL, outlier_frac=frac, cap=2.0)
+    util.assert_rows_close("adjoints (lagging)", b[4], o[4], tol=TOL, outlier_frac=frac, cap=2.0)
+    # with one iteration the lagging gradient is the gradient at U0 itself
+    if maxiter == 1:
+        g0 = h.ilqr(dev(x0), dev(U0), dev(goal), maxiter=0)[3]
+        moved = (b[6] == 1)
+        assert torch.equal(b[3][moved], g0[moved])
+
+
+def test_ilqr_gradient_lag_runs_one_more_iteration_on_convergence(built_lib):
+    """A problem iLQR solves (zero weights: linear dynamics x' = x, the staging cost alone): without the lag the loop
+    stops as soon as the gradient at the new iterate is below the threshold, with it one iteration later."""
+    cfg = util.SMALL
+    p, x0, U0, goal = util.case(cfg, 5, B=16)
+    for k in ("dyn_W", "cost_W"):
+        p[k] = [np.zeros_like(w) for w in p[k]]
+    h = util.make_handle(cfg, p)
+    U0s = (0.01 * U0[:, 0]).astype(np.float32)
+    a = h.ilqr(dev(x0), dev(U0s), dev(goal), maxiter=50, grad_norm_threshold=1e-3)
+    b = h.ilqr(dev(x0), dev(U0s), dev(goal), maxiter=50, grad_norm_threshold=1e-3, gradient_lag=True)
+    o = oilqr.ilqr(util.tt(x0), util.tt(U0s), util.tt(goal), util.to_oracle(p), maxiter=50, grad_norm_threshold=1e-3,
+                   gradient_lag=True)
+    print("iterations without / with lag / oracle with lag:", a[6].tolist(), b[6].tolist(), o[6].tolist())
+    conv = (a[6] < 50).cpu()
+    assert bool(conv.any())
+    assert bool((b[6].cpu()[conv] >= a[6].cpu()[conv]).all())
+    assert int((b[6].cpu() == o[6]).sum()) >= 14
