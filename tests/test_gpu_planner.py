@@ -381,3 +381,32 @@ def test_handles_of_different_shapes_coexist(path, built_lib):
         for h, x0, U0, goal, o in cases:
             Ub, Xb, Jb, idx, _ = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=3, lr=1e-2)
             assert util.rel_rows(Xb, o[1]) < TOL and util.rel_rows(Jb[:, None], o[2][:, None]) < TOL
+
+
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_t128_random_shapes_agree_with_fp32_kernel(seed, built_lib):
+    """Random model shapes (hidden widths 17..240 that are not multiples of 16, 2..5 dynamics layers, 1..4 cost layers,
+    n + m <= 32) and batches that span one to three tiles: the 128-trajectory kernel against the fp32 CUDA-core
+    kernel on the same inputs (plan, selection, objective gradient).  Exercises every N-part / round / narrow-layer
+    combination of the barrier protocol."""
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    n = int(rng.integers(1, 20)); m = int(rng.integers(1, min(12, 32 - n) + 1))
+    cfg = dict(n=n, m=m, T=int(rng.integers(1, 7)), dyn_layers=int(rng.integers(2, 6)),
+               dyn_hidden=int(rng.integers(17, 241)), cost_layers=int(rng.integers(1, 5)),
+               cost_hidden=int(rng.integers(17, 241)), cost_fout=int(rng.integers(1, 33)))
+    B = int(rng.integers(1, 140 if seed < 24 else 420)); K = int(rng.integers(1, 4))
+    p, x0, U0, goal = util.case(cfg, seed, B=B, K=K)
+    h = util.make_handle(cfg, p)
+    select_path(h, "t128")
+    a = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=2, lr=1e-2)
+    ga = h.objective_grad(dev(x0), dev(U0[:, 0]), dev(goal), want_lam=True)
+    h.set_path("ffma")
+    b = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=2, lr=1e-2)
+    gb = h.objective_grad(dev(x0), dev(U0[:, 0]), dev(goal), want_lam=True)
+    print(cfg, "B", B, "K", K)
+    assert util.rel_rows(ga[2], gb[2]) < TOL and util.rel_rows(ga[0][:, None], gb[0][:, None]) < TOL   # X, J
+    util.assert_rows_close("dU", ga[1], gb[1].double().cpu(), TOL, outlier_frac=0.1, cap=1.0)
+    util.assert_rows_close("J_all", a[4], b[4].double().cpu(), TOL, outlier_frac=0.1, cap=5e-2)
+    same = (a[3] == b[3])
+    assert int(same.sum()) >= B - max(1, B // 10)
+    util.assert_rows_close("X_best", a[1][same], b[1][same].double().cpu(), TOL, outlier_frac=0.1, cap=5e-2)
