@@ -383,12 +383,13 @@ def test_handles_of_different_shapes_coexist(path, built_lib):
             assert util.rel_rows(Xb, o[1]) < TOL and util.rel_rows(Jb[:, None], o[2][:, None]) < TOL
 
 
+@pytest.mark.parametrize("path", ["t128", "tc16s"])
 @pytest.mark.parametrize("seed", list(range(40)))
-def test_t128_random_shapes_agree_with_fp32_kernel(seed, built_lib):
+def test_random_shapes_agree_with_fp32_kernel(seed, path, built_lib):
     """Random model shapes (hidden widths 17..240 that are not multiples of 16, 2..5 dynamics layers, 1..4 cost layers,
-    n + m <= 32) and batches that span one to three tiles: the 128-trajectory kernel against the fp32 CUDA-core
-    kernel on the same inputs (plan, selection, objective gradient).  Exercises every N-part / round / narrow-layer
-    combination of the barrier protocol."""
+    n + m <= 32) and batches that span one to several tiles: both tensor-core kernels against the fp32 CUDA-core
+    kernel on the same inputs (plan, selection, objective gradient).  Exercises every round / narrow-layer / row-block
+    combination of their barrier protocols."""
     rng = np.random.Generator(np.random.PCG64(1000 + seed))
     n = int(rng.integers(1, 20)); m = int(rng.integers(1, min(12, 32 - n) + 1))
     cfg = dict(n=n, m=m, T=int(rng.integers(1, 7)), dyn_layers=int(rng.integers(2, 6)),
@@ -397,7 +398,7 @@ def test_t128_random_shapes_agree_with_fp32_kernel(seed, built_lib):
     B = int(rng.integers(1, 140 if seed < 24 else 420)); K = int(rng.integers(1, 4))
     p, x0, U0, goal = util.case(cfg, seed, B=B, K=K)
     h = util.make_handle(cfg, p)
-    select_path(h, "t128")
+    select_path(h, path)
     a = h.plan(dev(x0), dev(U0), dev(goal), method="adam", iters=2, lr=1e-2)
     ga = h.objective_grad(dev(x0), dev(U0[:, 0]), dev(goal), want_lam=True)
     h.set_path("ffma")
