@@ -788,7 +788,14 @@ extern "C" int gmpc_gemm_nt(gmpc_handle* h, int32_t M, int32_t N, int64_t R, con
   G.A = A; G.sam = R; G.sar = 1;
   G.B = B; G.sbr = 1; G.sbn = R;
   G.C = C; G.ldc = N; G.M = M; G.N = N; G.R = R; G.alpha = alpha; G.accumulate = accumulate;
-  CU_CHECK(small_gemm(G, SG_EPI_NONE, st));
+  float* part = nullptr;
+  if (const int sl = small_gemm_slices(M, N, R)) {   // long reduction, few output tiles: split it over the machine
+    int rc = grow(&h->d_vjp_ws, &h->vjp_ws_bytes, sizeof(float) * (size_t)sl * M * N);
+    if (rc) return rc;
+    part = (float*)h->d_vjp_ws;
+    ++h->launches;
+  }
+  CU_CHECK(small_gemm(G, SG_EPI_NONE, st, part));
   ++h->launches;
   if (rowsum_B) {
     strided_sum_kernel<<<(N + 7) / 8, 256, 0, st>>>(B, R, 1, N, R, alpha, rowsum_B);

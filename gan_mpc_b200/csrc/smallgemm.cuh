@@ -6,7 +6,8 @@
 //     weight gradients reduced over the batch.
 // These are a few hundred MFLOP per trainer step (plumbing next to the planner), so one deterministic tiled
 // kernel with generic strides and a fused epilogue serves all of them: 64 x 64 output tile per CTA, 4 x 4 per
-// thread, no split over the reduction (bitwise reproducible).
+// thread; a long reduction with few output tiles (dW of the dynamics fit) is cut into slices over gridDim.z whose
+// partial products are summed in slice order, so the result stays bitwise reproducible.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,6 +27,8 @@ struct SGemm {
   long long R;
   float alpha;
   int accumulate;   // C += alpha A B  instead of  C = alpha A B  (epilogue 0 only)
+  long long rslice; // > 0: blockIdx.z takes the reduction range [z rslice, (z + 1) rslice) and writes its raw partial
+  float* part;      //      product to part[z][M][ldc]; small_gemm_reduce_kernel sums the slices in a fixed order
 };
 
 template <int EPI>
@@ -39,7 +42,9 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const SGemm G) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (long long r0 = 0; r0 < G.R; r0 += TK) {
+  const long long rbeg = G.rslice > 0 ? (long long)blockIdx.z * G.rslice : 0;
+  const long long rend = G.rslice > 0 ? (rbeg + G.rslice < G.R ? rbeg + G.rslice : G.R) : G.R;
+  for (long long r0 = rbeg; r0 < rend; r0 += TK) {
     // 16 x 64 elements of each operand, 4 per thread; the faster-varying thread index follows the operand's
     // unit-stride dimension when it has one
     for (int e = tid; e < TK * TM; e += 256) {
@@ -47,14 +52,14 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const SGemm G) {
       if (G.sar == 1) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
       const long long r = r0 + kk;
       const int m = m0 + mm;
-      As[kk][mm] = (r < G.R && m < G.M) ? G.A[m * G.sam + r * G.sar] : 0.f;
+      As[kk][mm] = (r < rend && m < G.M) ? G.A[m * G.sam + r * G.sar] : 0.f;
     }
     for (int e = tid; e < TK * TN; e += 256) {
       int kk, nn;
       if (G.sbr == 1) { kk = e % TK; nn = e / TK; } else { nn = e % TN; kk = e / TN; }
       const long long r = r0 + kk;
       const int n = n0 + nn;
-      Bs[kk][nn] = (r < G.R && n < G.N) ? G.B[r * G.sbr + n * G.sbn] : 0.f;
+      Bs[kk][nn] = (r < rend && n < G.N) ? G.B[r * G.sbr + n * G.sbn] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -80,6 +85,10 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const SGemm G) {
       const int n = n0 + tx * 4 + j;
       if (n >= G.N) continue;
       const size_t ix = (size_t)m * G.ldc + n;
+      if (EPI == SG_EPI_NONE && G.rslice > 0) {   // one slice of a split reduction: the raw partial product
+        G.part[(size_t)blockIdx.z * G.M * G.ldc + ix] = acc[i][j];
+        continue;
+      }
       float v = G.alpha * acc[i][j];
       if (EPI == SG_EPI_NONE) {
         if (G.accumulate) v += G.C[ix];
@@ -98,8 +107,40 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const SGemm G) {
   }
 }
 
-inline cudaError_t small_gemm(const SGemm& G, int epi, cudaStream_t st) {
+// C = alpha * sum_z part[z] (+ C): the slices of a split reduction, summed in slice order (deterministic)
+__global__ void small_gemm_reduce_kernel(const float* __restrict__ part, int slices, long long count, float alpha,
+                                         int accumulate, float* __restrict__ C) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < slices; ++z) s += part[(size_t)z * count + i];
+    C[i] = accumulate ? fmaf(alpha, s, C[i]) : alpha * s;
+  }
+}
+
+// Slices a long reduction is cut into when the output has too few tiles to fill the machine (dW of the dynamics
+// fit: 200 x 200 outputs, thousands of columns): 0 = no split.
+inline int small_gemm_slices(int M, int N, long long R) {
+  const long long tiles = (long long)((M + 63) / 64) * ((N + 63) / 64);
+  if (R < 1024 || tiles >= 64) return 0;
+  long long s = R / 256;
+  if (s > 16) s = 16;
+  return s < 2 ? 0 : (int)s;
+}
+
+// `part`: workspace of small_gemm_slices(M, N, R) * M * ldc floats (epilogue NONE with ldc == N only), or nullptr.
+inline cudaError_t small_gemm(SGemm G, int epi, cudaStream_t st, float* part = nullptr) {
   if (G.M <= 0 || G.N <= 0) return cudaSuccess;
+  const int slices = (epi == SG_EPI_NONE && part != nullptr && G.ldc == G.N) ? small_gemm_slices(G.M, G.N, G.R) : 0;
+  if (slices > 0) {
+    G.rslice = ((G.R + slices - 1) / slices + 15) / 16 * 16;
+    G.part = part;
+    const dim3 grid3((G.N + 63) / 64, (G.M + 63) / 64, slices);
+    small_gemm_kernel<SG_EPI_NONE><<<grid3, 256, 0, st>>>(G);
+    const long long count = (long long)G.M * G.N;
+    small_gemm_reduce_kernel<<<(int)((count + 255) / 256), 256, 0, st>>>(part, slices, count, G.alpha, G.accumulate, G.C);
+    return cudaGetLastError();
+  }
+  G.rslice = 0;
   const dim3 grid((G.N + 63) / 64, (G.M + 63) / 64);
   switch (epi) {
     case SG_EPI_NONE: small_gemm_kernel<SG_EPI_NONE><<<grid, 256, 0, st>>>(G); break;

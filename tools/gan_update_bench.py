@@ -68,7 +68,7 @@ def main():
                                                           batch_size=128, discount_factor=0.9, teacher_forcing_factor=0.0,
                                                           key=0, id=1), reps=1)
     res["dynamics_train"] = dict(seconds=dt, minibatch_steps=D // 128, batch=128, window=S, steps_per_s=(D // 128) / dt,
-                                 includes="free-running windows: rollout + BPTT kernel, 4 cuBLAS GEMMs, clipped Adam per step")
+                                 includes="free-running windows: rollout + BPTT kernel, 4 gmpc_gemm_nt, clipped Adam per step")
     print(json.dumps(dict(workload=f"C3: GAN YAML dims n={n}, m={m}, T={T}, {D} trajectories", results=res)))
 
 
