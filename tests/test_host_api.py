@@ -171,3 +171,20 @@ def test_expert_network_layout_and_oracle():
     g3, _ = oexpert.propose(hx, fm, mlp._shapes(), 0, mlp.head_layers, 5)
     g4, _ = oexpert.propose(hx2, fm, mlp._shapes(), 0, mlp.head_layers, 5)
     assert torch.equal(g3, g4)          # the MLP cell has no carry besides x
+
+
+def test_bench_work_model_matches_the_survey_table():
+    """bench.py's algorithmic FLOPs and HBM bytes per planned state are SURVEY.md 8d's figures (true dims, 1 MAC =
+    2 FLOP, forward + input-adjoint backward): the numerator of every roofline fraction in the bench line."""
+    import importlib.util
+    from tests.conftest import ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from gan_mpc_b200 import synthetic
+    want_mflop = {"C2": 232.5, "C4": 12046.7, "C5": 572.8}
+    for name, mflop in want_mflop.items():
+        got = bench.flops_per_state(synthetic.CONFIGS[name]) / 1e6
+        assert abs(got - mflop) / mflop < 5e-4, (name, got)
+    assert bench.bytes_per_state(synthetic.CONFIGS["C2"]) == 6100     # 3 080 in + 3 020 out
+    assert bench.bytes_per_state(synthetic.CONFIGS["C4"]) > 22000
